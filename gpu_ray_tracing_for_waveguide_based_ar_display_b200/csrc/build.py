@@ -1,0 +1,74 @@
+"""Build libwgrt.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the tree).
+
+    python -m gpu_ray_tracing_for_waveguide_based_ar_display_b200.csrc.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+OUT = os.path.join(PKG, "libwgrt.so")
+OBJ_DIR = os.path.join(HERE, "build")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+# translation unit -> extra flags.  The strict walk must not contract multiply-adds: it is the
+# literal restatement that is compared with the CPU oracle.
+UNITS = {
+    "wgrt_strict.cu": ["-fmad=false"],
+    "wgrt_fast.cu": [],
+    "wgrt_api.cu": [],
+}
+HEADERS = ["wgrt_device.cuh", "wgrt_region.cuh", os.path.join("..", "..", "include", "wgrt.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _host_compiler_args():
+    # /opt/gcc wrappers in this image lack some spec files; the system g++ is complete.
+    for cand in ("/usr/bin/g++",):
+        if os.path.exists(cand):
+            return ["-ccbin", cand]
+    return []
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    for src, extra in UNITS.items():
+        s = os.path.join(HERE, src)
+        o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc, *ARCH, *COMMON, *_host_compiler_args(), *extra, "-c", s, "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd))
+            subprocess.run(cmd, check=True)
+    if force or _stale(OUT, objs):
+        cmd = [nvcc, *ARCH, "-shared", *_host_compiler_args(), "-o", OUT, *objs, "-lcudart"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

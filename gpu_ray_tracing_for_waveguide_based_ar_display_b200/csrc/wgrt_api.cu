@@ -1,0 +1,444 @@
+// wgrt_api.cu -- the C ABI of include/wgrt.h: validation, per-device workspace, launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "wgrt_device.cuh"
+
+namespace {
+
+using namespace wgrt;
+
+thread_local char g_err[512] = "no error";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t err__ = (expr);                                                             \
+    if (err__ != cudaSuccess)                                                               \
+      return fail(WGRT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+// ---- per-device workspace --------------------------------------------------------------------
+struct DeviceBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t want) {
+    if (want <= bytes) return cudaSuccess;
+    if (ptr) {
+      cudaError_t e = cudaFree(ptr);
+      ptr = nullptr;
+      bytes = 0;
+      if (e != cudaSuccess) return e;
+    }
+    size_t grown = want + want / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, grown);
+    if (e == cudaSuccess) bytes = grown;
+    return e;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+  }
+};
+
+struct Workspace {
+  int device = -1;
+  int num_sms = 0;
+  DeviceBuf cells[NUM_REGIONS], rowmask[NUM_REGIONS];
+  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | work counter + tile size | counters
+  DeviceBuf arena;   // staging for the host entry points
+  RegionDyn* dyn() { return static_cast<RegionDyn*>(small.ptr); }
+  int* work() { return reinterpret_cast<int*>(static_cast<char*>(small.ptr) + 512); }
+  unsigned long long* counters() {
+    return reinterpret_cast<unsigned long long*>(static_cast<char*>(small.ptr) + 1024);
+  }
+  void release() {
+    for (int r = 0; r < NUM_REGIONS; ++r) { cells[r].release(); rowmask[r].release(); }
+    small.release();
+    arena.release();
+  }
+};
+
+std::mutex g_mu;
+std::vector<Workspace> g_ws;
+
+int grid_resolution() {
+  static int res = [] {
+    const char* e = getenv("WGRT_GRID");
+    int v = e ? atoi(e) : 256;
+    if (v < 8) v = 8;
+    if (v > 4096) v = 4096;
+    return v;
+  }();
+  return res;
+}
+
+int get_workspace(Workspace** out) {
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(WGRT_ERR_NO_DEVICE, "cudaGetDevice: %s", cudaGetErrorString(e));
+  for (auto& w : g_ws)
+    if (w.device == dev) { *out = &w; return WGRT_OK; }
+  g_ws.reserve(64);
+  g_ws.emplace_back();
+  Workspace& w = g_ws.back();
+  w.device = dev;
+  CUDA_TRY(cudaDeviceGetAttribute(&w.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(w.small.reserve(2048));
+  CUDA_TRY(cudaMemset(w.small.ptr, 0, 2048));
+  *out = &w;
+  return WGRT_OK;
+}
+
+int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REGIONS],
+                  const int64_t* const offsets[NUM_REGIONS], const int64_t nverts[NUM_REGIONS],
+                  const int64_t npoly[NUM_REGIONS]) {
+  const int res = grid_resolution();
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    RegionStatic& st = rs.st[r];
+    if (nverts[r] > (1 << 24)) return fail(WGRT_ERR_UNSUPPORTED, "region %d: too many vertices", r);
+    st.verts = verts[r];
+    st.offsets = offsets[r];
+    st.nverts = static_cast<int>(nverts[r]);
+    st.npoly = static_cast<int>(npoly[r]);
+    st.nx = res;
+    st.ny = res;
+    st.words = (st.nverts + 31) / 32;
+    CUDA_TRY(w.cells[r].reserve(static_cast<size_t>(st.nx) * st.ny));
+    CUDA_TRY(w.rowmask[r].reserve(static_cast<size_t>(st.ny) * (st.words > 0 ? st.words : 1) * sizeof(uint32_t)));
+    st.cells = static_cast<uint8_t*>(w.cells[r].ptr);
+    st.rowmask = static_cast<uint32_t*>(w.rowmask[r].ptr);
+  }
+  rs.dyn = w.dyn();
+  return WGRT_OK;
+}
+
+int validate(const wgrt_problem_t* p) {
+  if (!p) return fail(WGRT_ERR_INVALID, "null problem");
+  if (p->num_rays < 0) return fail(WGRT_ERR_INVALID, "num_rays < 0");
+  if (p->L <= 0 || p->X <= 0 || p->Y <= 0 || p->EBx <= 0 || p->EBy <= 0)
+    return fail(WGRT_ERR_INVALID, "L, X, Y, EBy, EBx must be positive");
+  if (p->n_FC < 0 || p->n_OC < 0 || p->n_FC > 250 || p->n_OC > 250)
+    return fail(WGRT_ERR_INVALID, "n_FC / n_OC must be within [0, 250]");
+  if (p->C_ic < 41 || p->C_fc < 20 || p->C_oc < 41)
+    return fail(WGRT_ERR_INVALID, "LUT channel counts too small (need C_ic>=41, C_fc>=20, C_oc>=41)");
+  if (p->IC_n < 0 || p->FC_n < 0 || p->OC_n < 0 || p->eff_reg1_n < 0 || p->eff_reg2_n < 0)
+    return fail(WGRT_ERR_INVALID, "negative vertex count");
+#define NEED(f) \
+  if (!p->f) return fail(WGRT_ERR_INVALID, "null pointer: " #f)
+  NEED(x); NEED(y); NEED(m); NEED(n); NEED(lmd_num); NEED(te); NEED(tm); NEED(delta_phase); NEED(rng_states);
+  NEED(IC); NEED(FC); NEED(FC_offset); NEED(OC); NEED(OC_offset); NEED(eff_reg1); NEED(eff_reg2);
+  NEED(eff_reg_FOV); NEED(eff_reg_FOV_range); NEED(lut_ic1); NEED(lut_ic2); NEED(lut_ic3); NEED(lut_fc1);
+  NEED(lut_fc2); NEED(lut_oc1); NEED(lut_oc2); NEED(lut_TIR); NEED(lut_gap); NEED(matrix_EB);
+#undef NEED
+  return WGRT_OK;
+}
+
+int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
+  if (p.num_rays == 0) return WGRT_OK;
+  if (p.flags & WGRT_FLAG_STRICT) {
+    CUDA_TRY(launch_walk_strict(p, w.counters(), stream));
+    return WGRT_OK;
+  }
+  RegionSet rs;
+  const double* verts[NUM_REGIONS] = {p.IC, p.eff_reg1, p.eff_reg2, p.FC, p.OC};
+  const int64_t* offs[NUM_REGIONS] = {nullptr, nullptr, nullptr, p.FC_offset, p.OC_offset};
+  const int64_t nv[NUM_REGIONS] = {p.IC_n, p.eff_reg1_n, p.eff_reg2_n, p.FC_n, p.OC_n};
+  const int64_t np[NUM_REGIONS] = {1, 1, 1, p.n_FC, p.n_OC};
+  int rc = setup_regions(w, rs, verts, offs, nv, np);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(launch_region_build(rs, stream));
+  CUDA_TRY(launch_walk_fast(p, rs, w.work(), w.counters(), w.num_sms, stream));
+  return WGRT_OK;
+}
+
+// bump allocator over the workspace arena
+struct Arena {
+  char* base;
+  size_t cap, used = 0;
+  void* take(size_t bytes) {
+    size_t at = (used + 255) & ~size_t(255);
+    used = at + bytes;
+    return used <= cap ? base + at : nullptr;
+  }
+};
+size_t padded(size_t b) { return ((b + 255) & ~size_t(255)) + 256; }
+
+}  // namespace
+
+extern "C" {
+
+int wgrt_version(void) { return WGRT_VERSION; }
+
+const char* wgrt_last_error(void) { return g_err; }
+
+int wgrt_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(WGRT_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  return n;
+}
+
+int wgrt_release(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(WGRT_ERR_NO_DEVICE, "no CUDA device");
+  for (auto& w : g_ws)
+    if (w.device == dev) {
+      cudaDeviceSynchronize();
+      w.release();
+      w.device = -1;
+    }
+  return WGRT_OK;
+}
+
+int wgrt_trace_fullcolor(const wgrt_problem_t* p, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = validate(p);
+  if (rc != WGRT_OK) return rc;
+  Workspace* w = nullptr;
+  rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  return trace_device(*w, *p, static_cast<cudaStream_t>(stream));
+}
+
+int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* timings_ms) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = validate(hp);
+  if (rc != WGRT_OK) return rc;
+  if (num_iter < 0) return fail(WGRT_ERR_INVALID, "num_iter < 0");
+  for (int s = 0; s < 2; ++s) {
+    const int64_t* off = s ? hp->OC_offset : hp->FC_offset;
+    const int64_t np = s ? hp->n_OC : hp->n_FC, nv = s ? hp->OC_n : hp->FC_n;
+    if (off[0] != 0 || off[np] > nv) return fail(WGRT_ERR_INVALID, "polygon offsets out of range");
+    for (int64_t k = 0; k < np; ++k)
+      if (off[k + 1] < off[k]) return fail(WGRT_ERR_INVALID, "polygon offsets must be non-decreasing");
+  }
+  Workspace* w = nullptr;
+  rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+
+  const size_t N = static_cast<size_t>(hp->num_rays);
+  const size_t cells = static_cast<size_t>(hp->L * hp->X * hp->Y), fov = static_cast<size_t>(hp->X * hp->Y);
+  const size_t eb_elems = cells * static_cast<size_t>(hp->EBy * hp->EBx);
+  struct Item { const void* src; void** dst; size_t bytes; };
+  wgrt_problem_t dp = *hp;
+  dp.gap_x = dp.gap_y = dp.pol = dp.azi = nullptr;  // never read by the walk
+  std::vector<Item> in = {
+      {hp->x, (void**)&dp.x, N * 4}, {hp->y, (void**)&dp.y, N * 4}, {hp->m, (void**)&dp.m, N * 4},
+      {hp->n, (void**)&dp.n, N * 4}, {hp->lmd_num, (void**)&dp.lmd_num, N * 4}, {hp->te, (void**)&dp.te, N * 4},
+      {hp->tm, (void**)&dp.tm, N * 4}, {hp->delta_phase, (void**)&dp.delta_phase, N * 4},
+      {hp->rng_states, (void**)&dp.rng_states, N * 4},
+      {hp->IC, (void**)&dp.IC, (size_t)hp->IC_n * 16}, {hp->FC, (void**)&dp.FC, (size_t)hp->FC_n * 16},
+      {hp->FC_offset, (void**)&dp.FC_offset, (size_t)(hp->n_FC + 1) * 8},
+      {hp->OC, (void**)&dp.OC, (size_t)hp->OC_n * 16},
+      {hp->OC_offset, (void**)&dp.OC_offset, (size_t)(hp->n_OC + 1) * 8},
+      {hp->eff_reg1, (void**)&dp.eff_reg1, (size_t)hp->eff_reg1_n * 16},
+      {hp->eff_reg2, (void**)&dp.eff_reg2, (size_t)hp->eff_reg2_n * 16},
+      {hp->eff_reg_FOV, (void**)&dp.eff_reg_FOV, fov * 64},
+      {hp->eff_reg_FOV_range, (void**)&dp.eff_reg_FOV_range, fov * 32},
+      {hp->lut_ic1, (void**)&dp.lut_ic1, cells * hp->C_ic * 16}, {hp->lut_ic2, (void**)&dp.lut_ic2, cells * hp->C_ic * 16},
+      {hp->lut_ic3, (void**)&dp.lut_ic3, cells * hp->C_ic * 16},
+      {hp->lut_fc1, (void**)&dp.lut_fc1, cells * hp->n_FC * hp->C_fc * 16},
+      {hp->lut_fc2, (void**)&dp.lut_fc2, cells * hp->n_FC * hp->C_fc * 16},
+      {hp->lut_oc1, (void**)&dp.lut_oc1, cells * hp->n_OC * hp->C_oc * 16},
+      {hp->lut_oc2, (void**)&dp.lut_oc2, cells * hp->n_OC * hp->C_oc * 16},
+      {hp->lut_TIR, (void**)&dp.lut_TIR, cells * 32}, {hp->lut_gap, (void**)&dp.lut_gap, cells * 64},
+      {hp->matrix_EB, (void**)&dp.matrix_EB, eb_elems * 4},
+  };
+  size_t total = 0;
+  for (auto& it : in) total += padded(it.bytes);
+  CUDA_TRY(w->arena.reserve(total));
+  Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[4];
+  for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
+  CUDA_TRY(cudaEventRecord(ev[0], st));
+  for (auto& it : in) {
+    *it.dst = ar.take(it.bytes);
+    if (!*it.dst) return fail(WGRT_ERR_CUDA, "arena overflow");
+    if (it.bytes) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaEventRecord(ev[1], st));
+  for (int k = 0; k < num_iter; ++k) {
+    rc = trace_device(*w, dp, st);
+    if (rc != WGRT_OK) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(ev[2], st));
+  if (N) CUDA_TRY(cudaMemcpyAsync(hp->rng_states, dp.rng_states, N * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(hp->matrix_EB, dp.matrix_EB, eb_elems * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(ev[3], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (timings_ms)
+    for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventElapsedTime(&timings_ms[k], ev[k], ev[k + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return WGRT_OK;
+}
+
+int wgrt_counters_read(uint64_t* out, int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out || n < 0) return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  if (n > WGRT_NUM_COUNTERS) n = WGRT_NUM_COUNTERS;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, w->counters(), sizeof(uint64_t) * n, cudaMemcpyDeviceToHost));
+  return WGRT_OK;
+}
+
+int wgrt_counters_reset(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemset(w->counters(), 0, sizeof(uint64_t) * WGRT_NUM_COUNTERS));
+  return WGRT_OK;
+}
+
+int wgrt_debug_locate(const double* verts, int64_t n_verts, const int64_t* offsets, int64_t n_polys,
+                      const double* px, const double* py, int64_t n_points, int32_t* out, int mode) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!verts || !offsets || !px || !py || !out || n_verts < 0 || n_polys < 0 || n_polys > 250 || n_points < 0)
+    return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  const size_t vb = (size_t)n_verts * 16, ob = (size_t)(n_polys + 1) * 8, pb = (size_t)n_points * 8;
+  CUDA_TRY(w->arena.reserve(padded(vb) + padded(ob) + 2 * padded(pb) + padded((size_t)n_points * 4)));
+  Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+  double* d_v = static_cast<double*>(ar.take(vb));
+  int64_t* d_o = static_cast<int64_t*>(ar.take(ob));
+  double* d_x = static_cast<double*>(ar.take(pb));
+  double* d_y = static_cast<double*>(ar.take(pb));
+  int32_t* d_out = static_cast<int32_t*>(ar.take((size_t)n_points * 4));
+  if (vb) CUDA_TRY(cudaMemcpy(d_v, verts, vb, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_o, offsets, ob, cudaMemcpyHostToDevice));
+  if (pb) {
+    CUDA_TRY(cudaMemcpy(d_x, px, pb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_y, py, pb, cudaMemcpyHostToDevice));
+  }
+  if (mode == 0) {
+    CUDA_TRY(launch_debug_locate_literal(d_v, d_o, n_polys, d_x, d_y, n_points, d_out, nullptr));
+  } else {
+    RegionSet rs;
+    const double* vs[NUM_REGIONS] = {d_v, d_v, d_v, d_v, d_v};
+    const int64_t* os[NUM_REGIONS] = {d_o, d_o, d_o, d_o, d_o};
+    const int64_t nv[NUM_REGIONS] = {0, 0, 0, n_verts, 0};
+    const int64_t np[NUM_REGIONS] = {0, 0, 0, n_polys, 0};
+    rc = setup_regions(*w, rs, vs, os, nv, np);
+    if (rc != WGRT_OK) return rc;
+    CUDA_TRY(launch_region_build(rs, nullptr));
+    CUDA_TRY(launch_debug_locate_grid(rs, REG_FC, d_x, d_y, n_points, d_out, w->counters(), nullptr));
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (n_points) CUDA_TRY(cudaMemcpy(out, d_out, (size_t)n_points * 4, cudaMemcpyDeviceToHost));
+  return WGRT_OK;
+}
+
+int wgrt_debug_efield(const double* ete, const double* etm, const double* delta, const double* jones,
+                      int64_t n, double* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!ete || !etm || !delta || !jones || !out || n < 0) return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  const size_t b = (size_t)n * 8;
+  CUDA_TRY(w->arena.reserve(3 * padded(b) + padded(8 * b) + padded(3 * b)));
+  Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+  double* d_te = static_cast<double*>(ar.take(b));
+  double* d_tm = static_cast<double*>(ar.take(b));
+  double* d_dl = static_cast<double*>(ar.take(b));
+  double* d_j = static_cast<double*>(ar.take(8 * b));
+  double* d_o = static_cast<double*>(ar.take(3 * b));
+  if (n) {
+    CUDA_TRY(cudaMemcpy(d_te, ete, b, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_tm, etm, b, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_dl, delta, b, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_j, jones, 8 * b, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(launch_debug_efield(d_te, d_tm, d_dl, d_j, n, d_o, nullptr));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (n) CUDA_TRY(cudaMemcpy(out, d_o, 3 * b, cudaMemcpyDeviceToHost));
+  return WGRT_OK;
+}
+
+int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!states || n < 0 || draws < 0) return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(w->arena.reserve(padded((size_t)n * 4) + padded((size_t)n * 8)));
+  Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+  uint32_t* d_s = static_cast<uint32_t*>(ar.take((size_t)n * 4));
+  double* d_u = static_cast<double*>(ar.take((size_t)n * 8));
+  if (n) CUDA_TRY(cudaMemcpy(d_s, states, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(launch_debug_xorshift(d_s, n, draws, d_u, nullptr));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (n) {
+    CUDA_TRY(cudaMemcpy(states, d_s, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (out_last) CUDA_TRY(cudaMemcpy(out_last, d_u, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  }
+  return WGRT_OK;
+}
+
+int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
+                         int mask_size, int step_y, int step_x, float* dev_out, float* dev_cell_sums,
+                         void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!dev_EB || L < 0 || Yf < 0 || Xf < 0 || EBy <= 0 || EBx <= 0 || mask_size <= 0 || step_y <= 0 || step_x <= 0)
+    return fail(WGRT_ERR_INVALID, "bad arguments");
+  if ((size_t)(EBy * EBx) * 4 > 200 * 1024)
+    return fail(WGRT_ERR_UNSUPPORTED, "eyebox tile larger than 200 KB of shared memory");
+  CUDA_TRY(launch_pupil_sums(dev_EB, L, Yf, Xf, EBy, EBx, mask_size, step_y, step_x, dev_out, dev_cell_sums,
+                             static_cast<cudaStream_t>(stream)));
+  return WGRT_OK;
+}
+
+int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
+                              int mask_size, int step_y, int step_x, float* out, float* cell_sums) {
+  if (!EB || EBy <= 0 || EBx <= 0 || mask_size <= 0 || step_y <= 0 || step_x <= 0)
+    return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  size_t tiles, n_out, eb_b;
+  float *d_eb, *d_out, *d_cs;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int rc = get_workspace(&w);
+    if (rc != WGRT_OK) return rc;
+    tiles = (size_t)(L * Yf * Xf);
+    const size_t n_epy = EBy >= mask_size ? (size_t)((EBy - mask_size) / step_y + 1) : 0;
+    const size_t n_epx = EBx >= mask_size ? (size_t)((EBx - mask_size) / step_x + 1) : 0;
+    n_out = tiles * n_epy * n_epx;
+    eb_b = tiles * (size_t)(EBy * EBx) * 4;
+    CUDA_TRY(w->arena.reserve(padded(eb_b) + padded(n_out * 4) + padded(tiles * 4)));
+    Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+    d_eb = static_cast<float*>(ar.take(eb_b));
+    d_out = static_cast<float*>(ar.take(n_out * 4));
+    d_cs = static_cast<float*>(ar.take(tiles * 4));
+    if (eb_b) CUDA_TRY(cudaMemcpy(d_eb, EB, eb_b, cudaMemcpyHostToDevice));
+  }
+  int rc = wgrt_eval_pupil_sums(d_eb, L, Yf, Xf, EBy, EBx, mask_size, step_y, step_x, d_out, d_cs, nullptr);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (out && n_out) CUDA_TRY(cudaMemcpy(out, d_out, n_out * 4, cudaMemcpyDeviceToHost));
+  if (cell_sums && tiles) CUDA_TRY(cudaMemcpy(cell_sums, d_cs, tiles * 4, cudaMemcpyDeviceToHost));
+  return WGRT_OK;
+}
+
+}  // extern "C"

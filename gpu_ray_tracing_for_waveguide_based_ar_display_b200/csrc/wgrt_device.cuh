@@ -1,0 +1,176 @@
+// wgrt_device.cuh -- device helpers shared by the strict walk, the fast walk and the unit hooks.
+//
+// "literal" functions evaluate exactly the expressions of the reference device functions
+// (GPU_ray_tracing_functions.py, GRTF below) in the same order; translation units that must
+// stay comparable with the CPU oracle are compiled with -fmad=false.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/wgrt.h"
+
+namespace wgrt {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+struct cplx {
+  double re, im;
+};
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+  return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
+
+// GRTF:25-34 with the state kept in a register.
+__device__ __forceinline__ double xorshift_draw(uint32_t& s, int64_t index) {
+  if (s == 0u) s = 0x6D2B79F5u ^ static_cast<uint32_t>(index + 1);
+  s ^= s << 13;
+  s ^= s >> 17;
+  s ^= s << 5;
+  return static_cast<double>(s) * (1.0 / 4294967296.0);
+}
+
+// Per-thread event counts, flushed once per thread with warp-aggregated atomics.
+struct Counts {
+  unsigned long long c[WGRT_NUM_COUNTERS];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int k = 0; k < WGRT_NUM_COUNTERS; ++k) c[k] = 0ull;
+  }
+  __device__ __forceinline__ void flush(unsigned long long* global) {
+#pragma unroll
+    for (int k = 0; k < WGRT_NUM_COUNTERS; ++k) {
+      unsigned long long v = c[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+      if ((threadIdx.x & 31) == 0 && v) atomicAdd(global + k, v);
+    }
+  }
+};
+
+// GRTF:52-61
+template <bool COUNT>
+__device__ __forceinline__ bool on_segment_literal(double px, double py, double x1, double y1, double x2,
+                                                   double y2, double tol, Counts* cn) {
+  if ((px < fmin(x1, x2) - tol) || (px > fmax(x1, x2) + tol) || (py < fmin(y1, y2) - tol) ||
+      (py > fmax(y1, y2) + tol))
+    return false;
+  if (COUNT) cn->c[WGRT_CNT_CROSS]++;
+  return fabs((x2 - x1) * (py - y1) - (y2 - y1) * (px - x1)) <= tol;
+}
+
+// GRTF:63-71 then GRTF:36-50 over ring [start, end) of a [V,2] vertex array.
+template <bool COUNT>
+__device__ __noinline__ bool inside_or_on_edge_literal(double px, double py, const double* __restrict__ poly,
+                                                       int64_t start, int64_t end, Counts* cn) {
+  const int64_t nv = end - start;
+  if (COUNT) cn->c[WGRT_CNT_POLY_TESTS]++;
+  int64_t j = nv - 1;
+  for (int64_t i = 0; i < nv; ++i) {
+    const double2 a = *reinterpret_cast<const double2*>(poly + 2 * (start + j));
+    const double2 b = *reinterpret_cast<const double2*>(poly + 2 * (start + i));
+    if (COUNT) cn->c[WGRT_CNT_EDGE_VISITS]++;
+    if (on_segment_literal<COUNT>(px, py, a.x, a.y, b.x, b.y, 1e-12, cn)) return true;
+    j = i;
+  }
+  bool inside = false;
+  j = nv - 1;
+  for (int64_t i = 0; i < nv; ++i) {
+    const double2 vi = *reinterpret_cast<const double2*>(poly + 2 * (start + i));
+    const double2 vj = *reinterpret_cast<const double2*>(poly + 2 * (start + j));
+    if (COUNT) cn->c[WGRT_CNT_EDGE_VISITS]++;
+    if ((vi.y > py) != (vj.y > py)) {
+      if (COUNT) cn->c[WGRT_CNT_STRADDLE]++;
+      if (px < (vj.x - vi.x) * (py - vi.y) / (vj.y - vi.y + 1e-20) + vi.x) inside = !inside;
+    }
+    j = i;
+  }
+  return inside;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ int first_hit_literal(double x, double y, const double* __restrict__ poly,
+                                                 const int64_t* __restrict__ off, int64_t npoly, Counts* cn) {
+  for (int64_t i = 0; i < npoly; ++i)
+    if (inside_or_on_edge_literal<COUNT>(x, y, poly, off[i], off[i + 1], cn)) return static_cast<int>(i);
+  return -1;
+}
+
+// GRTF:124-130
+__device__ __forceinline__ double wrap_pi_literal(double x) {
+  const double pi = 3.141592653589793;
+  const double two_pi = 2.0 * pi;
+  x = x + pi;
+  x = x - two_pi * floor(x / two_pi);
+  x = x - pi;
+  return x;
+}
+
+// GRTF:132-152; q in CALL order (E_te_te, E_te_tm, E_tm_te, E_tm_tm)
+__device__ __forceinline__ void efield_literal(double Ete_abs, double Etm_abs, double delta, const cplx q[4],
+                                               double& o_te, double& o_tm, double& o_delta) {
+  double sn, cs;
+  sincos(delta, &sn, &cs);
+  const cplx phase{cs, sn};
+  const cplx te_in{Ete_abs, 0.0};
+  const cplx tm_in = cmul(phase, cplx{Etm_abs, 0.0});
+  const cplx a = q[0], b = q[2], c = q[1], d = q[3];
+  const cplx Ete_out = cadd(cmul(a, te_in), cmul(b, tm_in));
+  const cplx Etm_out = cadd(cmul(c, te_in), cmul(d, tm_in));
+  o_te = hypot(Ete_out.re, Ete_out.im);
+  o_tm = hypot(Etm_out.re, Etm_out.im);
+  const double eps = 1e-20;
+  const double phi_te = o_te >= eps ? atan2(Ete_out.im, Ete_out.re) : 0.0;
+  const double phi_tm = o_tm >= eps ? atan2(Etm_out.im, Etm_out.re) : 0.0;
+  o_delta = wrap_pi_literal(phi_tm - phi_te);
+}
+
+// GRTF:154-165 with the wavelength slice of GRTF:1168.  Deposits are all 1.0f, so float32
+// accumulation is exact and order independent (counts stay far below 2^24).
+__device__ __forceinline__ void deposit_bin(const wgrt_problem_t& p, int64_t lm, int64_t m, int64_t n, double x,
+                                            double y, double xmin, double xmax, double ymin, double ymax) {
+  const double dx = (xmax - xmin) / static_cast<double>(p.EBx);
+  const double dy = (ymax - ymin) / static_cast<double>(p.EBy);
+  const int64_t ix = static_cast<int64_t>(floor((x - xmin) / dx));
+  const int64_t iy = static_cast<int64_t>(floor((y - ymin) / dy));
+  const int64_t flat = (((lm * p.Y + n) * p.X + m) * p.EBy + iy) * p.EBx + ix;
+  const int64_t total = p.L * p.Y * p.X * p.EBy * p.EBx;
+  if (flat >= 0 && flat < total) atomicAdd(p.matrix_EB + flat, 1.0f);
+}
+
+// ---- launch plumbing shared by the translation units (defined in wgrt_api.cu / per TU) -------
+struct RegionStatic {          // host-known part of one region set
+  const double* verts;         // [V,2]
+  const int64_t* offsets;      // [npoly+1]; nullptr = one ring [0, nverts)
+  uint8_t* cells;              // [ny*nx] cell codes
+  uint32_t* rowmask;           // [ny][words] edges relevant to each cell row
+  int nverts, npoly, nx, ny, words;
+};
+struct RegionDyn {             // computed on the device from the vertex data
+  double x0, y0, inv_dx, inv_dy, cell_dx, cell_dy;
+};
+enum { REG_IC = 0, REG_R1, REG_R2, REG_FC, REG_OC, NUM_REGIONS };
+constexpr uint8_t CELL_NONE = 255, CELL_AMBIG = 254;
+
+struct RegionSet {
+  RegionStatic st[NUM_REGIONS];
+  RegionDyn* dyn;              // device array [NUM_REGIONS]
+};
+
+cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* counters, cudaStream_t s);
+cudaError_t launch_region_build(const RegionSet& rs, cudaStream_t s);
+cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
+                             unsigned long long* counters, int num_sms, cudaStream_t s);
+cudaError_t launch_debug_locate_literal(const double* verts, const int64_t* off, int64_t npoly, const double* px,
+                                        const double* py, int64_t n, int32_t* out, cudaStream_t s);
+cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const double* px, const double* py, int64_t n,
+                                     int32_t* out, unsigned long long* counters, cudaStream_t s);
+cudaError_t launch_debug_efield(const double* ete, const double* etm, const double* delta, const double* jones,
+                                int64_t n, double* out, cudaStream_t s);
+cudaError_t launch_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last, cudaStream_t s);
+cudaError_t launch_pupil_sums(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
+                              int mask, int step_y, int step_x, float* out, float* cell_sums, cudaStream_t s);
+
+}  // namespace wgrt

@@ -1,0 +1,678 @@
+// wgrt_fast.cu -- the production ray walk for sm_100a and the region-index builder.
+//
+// Same Monte-Carlo walk as process_rays_kernel_pro_fullColor (GRTF:833-1246), re-designed:
+//
+//  * work = tiles of consecutive rays; persistent CTAs pull tiles from a global counter.  Inside a
+//    tile, maximal runs of rays that share one (FoV-x, FoV-y, wavelength) cell are walked together
+//    (the runner lays rays out cell by cell, gpu_ray_tracing_pro_fullColor.py:82-115).
+//  * per run, the CTA gathers everything the cell needs into shared memory ONCE: for every event
+//    (in-coupling, the two in-coupler states, fold-coupler slice i x 2 states, out-coupler slice i
+//    x 2 states) and every diffraction order the Jones quartet, the cos-ratio factor, the new
+//    direction's 1/cos, and which TIR phase / bounce vector / next state the order leads to.  The
+//    walk itself is then table driven and identical for all states: no per-state code paths, no
+//    global LUT gathers, no transcendental in the loop.
+//  * the polarisation state is carried as the Jones vector (a, w) = (|E_te|, |E_tm| e^{i delta})
+//    instead of (|E_te|, |E_tm|, delta): E_field_cal's cos/sin/hypot/atan2 (GRTF:136-150) and the
+//    TIR phase additions become complex multiplies by per-cell phasors e^{iT}, e^{2iT}.  This is
+//    algebraically the same map; results differ from the literal evaluation by a few ulp, i.e. a
+//    decision `u <= efficiency` can flip only if u lands within ~1e-15 of the threshold.
+//  * point-in-region tests go through the cell grids of wgrt_region.cuh (exactly equivalent).
+//  * lanes whose ray terminated are refilled from the run's queue with a warp-aggregated
+//    (ballot + popc prefix) fetch, so warps stay full although path lengths are heavy tailed.
+//  * per-ray RNG state lives in a register and is stored once; bins get one red.global.add.f32.
+#include "wgrt_region.cuh"
+
+namespace wgrt {
+
+namespace {
+
+constexpr int WALK_THREADS = 128;
+constexpr int ENTRY_DOUBLES = 12;  // 8 Jones + factor + inv_cos_new + meta + spare
+constexpr int ST_INIT = 6;
+constexpr int ST_DEAD = -1;
+enum { POST_NONE = 0, POST_IC_FWD = 1, POST_IC_BACK = 2, POST_DEPOSIT = 3 };
+enum { EV_INIT = 0, EV_S0, EV_S1, EV_S2, EV_S3, EV_S4, EV_S5, NUM_EV };
+enum { DIR_IC1 = 0, DIR_IC2, DIR_IC3, DIR_FC1, DIR_FC2, DIR_OC1, DIR_OC2 };
+
+struct OrderSpec {
+  int8_t ch[4];   // LUT channels in E_field_cal CALL order (E_te_te, E_te_tm, E_tm_te, E_tm_tm)
+  int8_t dir;     // whose channel 0 gives the outgoing polar angle (numerator cosine)
+  int8_t tir;     // lut_TIR index added to the phase
+  int8_t gap;     // lut_gap pair index of the new bounce vector
+  int8_t nstate;  // region state after the order is taken
+  int8_t post;    // what happens after the move
+  int8_t fmode;   // 0: cos ratio, 1: * n_g (air -> glass), 2: / n_g (glass -> air)
+};
+
+// Transcribed from the kernel's call sites: INIT GRTF:860-904, state 0 GRTF:908-953, state 1
+// GRTF:954-999 (note the swapped te_tm/tm_te channels at GRTF:957-958), state 2 GRTF:1000-1052,
+// state 3 GRTF:1053-1108, state 4 GRTF:1110-1178, state 5 GRTF:1179-1246.
+__constant__ OrderSpec kOrders[NUM_EV][3] = {
+    /* INIT */ {{{13, 18, 33, 38}, DIR_IC2, 0, 0, 0, POST_IC_FWD, 1},
+                {{15, 20, 35, 40}, DIR_IC3, 2, 2, 1, POST_IC_BACK, 1},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S0   */ {{{4, 9, 24, 29}, DIR_IC2, 0, 0, 0, POST_IC_FWD, 0},
+                {{6, 11, 26, 31}, DIR_IC3, 2, 2, 1, POST_IC_BACK, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S1   */ {{{2, 22, 7, 27}, DIR_IC2, 0, 0, 0, POST_IC_FWD, 0},
+                {{4, 9, 24, 29}, DIR_IC3, 2, 2, 1, POST_IC_BACK, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S2   */ {{{3, 6, 15, 18}, DIR_FC1, 0, 0, 2, POST_NONE, 0},
+                {{2, 5, 14, 17}, DIR_FC2, 1, 1, 3, POST_NONE, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S3   */ {{{4, 7, 16, 19}, DIR_FC1, 0, 0, 2, POST_NONE, 0},
+                {{3, 6, 15, 18}, DIR_FC2, 1, 1, 3, POST_NONE, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S4   */ {{{4, 9, 24, 29}, DIR_OC1, 1, 1, 4, POST_NONE, 0},
+                {{2, 7, 22, 27}, DIR_OC2, 3, 3, 5, POST_NONE, 0},
+                {{13, 18, 33, 38}, DIR_IC1, 0, 0, 0, POST_DEPOSIT, 2}},
+    /* S5   */ {{{6, 11, 26, 31}, DIR_OC1, 1, 1, 4, POST_NONE, 0},
+                {{4, 9, 24, 29}, DIR_OC2, 3, 3, 5, POST_NONE, 0},
+                {{15, 20, 35, 40}, DIR_IC1, 0, 0, 0, POST_DEPOSIT, 2}},
+};
+
+struct alignas(16) CellConst {
+  cplx ph1[4];      // e^{i T[k]}
+  cplx ph2[4];      // e^{i 2 T[k]}
+  double gap[8];    // lut_gap[lm, m, n, :]
+  double rect[8];   // eff_reg_FOV[m, n, :, :]
+  double range[4];  // eff_reg_FOV_range[m, n, :]
+  double inv_cos_in;
+  int rowbase[8];   // first table row of each region state (index ST_INIT = in-coupling)
+};
+
+struct WalkShared {
+  Region reg[NUM_REGIONS];
+  CellConst cc;
+  int tile;        // current tile index
+  int run_end;     // end of the current run (ray index, exclusive)
+  int q_next;      // next unclaimed ray of the run
+};
+
+__device__ __forceinline__ const double* lut_slice(const wgrt_problem_t& p, int which, int i, int64_t cell,
+                                                   int64_t cells_per_poly, int32_t& C) {
+  switch (which) {
+    case DIR_IC1: C = p.C_ic; return p.lut_ic1 + 2 * cell * C;
+    case DIR_IC2: C = p.C_ic; return p.lut_ic2 + 2 * cell * C;
+    case DIR_IC3: C = p.C_ic; return p.lut_ic3 + 2 * cell * C;
+    case DIR_FC1: C = p.C_fc; return p.lut_fc1 + 2 * (i * cells_per_poly + cell) * C;
+    case DIR_FC2: C = p.C_fc; return p.lut_fc2 + 2 * (i * cells_per_poly + cell) * C;
+    case DIR_OC1: C = p.C_oc; return p.lut_oc1 + 2 * (i * cells_per_poly + cell) * C;
+    default: C = p.C_oc; return p.lut_oc2 + 2 * (i * cells_per_poly + cell) * C;
+  }
+}
+
+// Fill the event table and the per-cell constants for cell (lm, m, n).  All threads participate.
+__device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m, int64_t n, double* tab,
+                                  CellConst& cc, int rows) {
+  const int64_t cell = (lm * p.X + m) * p.Y + n;
+  const int64_t cpp = p.L * p.X * p.Y;
+  const int nFC = static_cast<int>(p.n_FC), nOC = static_cast<int>(p.n_OC);
+  for (int t = threadIdx.x; t < rows; t += blockDim.x) {
+    int ev, i, k;
+    if (t < 6) {
+      ev = t >> 1; i = 0; k = t & 1;
+    } else if (t < 6 + 4 * nFC) {
+      const int u = t - 6;
+      ev = u < 2 * nFC ? EV_S2 : EV_S3;
+      const int v = u < 2 * nFC ? u : u - 2 * nFC;
+      i = v >> 1; k = v & 1;
+    } else {
+      const int u = t - 6 - 4 * nFC;
+      ev = u < 3 * nOC ? EV_S4 : EV_S5;
+      const int v = u < 3 * nOC ? u : u - 3 * nOC;
+      i = v / 3; k = v - 3 * i;
+    }
+    const OrderSpec sp = kOrders[ev][k];
+    // Jones source table of this event
+    const int src = ev == EV_INIT ? DIR_IC1 : ev == EV_S0 ? DIR_IC2 : ev == EV_S1 ? DIR_IC3
+                  : ev == EV_S2 ? DIR_FC1 : ev == EV_S3 ? DIR_FC2 : ev == EV_S4 ? DIR_OC1 : DIR_OC2;
+    int32_t C;
+    const double* L = lut_slice(p, src, i, cell, cpp, C);
+    double* row = tab + t * ENTRY_DOUBLES;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(L) + sp.ch[q]);
+      row[2 * q] = v.x;
+      row[2 * q + 1] = v.y;
+    }
+    int32_t Cd;
+    const double* D = lut_slice(p, sp.dir, i, cell, cpp, Cd);
+    const double c_new = cos(__ldg(D));  // cos(theta_new.real)
+    double f = c_new;
+    if (sp.fmode == 1) f = c_new * p.n_g;
+    if (sp.fmode == 2) f = c_new / p.n_g;
+    row[8] = f;
+    row[9] = 1.0 / c_new;
+    const long long meta = (sp.tir & 3) | ((sp.gap & 3) << 2) | ((sp.nstate & 7) << 4) | ((sp.post & 3) << 7);
+    row[10] = __longlong_as_double(meta);
+    row[11] = 0.0;
+  }
+  const int t = threadIdx.x;
+  if (t < 4) {
+    const double T = __ldg(p.lut_TIR + 4 * cell + t);
+    double s, c;
+    sincos(T, &s, &c);
+    cc.ph1[t] = cplx{c, s};
+    sincos(2.0 * T, &s, &c);
+    cc.ph2[t] = cplx{c, s};
+  } else if (t < 12) {
+    cc.gap[t - 4] = __ldg(p.lut_gap + 8 * cell + (t - 4));
+  } else if (t < 20) {
+    cc.rect[t - 12] = __ldg(p.eff_reg_FOV + 8 * (m * p.Y + n) + (t - 12));
+  } else if (t < 24) {
+    cc.range[t - 20] = __ldg(p.eff_reg_FOV_range + 4 * (m * p.Y + n) + (t - 20));
+  } else if (t == 24) {
+    cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
+  } else if (t == 25) {
+    cc.rowbase[0] = 2; cc.rowbase[1] = 4; cc.rowbase[2] = 6; cc.rowbase[3] = 6 + 2 * nFC;
+    cc.rowbase[4] = 6 + 4 * nFC; cc.rowbase[5] = 6 + 4 * nFC + 3 * nOC; cc.rowbase[ST_INIT] = 0;
+    cc.rowbase[7] = 0;
+  }
+}
+
+struct Ray {
+  double x, y, gx, gy;  // position and current bounce vector
+  double a;             // |E_te|
+  cplx w;               // |E_tm| e^{i delta}
+  double inv_cos;       // 1 / cos(theta_current.real)
+  double ener;
+  uint32_t rng;
+  int state;
+  int iter;
+  int64_t idx;          // global ray index
+};
+
+__device__ __forceinline__ void jones_apply(const double* __restrict__ e, double a, cplx w, cplx& ote, cplx& otm) {
+  // Ete_out = L0 * te + L2 * tm ; Etm_out = L1 * te + L3 * tm        (GRTF:139-144)
+  const cplx L0{e[0], e[1]}, L1{e[2], e[3]}, L2{e[4], e[5]}, L3{e[6], e[7]};
+  ote = cplx{L0.re * a + (L2.re * w.re - L2.im * w.im), L0.im * a + (L2.re * w.im + L2.im * w.re)};
+  otm = cplx{L1.re * a + (L3.re * w.re - L3.im * w.im), L1.im * a + (L3.re * w.im + L3.im * w.re)};
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& sh, const double* __restrict__ tab,
+                                          int64_t lm, int64_t m, int64_t n, Ray& r, Counts* cn) {
+  const CellConst& cc = sh.cc;
+  if (r.state != ST_INIT) {
+    if (++r.iter > 100000) { r.state = ST_DEAD; return; }  // GRTF:905
+    if (COUNT) cn->c[WGRT_CNT_ITERS]++;
+    if (region_locate<COUNT>(sh.reg[REG_R1], r.x, r.y, cn) < 0) { r.state = ST_DEAD; return; }  // GRTF:906
+  }
+  int row;
+  if (r.state == ST_INIT || r.state <= 1) {
+    row = cc.rowbase[r.state];
+  } else {
+    const int hit = region_locate<COUNT>(sh.reg[r.state <= 3 ? REG_FC : REG_OC], r.x, r.y, cn);
+    row = hit < 0 ? -1 : cc.rowbase[r.state] + (r.state <= 3 ? 2 : 3) * hit;
+  }
+
+  if (row < 0) {
+    // no grating under the ray: free TIR bounce (GRTF:1049-1052, 1102-1108, 1175-1178, 1244-1246)
+    if (r.state == 5) { r.state = ST_DEAD; return; }
+    if (r.state == 3 && region_locate<COUNT>(sh.reg[REG_R2], r.x, r.y, cn) < 0) { r.state = 4; return; }
+    r.x += r.gx;
+    r.y += r.gy;
+    r.w = cmul(r.w, cc.ph2[r.state == 2 ? 0 : 1]);
+    if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
+    return;
+  }
+
+  const bool three = r.state == 4 || r.state == 5;
+  const bool gated = r.state >= 2 && r.state <= 5;  // `and ener_k > threshold` only in these states
+  const double* e = tab + row * ENTRY_DOUBLES;
+  cplx ote, otm;
+  jones_apply(e, r.a, r.w, ote, otm);
+  const double e1 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[8] * r.inv_cos;
+  jones_apply(e + ENTRY_DOUBLES, r.a, r.w, ote, otm);
+  const double e2 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[ENTRY_DOUBLES + 8] * r.inv_cos;
+  double e3 = 0.0;
+  if (three) {
+    jones_apply(e + 2 * ENTRY_DOUBLES, r.a, r.w, ote, otm);
+    e3 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[2 * ENTRY_DOUBLES + 8] * r.inv_cos;
+  }
+  const double u = xorshift_draw(r.rng, r.idx);
+  if (COUNT) {
+    cn->c[WGRT_CNT_DRAWS]++;
+    cn->c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
+    cn->c[WGRT_CNT_EFIELD] += three ? 3 : 2;
+  }
+  int sel;
+  double esel;
+  if (u <= e1 && (!gated || r.ener * e1 > 0.0)) { sel = 0; esel = e1; }
+  else if (u <= e1 + e2 && (!gated || r.ener * e2 > 0.0)) { sel = 1; esel = e2; }
+  else if (three && u <= e1 + e2 + e3 && r.ener * e3 > 0.0) { sel = 2; esel = e3; }
+  else { r.state = ST_DEAD; return; }
+
+  e += sel * ENTRY_DOUBLES;
+  const long long meta = __double_as_longlong(e[10]);
+  const int post = static_cast<int>((meta >> 7) & 3);
+  if (post == POST_DEPOSIT) {
+    // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
+    if (inside_or_on_edge_literal<COUNT>(r.x, r.y, cc.rect, 0, 4, cn)) {
+      deposit_bin(p, lm, m, n, r.x, r.y, cc.range[0], cc.range[1], cc.range[2], cc.range[3]);
+      if (COUNT) cn->c[WGRT_CNT_DEPOSITS]++;
+    }
+    r.state = ST_DEAD;
+    return;
+  }
+  if (three || sel == 0) jones_apply(e, r.a, r.w, ote, otm);  // otherwise (ote, otm) still hold order 1
+  {
+    const double te2 = ote.re * ote.re + ote.im * ote.im;
+    const double tm2 = otm.re * otm.re + otm.im * otm.im;
+    const double inv_norm = rsqrt(te2 + tm2);
+    const cplx ph = cc.ph1[meta & 3];
+    cplx num;
+    const double eps2 = 1e-40;  // (1e-20)^2: E_field_cal zeroes a phase when its amplitude < 1e-20
+    if (te2 >= eps2 && tm2 >= eps2) {
+      const double inv_te = rsqrt(te2);
+      r.a = te2 * inv_te * inv_norm;
+      // E_tm * conj(E_te) / |E_te|: amplitude |E_tm|, phase phi_tm - phi_te
+      num = cplx{(otm.re * ote.re + otm.im * ote.im) * inv_te, (otm.im * ote.re - otm.re * ote.im) * inv_te};
+    } else {
+      const double te_abs = sqrt(te2), tm_abs = sqrt(tm2);
+      r.a = te_abs * inv_norm;
+      if (te2 < eps2 && tm2 >= eps2) num = otm;                                                // phi_te := 0
+      else if (te2 >= eps2) num = cplx{tm_abs * ote.re / te_abs, -tm_abs * ote.im / te_abs};  // phi_tm := 0
+      else num = cplx{tm_abs, 0.0};
+    }
+    num.re *= inv_norm;
+    num.im *= inv_norm;
+    r.w = cmul(num, ph);
+  }
+  const int g = static_cast<int>((meta >> 2) & 3);
+  r.gx = cc.gap[2 * g];
+  r.gy = cc.gap[2 * g + 1];
+  r.x += r.gx;
+  r.y += r.gy;
+  r.inv_cos = e[9];
+  r.ener *= esel;
+  r.state = static_cast<int>((meta >> 4) & 7);
+  if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
+  if (post != POST_NONE) {
+    const bool in_ic = region_locate<COUNT>(sh.reg[REG_IC], r.x, r.y, cn) >= 0;
+    if (post == POST_IC_FWD) r.state = in_ic ? 0 : 2;       // GRTF:883-886
+    else if (!in_ic) r.state = ST_DEAD;                      // GRTF:899-902
+  }
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(WALK_THREADS, 4)
+walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
+                 int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
+                 unsigned long long* counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WalkShared& sh = *reinterpret_cast<WalkShared*>(smem_raw);
+  double* tab = reinterpret_cast<double*>(smem_raw + ((sizeof(WalkShared) + 15) & ~size_t(15)));
+  const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  Counts cn;
+  if (COUNT) cn.clear();
+
+  if (threadIdx.x < NUM_REGIONS) region_load(sh.reg[threadIdx.x], rs.st[threadIdx.x], rs.dyn[threadIdx.x]);
+  const int64_t tile_size = *tile_size_ptr;
+  const int64_t num_tiles = (p.num_rays + tile_size - 1) / tile_size;
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.tile = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int64_t tile = sh.tile;
+    if (tile >= num_tiles) break;
+    const int64_t t_begin = tile * tile_size;
+    const int64_t t_end = min(p.num_rays, t_begin + tile_size);
+
+    int64_t run_begin = t_begin;
+    while (run_begin < t_end) {
+      // ---- find the run of rays sharing the cell of ray run_begin --------------------------
+      const float km = __ldg(p.m + run_begin), kn = __ldg(p.n + run_begin), kl = __ldg(p.lmd_num + run_begin);
+      __syncthreads();  // previous run fully walked; shared tables may be overwritten
+      if (threadIdx.x == 0) sh.run_end = static_cast<int>(t_end - t_begin);
+      __syncthreads();
+      for (int64_t base = run_begin + 1; base < t_end; base += 4 * WALK_THREADS) {
+        int first_bad = INT_MAX;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int64_t i = base + k * WALK_THREADS + threadIdx.x;
+          if (i < t_end && first_bad == INT_MAX &&
+              (__ldg(p.m + i) != km || __ldg(p.n + i) != kn || __ldg(p.lmd_num + i) != kl))
+            first_bad = static_cast<int>(i - t_begin);
+        }
+        if (first_bad != INT_MAX) atomicMin(&sh.run_end, first_bad);
+        if (__syncthreads_or(first_bad != INT_MAX)) break;
+      }
+      __syncthreads();
+      const int64_t run_end = t_begin + sh.run_end;
+      const int64_t m = static_cast<int64_t>(km), n = static_cast<int64_t>(kn), lm = static_cast<int64_t>(kl);
+      const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
+      if (valid) {
+        build_cell_tables(p, lm, m, n, tab, sh.cc, rows);
+        if (threadIdx.x == 0) sh.q_next = 0;
+        __syncthreads();
+        const int run_len = static_cast<int>(run_end - run_begin);
+
+        // ---- walk the run: every lane owns at most one ray, refilled from the run queue -----
+        Ray r;
+        r.state = ST_DEAD;
+        bool queue_open = true;
+        for (;;) {
+          const unsigned need = __ballot_sync(FULL_MASK, r.state == ST_DEAD);
+          if (need && queue_open) {
+            const int cnt = __popc(need);
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&sh.q_next, cnt);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (r.state == ST_DEAD) {
+              const int q = base + __popc(need & lt_mask);
+              if (q < run_len) {
+                const int64_t idx = run_begin + q;
+                r.idx = idx;
+                r.x = static_cast<double>(__ldg(p.x + idx));
+                r.y = static_cast<double>(__ldg(p.y + idx));
+                const double te = static_cast<double>(__ldg(p.te + idx));
+                const double tm = static_cast<double>(__ldg(p.tm + idx));
+                const float dlf = __ldg(p.delta_phase + idx);
+                r.rng = p.rng_states[idx];
+                r.a = te;
+                if (dlf == 0.0f) {
+                  r.w = cplx{tm, 0.0};
+                } else {
+                  double s, c;
+                  sincos(static_cast<double>(dlf), &s, &c);
+                  r.w = cplx{tm * c, tm * s};
+                }
+                r.gx = 0.0; r.gy = 0.0;
+                r.inv_cos = sh.cc.inv_cos_in;
+                r.ener = 1.0;
+                r.iter = 0;
+                r.state = ST_INIT;
+                if (COUNT) cn.c[WGRT_CNT_RAYS]++;
+              }
+            }
+            if (base + cnt >= run_len) queue_open = false;
+          }
+          if (__ballot_sync(FULL_MASK, r.state != ST_DEAD) == 0u) break;
+          if (r.state != ST_DEAD) {
+            walk_step<COUNT>(p, sh, tab, lm, m, n, r, &cn);
+            if (r.state == ST_DEAD) p.rng_states[r.idx] = r.rng;
+          }
+        }
+      }
+      run_begin = run_end;
+    }
+  }
+  if (COUNT) cn.flush(counters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile size: one work tile should hold whole runs.  A single warp measures the first run.
+// ---------------------------------------------------------------------------------------------
+__global__ void pick_tile_kernel(const __grid_constant__ wgrt_problem_t p, int* tile_size, int* work_counter) {
+  const int lane = threadIdx.x;
+  if (lane == 0) *work_counter = 0;
+  if (p.tile_hint) {
+    if (lane == 0) *tile_size = static_cast<int>(p.tile_hint);
+    return;
+  }
+  const int64_t limit = p.num_rays < (1 << 16) ? p.num_rays : (1 << 16);
+  const float km = p.m[0], kn = p.n[0], kl = p.lmd_num[0];
+  int64_t run = limit;
+  for (int64_t base = 1; base < limit; base += 32) {
+    const int64_t i = base + lane;
+    const bool bad = i < limit && (p.m[i] != km || p.n[i] != kn || p.lmd_num[i] != kl);
+    const unsigned b = __ballot_sync(FULL_MASK, bad);
+    if (b) { run = base + __ffs(b) - 1; break; }
+  }
+  if (lane == 0) {
+    const int64_t target = 2560;  // rays per tile: ~20 per lane keeps the end-of-run tail small
+    int64_t t;
+    if (run >= target) {
+      const int64_t pieces = (run + target - 1) / target;
+      t = (run + pieces - 1) / pieces;
+    } else {
+      t = run * ((target + run - 1) / run);
+    }
+    *tile_size = static_cast<int>(t > 32 ? t : 32);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// region index construction (see wgrt_region.cuh)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int total_ring_verts(const RegionStatic& st) {
+  return st.offsets ? static_cast<int>(st.offsets[st.npoly]) : st.nverts;
+}
+
+__global__ void region_bbox_kernel(const __grid_constant__ RegionSet rs) {
+  const RegionStatic& st = rs.st[blockIdx.x];
+  __shared__ double s_min[2][256], s_max[2][256];
+  const int nv = min(total_ring_verts(st), st.nverts);
+  double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const double vx = st.verts[2 * i], vy = st.verts[2 * i + 1];
+    xmin = fmin(xmin, vx); xmax = fmax(xmax, vx);
+    ymin = fmin(ymin, vy); ymax = fmax(ymax, vy);
+  }
+  s_min[0][threadIdx.x] = xmin; s_max[0][threadIdx.x] = xmax;
+  s_min[1][threadIdx.x] = ymin; s_max[1][threadIdx.x] = ymax;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_min[0][threadIdx.x] = fmin(s_min[0][threadIdx.x], s_min[0][threadIdx.x + o]);
+      s_max[0][threadIdx.x] = fmax(s_max[0][threadIdx.x], s_max[0][threadIdx.x + o]);
+      s_min[1][threadIdx.x] = fmin(s_min[1][threadIdx.x], s_min[1][threadIdx.x + o]);
+      s_max[1][threadIdx.x] = fmax(s_max[1][threadIdx.x], s_max[1][threadIdx.x + o]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    RegionDyn d;
+    xmin = s_min[0][0]; xmax = s_max[0][0]; ymin = s_min[1][0]; ymax = s_max[1][0];
+    if (!(xmax >= xmin) || !(ymax >= ymin) || !isfinite(xmax - xmin) || !isfinite(ymax - ymin)) {
+      xmin = ymin = 0.0; xmax = ymax = 1.0;  // empty or non-finite ring set: every cell ends up NONE/AMBIG
+    }
+    const double pad_x = 1e-3 * (xmax - xmin) + 1e-9, pad_y = 1e-3 * (ymax - ymin) + 1e-9;
+    d.x0 = xmin - pad_x;
+    d.y0 = ymin - pad_y;
+    d.cell_dx = (xmax - xmin + 2.0 * pad_x) / st.nx;
+    d.cell_dy = (ymax - ymin + 2.0 * pad_y) / st.ny;
+    d.inv_dx = 1.0 / d.cell_dx;
+    d.inv_dy = 1.0 / d.cell_dy;
+    rs.dyn[blockIdx.x] = d;
+  }
+}
+
+__device__ __forceinline__ double margin_of(double cell) { return 0.02 * cell + 1e-11; }
+
+__global__ void region_rowmask_kernel(const __grid_constant__ RegionSet rs) {
+  const RegionStatic& st = rs.st[blockIdx.y];
+  const RegionDyn d = rs.dyn[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= st.ny * st.words) return;
+  const int row = t / st.words, word = t - row * st.words;
+  const double mrg = margin_of(d.cell_dy);
+  const double row_lo = d.y0 + row * d.cell_dy - mrg, row_hi = d.y0 + (row + 1) * d.cell_dy + mrg;
+  const int nv = min(total_ring_verts(st), st.nverts);
+  uint32_t bits = 0;
+  int k = 0;
+  for (int b = 0; b < 32; ++b) {
+    const int i = word * 32 + b;
+    if (i >= nv) break;
+    while (k < st.npoly && ring_begin(st.offsets, st.nverts, k + 1) <= i) ++k;
+    if (k >= st.npoly) break;
+    const int s = ring_begin(st.offsets, st.nverts, k), e = ring_begin(st.offsets, st.nverts, k + 1);
+    const int j = (i == s) ? e - 1 : i - 1;
+    const double yi = st.verts[2 * i + 1], yj = st.verts[2 * j + 1];
+    if (!(fmax(yi, yj) < row_lo || fmin(yi, yj) > row_hi)) bits |= 1u << b;
+  }
+  st.rowmask[t] = bits;
+}
+
+__global__ void region_cells_kernel(const __grid_constant__ RegionSet rs) {
+  const RegionStatic& st = rs.st[blockIdx.y];
+  const RegionDyn d = rs.dyn[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= st.nx * st.ny) return;
+  const int iy = t / st.nx, ix = t - iy * st.nx;
+  const double mx = margin_of(d.cell_dx), my = margin_of(d.cell_dy);
+  const double x_lo = d.x0 + ix * d.cell_dx - mx, x_hi = d.x0 + (ix + 1) * d.cell_dx + mx;
+  const double y_lo = d.y0 + iy * d.cell_dy - my, y_hi = d.y0 + (iy + 1) * d.cell_dy + my;
+  const double cx = d.x0 + (ix + 0.5) * d.cell_dx, cy = d.y0 + (iy + 0.5) * d.cell_dy;
+  const uint32_t* mask = st.rowmask + static_cast<size_t>(iy) * st.words;
+  uint8_t code = CELL_NONE;
+  for (int k = 0; k < st.npoly && code == CELL_NONE; ++k) {
+    const int s = ring_begin(st.offsets, st.nverts, k), e = ring_begin(st.offsets, st.nverts, k + 1);
+    if (e <= s) continue;
+    bool near_edge = false, inside = false;
+    for (int w = s >> 5; w <= (e - 1) >> 5 && !near_edge; ++w) {
+      uint32_t bits = mask[w];
+      if (w == (s >> 5)) bits &= 0xffffffffu << (s & 31);
+      if (w == ((e - 1) >> 5) && (e & 31)) bits &= 0xffffffffu >> (32 - (e & 31));
+      while (bits) {
+        const int i = (w << 5) + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int j = (i == s) ? e - 1 : i - 1;
+        const double xi = st.verts[2 * i], yi = st.verts[2 * i + 1];
+        const double xj = st.verts[2 * j], yj = st.verts[2 * j + 1];
+        // conservative segment / inflated-cell intersection: bounding boxes meet and the four
+        // corners are not strictly on one side of the supporting line (NaNs fall through to "near")
+        if (!(fmax(xi, xj) < x_lo || fmin(xi, xj) > x_hi || fmax(yi, yj) < y_lo || fmin(yi, yj) > y_hi)) {
+          const double ex = xi - xj, ey = yi - yj;
+          const double c0 = ex * (y_lo - yj) - ey * (x_lo - xj);
+          const double c1 = ex * (y_lo - yj) - ey * (x_hi - xj);
+          const double c2 = ex * (y_hi - yj) - ey * (x_lo - xj);
+          const double c3 = ex * (y_hi - yj) - ey * (x_hi - xj);
+          const bool all_pos = c0 > 0 && c1 > 0 && c2 > 0 && c3 > 0;
+          const bool all_neg = c0 < 0 && c1 < 0 && c2 < 0 && c3 < 0;
+          if (!(all_pos || all_neg)) { near_edge = true; break; }
+        }
+        if ((yi > cy) != (yj > cy))
+          if (cx < (xj - xi) * (cy - yi) / (yj - yi + 1e-20) + xi) inside = !inside;
+      }
+    }
+    if (near_edge) code = CELL_AMBIG;
+    else if (inside) code = static_cast<uint8_t>(k);
+  }
+  st.cells[t] = code;
+}
+
+template <bool COUNT>
+__global__ void locate_grid_kernel(const __grid_constant__ RegionSet rs, int region, const double* px,
+                                   const double* py, int64_t n, int32_t* out, unsigned long long* counters) {
+  __shared__ Region reg;
+  if (threadIdx.x == 0) region_load(reg, rs.st[region], rs.dyn[region]);
+  __syncthreads();
+  Counts cn;
+  if (COUNT) cn.clear();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = region_locate<COUNT>(reg, px[i], py[i], &cn);
+  if (COUNT) cn.flush(counters);
+}
+
+// pupil-mask sums (AR_system_evaluation_functions.py:68-109) and per-cell totals
+// (gpu_ray_tracing_pro_fullColor.py:186): one CTA per (lambda, FoV-y, FoV-x) bin tile.
+__global__ void __launch_bounds__(256) pupil_sums_kernel(const float* __restrict__ EB, int64_t tiles, int EBy,
+                                                         int EBx, int mask, int step_y, int step_x, int n_epy,
+                                                         int n_epx, float* __restrict__ out,
+                                                         float* __restrict__ cell_sums) {
+  extern __shared__ float s_tile[];
+  const int64_t tile = blockIdx.x;
+  if (tile >= tiles) return;
+  const int npix = EBy * EBx;
+  const float* src = EB + tile * npix;
+  float local = 0.f;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+    const float v = __ldg(src + i);
+    s_tile[i] = v;
+    local += v;
+  }
+  // counts are non-negative integers < 2^24 per tile in practice; float sum of a tile stays exact
+  __shared__ float s_red[8];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL_MASK, local, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0 && cell_sums) {
+    float tot = 0.f;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot += s_red[w];
+    cell_sums[tile] = tot;
+  }
+  if (!out) return;
+  const float radius = mask * 0.5f, ctr = radius - 0.5f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int pos = warp; pos < n_epy * n_epx; pos += nwarps) {
+    const int y0 = (pos / n_epx) * step_y, x0 = (pos % n_epx) * step_x;
+    float acc = 0.f;
+    for (int q = lane; q < mask * mask; q += 32) {
+      const int my = q / mask, mx = q - my * mask;
+      const float dx = mx - ctr, dy = my - ctr;
+      if (sqrtf(dx * dx + dy * dy) <= radius) acc += s_tile[(y0 + my) * EBx + (x0 + mx)];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL_MASK, acc, o);
+    if (lane == 0) out[tile * (n_epy * n_epx) + pos] = acc;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_region_build(const RegionSet& rs, cudaStream_t s) {
+  region_bbox_kernel<<<NUM_REGIONS, 256, 0, s>>>(rs);
+  int max_rw = 0, max_cells = 0;
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    max_rw = max(max_rw, rs.st[r].ny * rs.st[r].words);
+    max_cells = max(max_cells, rs.st[r].nx * rs.st[r].ny);
+  }
+  region_rowmask_kernel<<<dim3((max_rw + 127) / 128, NUM_REGIONS), 128, 0, s>>>(rs);
+  region_cells_kernel<<<dim3((max_cells + 127) / 128, NUM_REGIONS), 128, 0, s>>>(rs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
+                             unsigned long long* counters, int num_sms, cudaStream_t s) {
+  if (p.num_rays == 0) return cudaSuccess;
+  int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
+  pick_tile_kernel<<<1, 32, 0, s>>>(p, tile_size, work_counter);
+  const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
+  const size_t smem = ((sizeof(WalkShared) + 15) & ~size_t(15)) + static_cast<size_t>(rows) * ENTRY_DOUBLES * sizeof(double);
+  const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
+  auto kern = count ? walk_fast_kernel<true> : walk_fast_kernel<false>;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  int per_sm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WALK_THREADS, smem);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  const int64_t min_tiles = (p.num_rays + 31) / 32;
+  const int64_t resident = static_cast<int64_t>(num_sms) * per_sm;
+  const int grid = static_cast<int>(resident < min_tiles ? resident : (min_tiles > 1 ? min_tiles : 1));
+  kern<<<grid, WALK_THREADS, smem, s>>>(p, rs, work_counter, tile_size, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const double* px, const double* py, int64_t n,
+                                     int32_t* out, unsigned long long* counters, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
+  if (counters) locate_grid_kernel<true><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters);
+  else locate_grid_kernel<false><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pupil_sums(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
+                              int mask, int step_y, int step_x, float* out, float* cell_sums, cudaStream_t s) {
+  const int64_t tiles = L * Yf * Xf;
+  if (tiles == 0) return cudaSuccess;
+  const int n_epy = EBy >= mask ? static_cast<int>((EBy - mask) / step_y + 1) : 0;
+  const int n_epx = EBx >= mask ? static_cast<int>((EBx - mask) / step_x + 1) : 0;
+  const size_t smem = static_cast<size_t>(EBy * EBx) * sizeof(float);
+  cudaError_t err = cudaFuncSetAttribute(pupil_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  pupil_sums_kernel<<<static_cast<unsigned>(tiles), 256, smem, s>>>(EB, tiles, static_cast<int>(EBy),
+                                                                   static_cast<int>(EBx), mask, step_y, step_x,
+                                                                   n_epy, n_epx, (n_epy && n_epx) ? out : nullptr,
+                                                                   cell_sums);
+  return cudaGetLastError();
+}
+
+}  // namespace wgrt

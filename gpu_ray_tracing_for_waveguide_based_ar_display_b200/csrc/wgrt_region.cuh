@@ -1,0 +1,106 @@
+// wgrt_region.cuh -- exact-equivalent acceleration of the reference's point-in-region tests.
+//
+// The reference answers "which coupler polygon contains (x, y)?" by running
+// is_inside_or_on_edge (GRTF:63-71 -> GRTF:52-61 and GRTF:36-50) over every ring in order and
+// every edge of each ring, twice.  That scan is ~92 % of its arithmetic.
+// Here each region set (in-coupler, effective regions 1 and 2, fold-coupler slices, out-coupler
+// slices) gets a uniform cell grid over its bounding box:
+//
+//   cell code  0..253 : every point that maps to this cell is inside ring <code> and in no
+//                       earlier ring -> the reference's first-hit index, no arithmetic
+//   CELL_NONE         : every such point is outside all rings
+//   CELL_AMBIG        : an edge of a not-yet-excluded ring passes within the safety margin of the
+//                       cell -> run the reference's own expressions, but only on the edges whose
+//                       y-range meets this cell row (a per-row edge bit mask).  Edges outside that
+//                       mask cannot satisfy (yi>y)!=(yj>y) nor the tolerance box of
+//                       point_on_segment, so skipping them cannot change either pass.
+//
+// Booleans are therefore identical to the literal scan for every input point; only the amount of
+// work differs.  tests/test_region_index.py checks this against the oracle on adversarial points
+// (vertices, edge midpoints, points 5e-13 and 5e-12 off an edge).
+#pragma once
+
+#include "wgrt_device.cuh"
+
+namespace wgrt {
+
+// Region descriptor as the walk kernels see it (shared memory copy: static + device-computed part).
+struct alignas(16) Region {
+  double x0, y0, inv_dx, inv_dy;
+  const uint8_t* cells;
+  const uint32_t* rowmask;
+  const double* verts;
+  const int64_t* offsets;
+  int nverts, npoly, nx, ny, words;
+  int pad_;
+};
+
+__device__ __forceinline__ void region_load(Region& r, const RegionStatic& st, const RegionDyn& dy) {
+  r.x0 = dy.x0; r.y0 = dy.y0; r.inv_dx = dy.inv_dx; r.inv_dy = dy.inv_dy;
+  r.cells = st.cells; r.rowmask = st.rowmask; r.verts = st.verts; r.offsets = st.offsets;
+  r.nverts = st.nverts; r.npoly = st.npoly; r.nx = st.nx; r.ny = st.ny; r.words = st.words; r.pad_ = 0;
+}
+
+__device__ __forceinline__ int ring_begin(const int64_t* off, int nverts, int k) {
+  return off ? static_cast<int>(off[k]) : (k == 0 ? 0 : nverts);
+}
+
+// The reference's two passes over ring [s, e), restricted to edges whose bit is set in `mask`
+// (bit i <-> the edge ending at vertex i, i.e. (prev(i) -> i) exactly as GRTF:40-49 / 66-70 pair
+// them).  Pass 1's early `return True` and pass 2's parity commute with skipping, so both passes
+// are fused into one sweep: result = any(on_segment) or odd(crossings).
+template <bool COUNT>
+__device__ __forceinline__ bool ring_test_masked(double px, double py, const double* __restrict__ verts, int s,
+                                                 int e, const uint32_t* __restrict__ mask, Counts* cn) {
+  if (e <= s) return false;
+  bool on_edge = false, inside = false;
+  const int w0 = s >> 5, w1 = (e - 1) >> 5;
+  for (int w = w0; w <= w1; ++w) {
+    uint32_t bits = __ldg(mask + w);
+    if (w == w0) bits &= 0xffffffffu << (s & 31);
+    if (w == w1 && ((e & 31) != 0)) bits &= 0xffffffffu >> (32 - (e & 31));
+    while (bits) {
+      const int i = (w << 5) + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int j = (i == s) ? e - 1 : i - 1;
+      const double2 vi = __ldg(reinterpret_cast<const double2*>(verts) + i);
+      const double2 vj = __ldg(reinterpret_cast<const double2*>(verts) + j);
+      // GRTF:68 calls point_on_segment(px, py, poly, start + j, start + i)
+      on_edge |= on_segment_literal<COUNT>(px, py, vj.x, vj.y, vi.x, vi.y, 1e-12, cn);
+      if ((vi.y > py) != (vj.y > py)) {
+        if (COUNT) cn->c[WGRT_CNT_STRADDLE]++;
+        if (px < (vj.x - vi.x) * (py - vi.y) / (vj.y - vi.y + 1e-20) + vi.x) inside = !inside;
+      }
+    }
+  }
+  return on_edge || inside;
+}
+
+template <bool COUNT>
+__device__ __noinline__ int region_locate_exact(const Region& r, double x, double y, int iy, Counts* cn) {
+  if (COUNT) cn->c[WGRT_CNT_EXACT_FALLBACK]++;
+  const uint32_t* mask = r.rowmask + static_cast<size_t>(iy) * r.words;
+  for (int k = 0; k < r.npoly; ++k) {
+    const int s = ring_begin(r.offsets, r.nverts, k), e = ring_begin(r.offsets, r.nverts, k + 1);
+    if (ring_test_masked<COUNT>(x, y, r.verts, s, e, mask, cn)) return k;
+  }
+  return -1;
+}
+
+// Index of the first ring of the set containing (x, y) -- what the reference's
+// `for i in range(len(offset)-1): if is_inside_or_on_edge(...): ... break` finds -- or -1.
+template <bool COUNT>
+__device__ __forceinline__ int region_locate(const Region& r, double x, double y, Counts* cn) {
+  if (COUNT) cn->c[WGRT_CNT_POLY_TESTS]++;
+  const double fx = (x - r.x0) * r.inv_dx;
+  const double fy = (y - r.y0) * r.inv_dy;
+  // also rejects NaN coordinates, which the literal test classifies as outside
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < static_cast<double>(r.nx) && fy < static_cast<double>(r.ny))) return -1;
+  const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
+  const uint8_t code = __ldg(r.cells + iy * r.nx + ix);
+  if (code == CELL_NONE) return -1;
+  if (code != CELL_AMBIG) return code;
+  return region_locate_exact<COUNT>(r, x, y, iy, cn);
+}
+
+}  // namespace wgrt

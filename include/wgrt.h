@@ -1,0 +1,195 @@
+/*
+ * wgrt.h -- C ABI of the B200 waveguide ray-propagation engine (libwgrt.so).
+ *
+ * Drop-in boundary for ONE path of yefuzhang/GPU_ray_tracing_for_waveguide_based_AR_display:
+ * the Monte-Carlo ray walk `process_rays_kernel_pro_fullColor`
+ * (reference: GPU_ray_tracing_functions.py:833-1246) as launched by the runner
+ * (reference: gpu_ray_tracing_pro_fullColor.py:168-178).
+ *
+ * Plain pointers and sizes only; no torch / numba types.  All arrays are C-contiguous.
+ * Complex LUT entries are complex128 stored as (re, im) double pairs, i.e. a NumPy
+ * complex128 array can be passed as `const double*` unchanged.
+ */
+#ifndef WGRT_H_
+#define WGRT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGRT_VERSION 100 /* major*10000 + minor*100 + patch */
+
+/* ---- error codes (negative); wgrt_last_error() gives the text ------------------------- */
+#define WGRT_OK 0
+#define WGRT_ERR_INVALID (-1)   /* bad argument: null pointer, inconsistent shapes, ...   */
+#define WGRT_ERR_CUDA (-2)      /* a CUDA runtime call failed                              */
+#define WGRT_ERR_NO_DEVICE (-3) /* no CUDA device / driver                                 */
+#define WGRT_ERR_UNSUPPORTED (-4)
+
+/* ---- flags ---------------------------------------------------------------------------- */
+#define WGRT_FLAG_STRICT 0x1u   /* literal thread-per-ray walk (parity anchor; slow)       */
+#define WGRT_FLAG_COUNTERS 0x2u /* accumulate the device event counters (see below)       */
+
+/* ---- event counters (uint64 each) ------------------------------------------------------ */
+enum {
+  WGRT_CNT_RAYS = 0,     /* rays launched                                                   */
+  WGRT_CNT_BOUNCES,      /* position advances x += gap (a "bounce")   */
+  WGRT_CNT_DRAWS,        /* xorshift32 draws                                                */
+  WGRT_CNT_DRAW2,        /* two-order decisions                                             */
+  WGRT_CNT_DRAW3,        /* three-order decisions                                           */
+  WGRT_CNT_EFIELD,       /* Jones-matrix applications (E_field_cal evaluations)             */
+  WGRT_CNT_ITERS,        /* iterations of the walk loop                                     */
+  WGRT_CNT_DEPOSITS,     /* rays counted into an eyebox bin                                 */
+  WGRT_CNT_POLY_TESTS,   /* point-in-region queries (one per polygon ring)                  */
+  WGRT_CNT_EDGE_VISITS,  /* polygon edges visited by the literal scan (strict/oracle only)  */
+  WGRT_CNT_STRADDLE,     /* edges with (yi>y)!=(yj>y): intersection arithmetic needed       */
+  WGRT_CNT_CROSS,        /* on-segment cross products evaluated                             */
+  WGRT_CNT_EXACT_FALLBACK, /* region queries that left the cell grid for the exact edge scan */
+  WGRT_NUM_COUNTERS = 16
+};
+
+/*
+ * One launch of the full-colour ray walk.  Field order follows the 33 positional arguments of
+ * the reference kernel (GPU_ray_tracing_functions.py:834-841); sizes follow each pointer.
+ *
+ * For wgrt_trace_fullcolor every pointer is a DEVICE pointer on the current device.
+ * For wgrt_trace_fullcolor_host (and the CPU oracle, which reuses this struct) every pointer is
+ * a HOST pointer.
+ */
+typedef struct wgrt_problem {
+  /* rays: float32[num_rays] each.  gap_x, gap_y, pol, azi are accepted for signature
+   * compatibility; the reference overwrites them before any use (GPU_ray_tracing_functions.py:
+   * 848-851 vs 872-879), so they are never read and may be NULL. */
+  const float* x;
+  const float* y;
+  const float* gap_x;
+  const float* gap_y;
+  const float* pol;
+  const float* azi;
+  const float* m;       /* FoV-x index, integer valued */
+  const float* n;       /* FoV-y index, integer valued */
+  const float* lmd_num; /* wavelength index, integer valued */
+  const float* te;
+  const float* tm;
+  const float* delta_phase;
+  uint32_t* rng_states; /* uint32[num_rays], read and written */
+  int64_t num_rays;
+
+  /* geometry: float64 [V,2] vertex rings; *_offset int64[n_polys+1] */
+  const double* IC;
+  int64_t IC_n;
+  const double* FC;
+  int64_t FC_n;
+  const int64_t* FC_offset;
+  int64_t n_FC; /* number of fold-coupler polygons = len(FC_offset)-1 */
+  const double* OC;
+  int64_t OC_n;
+  const int64_t* OC_offset;
+  int64_t n_OC;
+  double n_g;
+  const double* eff_reg1;
+  int64_t eff_reg1_n;
+  const double* eff_reg2;
+  int64_t eff_reg2_n;
+  const double* eff_reg_FOV;       /* [X, Y, 4, 2] */
+  const double* eff_reg_FOV_range; /* [X, Y, 4] = xmin, xmax, ymin, ymax */
+
+  /* RCWA tables, complex128 */
+  const double* lut_ic1; /* [L, X, Y, C_ic] */
+  const double* lut_ic2;
+  const double* lut_ic3;
+  const double* lut_fc1; /* [n_FC, L, X, Y, C_fc] */
+  const double* lut_fc2;
+  const double* lut_oc1; /* [n_OC, L, X, Y, C_oc] */
+  const double* lut_oc2;
+  int32_t C_ic; /* channels per entry: >= 41 */
+  int32_t C_fc; /* >= 20 */
+  int32_t C_oc; /* >= 41 */
+  int32_t reserved0;
+  const double* lut_TIR; /* [L, X, Y, 4] */
+  const double* lut_gap; /* [L, X, Y, 8] */
+  int64_t L;             /* wavelengths */
+  int64_t X;             /* FoV-x cells */
+  int64_t Y;             /* FoV-y cells */
+
+  /* bins: float32 [L, Y, X, EBy, EBx], accumulated in place */
+  float* matrix_EB;
+  int64_t EBy;
+  int64_t EBx;
+
+  uint32_t flags;
+  uint32_t tile_hint; /* 0 = automatic; otherwise rays per work tile of the fast path */
+} wgrt_problem_t;
+
+/* Library / runtime ------------------------------------------------------------------------ */
+int wgrt_version(void);
+const char* wgrt_last_error(void);
+/* number of CUDA devices visible, or WGRT_ERR_NO_DEVICE */
+int wgrt_device_count(void);
+/* free cached device workspaces of the calling thread's current device */
+int wgrt_release(void);
+
+/*
+ * Replaces: GRTF.process_rays_kernel_pro_fullColor[grid, block](...33 args...)
+ * (reference call site gpu_ray_tracing_pro_fullColor.py:170-177).  Asynchronous on `stream`
+ * (a cudaStream_t; NULL = legacy default stream, which is what Numba launches on, so the
+ * runner's cuda.synchronize() at gpu_ray_tracing_pro_fullColor.py:178 still fences it).
+ * Mutates only rng_states and matrix_EB, like the reference kernel.
+ */
+int wgrt_trace_fullcolor(const wgrt_problem_t* dev_problem, void* stream);
+
+/*
+ * Replaces the runner's region gpu_ray_tracing_pro_fullColor.py:145-185 for HOST buffers:
+ * H2D of rays/geometry/LUTs/bins, `num_iter` launches (RUN:169-177), synchronize, D2H of
+ * matrix_EB and rng_states.  Synchronous.  `timings_ms`, if not NULL, receives
+ * {h2d, trace, d2h} device-event times in milliseconds.
+ */
+int wgrt_trace_fullcolor_host(const wgrt_problem_t* host_problem, int num_iter, float* timings_ms);
+
+/* Counters accumulated by launches that carried WGRT_FLAG_COUNTERS (device-wide, since reset). */
+int wgrt_counters_read(uint64_t* out, int n);
+int wgrt_counters_reset(void);
+
+/*
+ * Unit-level entry points used by the parity tests (each mirrors one reference device function).
+ * All pointers are HOST pointers; the call copies, runs on the GPU, and copies back.
+ */
+
+/* is_inside_or_on_edge over a set of rings (GPU_ray_tracing_functions.py:36-71): out[i] = index
+ * of the first ring containing point i, or -1.  mode 0 = literal scan, mode 1 = cell-grid index
+ * + exact row-masked fallback (the fast path's classifier). */
+int wgrt_debug_locate(const double* verts, int64_t n_verts, const int64_t* offsets, int64_t n_polys,
+                      const double* px, const double* py, int64_t n_points, int32_t* out, int mode);
+
+/* E_field_cal (GPU_ray_tracing_functions.py:132-152) on n inputs: jones = [n,4] complex128 in
+ * the CALL order (E_te_te, E_te_tm, E_tm_te, E_tm_tm); out = [n,3] (Ete_abs, Etm_abs, delta). */
+int wgrt_debug_efield(const double* ete, const double* etm, const double* delta, const double* jones,
+                      int64_t n, double* out);
+
+/* get_uniform_random_number (GPU_ray_tracing_functions.py:25-34): advance each state `draws`
+ * times; out_last[i] = last uniform of stream i. */
+int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last);
+
+/*
+ * Evaluation reductions on the bin tensor:
+ *   out[l, fy, fx, iy, ix] = sum over the disc pupil mask of EB[l, fy, fx, y0:y0+mask, x0:x0+mask],
+ *   y0 = iy*step_y, x0 = ix*step_x   (AR_system_evaluation_functions.py:68-109; the reference uses
+ *   mask_size 30, step_y 8, step_x 12), and
+ *   cell_sums[l, fy, fx] = sum of EB[l, fy, fx, :, :]   (gpu_ray_tracing_pro_fullColor.py:186).
+ * EB is float32 [L, Yf, Xf, EBy, EBx]; out is float32 [L, Yf, Xf, n_epy, n_epx] with
+ * n_ep* = (EB* - mask_size) / step_* + 1; either output may be NULL.
+ * wgrt_eval_pupil_sums takes DEVICE pointers and is asynchronous on `stream`;
+ * wgrt_eval_pupil_sums_host takes HOST pointers and is synchronous.
+ */
+int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
+                         int mask_size, int step_y, int step_x, float* dev_out, float* dev_cell_sums,
+                         void* stream);
+int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
+                              int mask_size, int step_y, int step_x, float* out, float* cell_sums);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGRT_H_ */

@@ -1,0 +1,205 @@
+"""Generate golden vectors by executing the REFERENCE kernel itself (test infrastructure only).
+
+Runs /root/reference/GPU_ray_tracing_functions.py unmodified under Numba's CUDA simulator
+(``NUMBA_ENABLE_CUDASIM=1``) -- the reference's only CPU path -- on the deterministic synthetic
+scenes of ``synthetic_inputs.make_scene`` and stores the results under tests/golden/.  Two
+non-invasive shims are needed: ``matplotlib`` is stubbed in ``sys.modules``
+(imported at GRTF:5-7, not installed here) and an int-coercing ``range`` is injected into the
+module globals (GRTF:905 calls ``range(1e5)``, legal for the JIT, a TypeError in the simulator).
+
+The reference cannot travel to the GPU box, hence the committed fixtures.  Usage (in the build
+container, where /root/reference exists)::
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz  (a few minutes, 8 procs)
+
+Each fixture stores the scene recipe, a SHA-256 of every input array (so a drifting generator is
+caught), the final ``rng_states`` and the non-zero bins of ``matrix_EB``.  ``walk_small`` also
+stores its complete inputs, so the oracle stays pinned even if the generators change.
+"""
+from __future__ import annotations
+
+import builtins
+import hashlib
+import os
+import sys
+import time
+import types
+
+os.environ["NUMBA_ENABLE_CUDASIM"] = "1"
+os.environ.setdefault("NUMBA_DISABLE_JIT", "0")
+
+import numpy as np  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REFERENCE_DIR = os.environ.get("WGRT_REFERENCE_DIR", "/root/reference")
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    """Import the reference module with the two shims."""
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.path", "matplotlib.colors"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            mod.Path = object
+            mod.LogNorm = object
+            sys.modules[name] = mod
+    sys.path.insert(0, REFERENCE_DIR)
+    import GPU_ray_tracing_functions as GRTF  # the reference file, unmodified
+    GRTF.range = lambda *a: builtins.range(*map(int, a))
+    return GRTF
+
+
+SCENES = {
+    # BASELINE.json config 1: single wavelength 532 nm, 5x5 FoV grid, 64 rays per FoV
+    "walk_c1": dict(num_FOV_x=5, num_FOV_y=5, num_rays_per_FoV=64, seed=11, lmd_subset=[1], num_iter=2),
+    # all three wavelengths, self-contained fixture (inputs stored)
+    "walk_small": dict(num_FOV_x=4, num_FOV_y=3, num_rays_per_FoV=48, seed=5, lmd_subset=None, num_iter=1,
+                       store_inputs=True),
+    # default efficiencies, more rays: statistics for the out-coupler states
+    "walk_mid": dict(num_FOV_x=6, num_FOV_y=5, num_rays_per_FoV=200, seed=3, lmd_subset=None, num_iter=1),
+    # lossless gratings: long walks, many fold/out-coupler events per ray
+    "walk_deep": dict(num_FOV_x=3, num_FOV_y=3, num_rays_per_FoV=400, seed=23, lmd_subset=None, num_iter=1,
+                      eff=dict(incouple=0.9, incouple_m1=0.08, ic_zero=0.9, ic_cross=0.05, fc_zero=0.7,
+                               fc_turn=0.28, oc_zero=0.85, oc_cross=0.06, outcouple=0.06)),
+}
+
+
+def scene_from_recipe(r):
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.synthetic_inputs import make_scene
+    return make_scene(r["num_FOV_x"], r["num_FOV_y"], r["num_rays_per_FoV"], seed=r["seed"],
+                      lmd_subset=r.get("lmd_subset"), eff=r.get("eff"))
+
+
+def input_digest(scene) -> str:
+    h = hashlib.sha256()
+    for a in scene.kernel_args(scene.new_matrix_EB()):
+        if isinstance(a, np.ndarray):
+            h.update(str(a.dtype).encode()); h.update(str(a.shape).encode())
+            h.update(np.ascontiguousarray(a).tobytes())
+        else:
+            h.update(repr(float(a)).encode())
+    return h.hexdigest()
+
+
+def _run_chunk(job):
+    """Worker: trace rays [lo, hi) for num_iter launches in the simulator."""
+    recipe, lo, hi, num_iter = job
+    GRTF = import_reference()
+    scene = scene_from_recipe(recipe)
+    sub = scene.rays.take(slice(lo, hi))
+    scene.rays = sub
+    # the zero-state reseed (GRTF:28-29) depends on the absolute index; it never triggers for the
+    # runner's seeds, which we assert so that chunking stays exact
+    assert np.all(sub.rng_states != 0)
+    EB = scene.new_matrix_EB()
+    rng = sub.rng_states.copy()
+    threads = 32
+    blocks = (sub.num_rays + threads - 1) // threads
+    for _ in range(num_iter):
+        GRTF.process_rays_kernel_pro_fullColor[blocks, threads](*scene.kernel_args(EB, rng))
+        assert np.all(rng != 0)
+    nz = np.flatnonzero(EB)
+    return lo, hi, rng, nz, EB.ravel()[nz]
+
+
+def make_walk(name: str, recipe: dict, procs: int):
+    import multiprocessing as mp
+    scene = scene_from_recipe(recipe)
+    N = scene.rays.num_rays
+    num_iter = recipe.get("num_iter", 1)
+    step = max(32, (N + 4 * procs - 1) // (4 * procs))
+    jobs = [(recipe, lo, min(N, lo + step), num_iter) for lo in range(0, N, step)]
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(procs) as pool:
+        parts = pool.map(_run_chunk, jobs)
+    dt = time.time() - t0
+    rng = np.zeros(N, dtype=np.uint32)
+    EB = scene.new_matrix_EB().ravel()
+    for lo, hi, r, nz, val in parts:
+        rng[lo:hi] = r
+        EB[nz] += val
+    nz = np.flatnonzero(EB)
+    out = dict(recipe=np.array(repr({k: v for k, v in recipe.items() if k != "store_inputs"})),
+               digest=np.array(input_digest(scene)), num_iter=np.array(num_iter),
+               rng_states=rng, eb_index=nz.astype(np.int64), eb_value=EB[nz].astype(np.float32),
+               eb_shape=np.array(scene.eb_shape, dtype=np.int64),
+               sim_seconds=np.array(dt), sim_procs=np.array(procs))
+    if recipe.get("store_inputs"):
+        args = scene.kernel_args(scene.new_matrix_EB())
+        from gpu_ray_tracing_for_waveguide_based_ar_display_b200.GPU_ray_tracing_functions import _ARG_NAMES
+        for nm, a in zip(_ARG_NAMES[:-1], args[:-1]):
+            out["in_" + nm] = np.asarray(a)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {N} rays x {num_iter} launches in {dt:.1f}s ({N * num_iter / dt:.0f} rays/s, "
+          f"{procs} procs), deposits={EB.sum():.0f} -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
+def make_units(procs: int):
+    """Unit-level golden vectors from the reference device functions (plain callables in the simulator)."""
+    GRTF = import_reference()
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.couplers_coor import couplers_coor_full_color
+    rs = np.random.default_rng(77)
+    # xorshift32, GRTF:25-34
+    states = np.concatenate(([0, 1, 0xFFFFFFFF, 0x9E3779B9], rs.integers(1, 2 ** 32, 60))).astype(np.uint32)
+    st = states.copy()
+    last = np.zeros(len(st))
+    for i in range(len(st)):
+        for _ in range(7):
+            last[i] = GRTF.get_uniform_random_number(st, i)
+    # E_field_cal, GRTF:132-152
+    n = 400
+    ete = rs.uniform(0, 1, n); etm = rs.uniform(0, 1, n)
+    ete[:8] = [1, 0, 1, 0, 0.5, 0, 0, 1]; etm[:8] = [0, 1, 0, 1, 0.5, 0, 0, 1]
+    delta = rs.uniform(-np.pi, np.pi, n); delta[:4] = 0.0
+    jones = (rs.normal(size=(n, 4)) + 1j * rs.normal(size=(n, 4))) * 0.5
+    jones[4] = 0.0                       # both outputs below eps -> phases forced to 0
+    jones[5, [0, 2]] = 0.0               # te output exactly 0
+    jones[6, :] = [1, 0, 0, -1]
+    ef = np.zeros((n, 3))
+    for i in range(n):
+        ef[i] = GRTF.E_field_cal(float(ete[i]), float(etm[i]), float(delta[i]),
+                                 complex(jones[i, 0]), complex(jones[i, 1]), complex(jones[i, 2]),
+                                 complex(jones[i, 3]))
+    # is_inside_or_on_edge over the design's rings, GRTF:36-71
+    out = couplers_coor_full_color(5, 5)
+    IC, FC, FC_offset, OC, OC_offset, eff_reg1, eff_reg2 = out[:7]
+    rings = dict(IC=(IC, np.array([0, len(IC)])), FC=(FC, FC_offset), OC=(OC, OC_offset),
+                 eff_reg1=(eff_reg1, np.array([0, len(eff_reg1)])),
+                 eff_reg2=(eff_reg2, np.array([0, len(eff_reg2)])))
+    loc = {}
+    for nm, (verts, off) in rings.items():
+        lo = verts.min(0) - 1.0; hi = verts.max(0) + 1.0
+        pts = rs.uniform(lo, hi, size=(500, 2))
+        # adversarial points: vertices, edge midpoints, points 5e-13 / 5e-12 off an edge
+        mids = 0.5 * (verts + np.roll(verts, 1, axis=0))
+        nrm = np.roll(verts, 1, axis=0) - verts
+        nrm = np.stack((-nrm[:, 1], nrm[:, 0]), 1)
+        nrm /= np.maximum(np.hypot(nrm[:, 0], nrm[:, 1]), 1e-300)[:, None]
+        extra = np.concatenate((verts, mids, mids + 5e-13 * nrm, mids - 5e-13 * nrm, mids + 5e-12 * nrm,
+                                mids - 5e-12 * nrm))
+        pts = np.concatenate((pts, extra[rs.permutation(len(extra))[:300]]))
+        res = np.full(len(pts), -1, dtype=np.int32)
+        for k in range(len(pts)):
+            for i in range(len(off) - 1):
+                if GRTF.is_inside_or_on_edge(pts[k, 0], pts[k, 1], verts, int(off[i]), int(off[i + 1])):
+                    res[k] = i
+                    break
+        loc[nm + "_verts"] = verts; loc[nm + "_off"] = np.asarray(off, dtype=np.int64)
+        loc[nm + "_pts"] = pts; loc[nm + "_hit"] = res
+    path = os.path.join(GOLDEN_DIR, "units.npz")
+    np.savez_compressed(path, xs_in=states, xs_out=st, xs_last=last, ef_ete=ete, ef_etm=etm,
+                        ef_delta=delta, ef_jones=jones, ef_out=ef, **loc)
+    print(f"units -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    procs = int(os.environ.get("WGRT_GOLDEN_PROCS", os.cpu_count() or 1))
+    which = sys.argv[1:] or ["units"] + list(SCENES)
+    for w in which:
+        if w == "units":
+            make_units(procs)
+        else:
+            make_walk(w, SCENES[w], procs)

@@ -1,0 +1,95 @@
+"""ctypes front-end of oracle/libwgrt_oracle.so (TEST INFRASTRUCTURE ONLY).
+
+``trace(scene_args...)`` walks rays on the CPU exactly as the reference kernel does
+(GPU_ray_tracing_functions.py:833-1246, restated in wgrt_oracle.c) and mutates ``rng_states`` and
+``matrix_EB`` in place, like the kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from gpu_ray_tracing_for_waveguide_based_ar_display_b200._capi import (
+    COUNTER_NAMES, WGRT_NUM_COUNTERS, WgrtProblem)
+from gpu_ray_tracing_for_waveguide_based_ar_display_b200.GPU_ray_tracing_functions import (
+    pack_problem)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libwgrt_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "wgrt_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "libwgrt_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        L = C.CDLL(_LIB)
+        L.wgrt_oracle_trace.restype = C.c_int
+        L.wgrt_oracle_trace.argtypes = [C.POINTER(WgrtProblem), C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        L.wgrt_oracle_locate.restype = C.c_int
+        L.wgrt_oracle_locate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_int64, C.c_void_p]
+        L.wgrt_oracle_efield.restype = C.c_int
+        L.wgrt_oracle_efield.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
+        L.wgrt_oracle_xorshift.restype = C.c_int
+        L.wgrt_oracle_xorshift.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def trace(*args, first: int = 0, count: Optional[int] = None, num_threads: int = 0,
+          counters: bool = False):
+    """Same 33 positional arguments as the reference kernel, all host NumPy arrays."""
+    prob, keep = pack_problem(args, host=True)
+    n = prob.num_rays if count is None else count
+    cnt = np.zeros(WGRT_NUM_COUNTERS, dtype=np.uint64)
+    nt = num_threads or (os.cpu_count() or 1)
+    rc = lib().wgrt_oracle_trace(C.byref(prob), first, n, cnt.ctypes.data, nt)
+    del keep
+    if rc != 0:
+        raise RuntimeError(f"oracle error {rc}")
+    if counters:
+        return {k: int(cnt[i]) for i, k in enumerate(COUNTER_NAMES)}
+    return None
+
+
+def locate(verts, offsets, px, py):
+    verts = np.ascontiguousarray(verts, dtype=np.float64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    px = np.ascontiguousarray(px, dtype=np.float64)
+    py = np.ascontiguousarray(py, dtype=np.float64)
+    out = np.empty(len(px), dtype=np.int32)
+    lib().wgrt_oracle_locate(verts.ctypes.data, len(verts), offsets.ctypes.data, len(offsets) - 1,
+                             px.ctypes.data, py.ctypes.data, len(px), out.ctypes.data)
+    return out
+
+
+def efield(ete, etm, delta, jones):
+    ete = np.ascontiguousarray(ete, dtype=np.float64)
+    etm = np.ascontiguousarray(etm, dtype=np.float64)
+    delta = np.ascontiguousarray(delta, dtype=np.float64)
+    jones = np.ascontiguousarray(jones, dtype=np.complex128)
+    out = np.empty((len(ete), 3), dtype=np.float64)
+    lib().wgrt_oracle_efield(ete.ctypes.data, etm.ctypes.data, delta.ctypes.data, jones.ctypes.data,
+                             len(ete), out.ctypes.data)
+    return out
+
+
+def xorshift(states, draws):
+    states = np.ascontiguousarray(states, dtype=np.uint32).copy()
+    last = np.empty(len(states), dtype=np.float64)
+    lib().wgrt_oracle_xorshift(states.ctypes.data, len(states), draws, last.ctypes.data)
+    return states, last

@@ -1,0 +1,82 @@
+"""The CPU oracle must reproduce what the REFERENCE file itself produced (oracle/make_golden.py ran
+/root/reference/GPU_ray_tracing_functions.py under Numba's CUDA simulator) -- bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_bins, input_digest, load_golden_walk
+
+WALKS = ["walk_small", "walk_c1", "walk_mid", "walk_deep"]
+
+
+@pytest.mark.parametrize("name", WALKS)
+def test_walk_matches_reference(name, oracle):
+    scene, g = load_golden_walk(name)
+    assert input_digest(scene) == str(g["digest"]), "input generators drifted from the fixture"
+    EB = scene.new_matrix_EB()
+    rng = scene.rays.rng_states.copy()
+    for _ in range(int(g["num_iter"])):
+        oracle.trace(*scene.kernel_args(EB, rng))
+    assert np.array_equal(rng, g["rng_states"]), "final RNG states differ (a ray drew a different number of times)"
+    assert np.array_equal(EB, golden_bins(g)), "eyebox bins differ"
+    assert EB.sum() > 0
+
+
+def test_walk_small_from_stored_inputs(oracle):
+    """Self-contained fixture: inputs are stored, so this pins the oracle independently of the generators."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.GPU_ray_tracing_functions import _ARG_NAMES
+    g = np.load(os.path.join(GOLDEN, "walk_small.npz"))
+    args = []
+    for nm in _ARG_NAMES[:-1]:
+        a = g["in_" + nm]
+        args.append(float(a) if nm == "n_g" else np.ascontiguousarray(a))
+    EB = np.zeros(tuple(g["eb_shape"]), dtype=np.float32)
+    rng = args[12].copy()
+    args[12] = rng
+    oracle.trace(*args, EB)
+    assert np.array_equal(rng, g["rng_states"])
+    assert np.array_equal(EB, golden_bins(g))
+
+
+def test_thread_count_invariance(oracle, small_scene):
+    res = []
+    for nt in (1, 3, 8):
+        EB = small_scene.new_matrix_EB(); rng = small_scene.rays.rng_states.copy()
+        oracle.trace(*small_scene.kernel_args(EB, rng), num_threads=nt)
+        res.append((EB, rng))
+    for EB, rng in res[1:]:
+        assert np.array_equal(EB, res[0][0]) and np.array_equal(rng, res[0][1])
+
+
+def test_xorshift_unit(oracle):
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    st, last = oracle.xorshift(g["xs_in"], 7)
+    assert np.array_equal(st, g["xs_out"])
+    assert np.array_equal(last, g["xs_last"])
+    assert np.all((last > 0) & (last < 1))
+
+
+def test_efield_unit(oracle):
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    out = oracle.efield(g["ef_ete"], g["ef_etm"], g["ef_delta"], g["ef_jones"])
+    assert np.array_equal(out, g["ef_out"])          # same libm, same operation order -> bit equal
+    assert np.all(np.abs(out[:, 2]) <= np.pi)
+
+
+@pytest.mark.parametrize("ring", ["IC", "FC", "OC", "eff_reg1", "eff_reg2"])
+def test_polygon_unit(ring, oracle):
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    pts = g[ring + "_pts"]
+    hit = oracle.locate(g[ring + "_verts"], g[ring + "_off"], pts[:, 0], pts[:, 1])
+    assert np.array_equal(hit, g[ring + "_hit"])
+    assert (hit >= 0).any() and (hit < 0).any()
+
+
+def test_counters_consistent(oracle, small_scene):
+    EB = small_scene.new_matrix_EB(); rng = small_scene.rays.rng_states.copy()
+    c = oracle.trace(*small_scene.kernel_args(EB, rng), counters=True)
+    assert c["rays"] == small_scene.rays.num_rays
+    assert c["draws"] == c["draw2"] + c["draw3"]
+    assert c["efield"] == 2 * c["draw2"] + 3 * c["draw3"]
+    assert c["deposits"] == int(EB.sum())
