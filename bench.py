@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-propagation hot path (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- the default full-colour RGB design of
+couplers_coor_full_color() at the runner's sizes (gpu_ray_tracing_pro_fullColor.py:16-17, 60-61):
+100 x 75 FoV cells x 3 wavelengths x 5000 rays per cell = 112.5 M rays per launch, bins
+3 x 75 x 100 x 80 x 120 float32 (864 MB), synthetic complex128 LUTs of the real shapes (the real
+LUT files are not reachable).  One "step" = one launch of the walk over the whole ray set, which is
+what the runner repeats num_iter = 4 times with continuing RNG streams (RUN:169-177).
+
+Printed JSON line (rank 0):
+  value    ray-bounces / s, all ranks, inputs resident in HBM, CUDA events on the launch stream
+           (a bounce = one position advance x += gap; counted exactly for the
+           timed launches by replaying them with device counters from the saved RNG states)
+  e2e      the same metric through the C ABI host entry wgrt_trace_fullcolor_host: pinned HOST
+           buffers, H2D of rays / LUTs / geometry / bins and D2H of bins + RNG states inside the
+           timed region, every step
+  roofline dominant kernel (walk_fast_kernel) against the FP64 FMA peak measured live on this GPU
+           (the path is FP64-issue bound, not HBM bound: SURVEY.md section 8d); roofline_hbm gives
+           the algorithmic-bytes view against MEASURED_PEAKS.json
+  cpu_baseline   the CPU oracle port (oracle/) on the host cores, bounded sample (rank 0, N = 1)
+Multi-GPU (torchrun): weak scaling -- every rank walks the full workload with its own RNG streams
+(more Monte-Carlo samples per FoV), then ONE NCCL all-reduce of the bin tensor inside the timed
+region.  --impl reference times the CPU oracle port on all host threads (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ray_bounces_per_s"
+UNIT = "ray-bounces/s"
+WORKLOADS = {
+    # name: (num_FOV_x, num_FOV_y, rays_per_FoV, (EBy, EBx))
+    "c2_default_fullcolor_100x75x3x5000": (100, 75, 5000, (80, 120)),
+    "small_20x15x3x2000": (20, 15, 2000, (80, 120)),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("WGRT_BENCH_WORKLOAD", "c2_default_fullcolor_100x75x3x5000"),
+                    choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_flops(c):
+    """F = 40 N_E + 30 N_draw2 + 40 N_draw3 + 8 N_straddle + 9 N_cross + 6 N_bounce."""
+    return (40 * c["efield"] + 30 * c["draw2"] + 40 * c["draw3"] + 8 * c["straddle"] + 9 * c["cross"]
+            + 6 * c["bounces"])
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def pinned_like(a: np.ndarray):
+    """A pinned host copy of ``a`` (as a torch tensor and a NumPy view of the same memory)."""
+    import torch
+    v = a.view(np.float64) if a.dtype == np.complex128 else a
+    v = v.view(np.int32) if v.dtype == np.uint32 else v
+    t = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+    return t, t.numpy().view(a.dtype).reshape(a.shape)
+
+
+# ------------------------------------------------------------------------------------------------
+def sample_scene(scene, target_rays: int):
+    """Bounded sample of the workload for CPU timing: every stride-th cell, whole cells."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import synthetic_inputs as si
+    rpc = scene.meta["num_rays_per_FoV"]
+    n_cells = scene.rays.num_rays // rpc
+    stride = max(1, int(round(n_cells * rpc / max(target_rays, 1))))
+    idx = np.arange(0, n_cells, stride)
+    sel = (idx[:, None] * rpc + np.arange(rpc)[None, :]).ravel()
+    rays = scene.rays
+    sub = si.RaySet(*(a[sel].copy() for a in rays.arrays()), rays.rng_states[sel].copy())
+    return sub, f"every {stride}th FoV-wavelength cell of the workload ({len(idx)} cells x {rpc} rays = {len(sel)} rays), one launch"
+
+
+def run_cpu_oracle(scene, sub, threads: int):
+    """Time one launch of the oracle port over the sample. Returns (seconds, counters)."""
+    from oracle import oracle
+    EB = scene.new_matrix_EB()
+    rng = sub.rng_states.copy()
+    full = scene.rays
+    scene.rays = sub
+    try:
+        args = scene.kernel_args(EB, rng)
+        t0 = time.perf_counter()
+        cnt = oracle.trace(*args, num_threads=threads, counters=True)
+        dt = time.perf_counter() - t0
+    finally:
+        scene.rays = full
+    return dt, cnt
+
+
+def reference_arm(args, nx, ny, rpc, eb):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (the
+    reference itself is Python/Numba and cannot travel to this box), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import synthetic_inputs as si
+    from oracle import oracle
+    oracle.build()
+    threads = os.cpu_count() or 1
+    scene = si.make_scene(nx, ny, rpc, eb=eb, seed=2024)
+    # size the per-step sample so that (steps + warmup) launches stay within a few minutes
+    probe, _ = sample_scene(scene, 200_000)
+    dt, cnt = run_cpu_oracle(scene, probe, threads)
+    rate = cnt["rays"] / dt
+    budget_s = min(args.cpu_seconds, 150.0 / max(args.steps + args.warmup, 1))
+    sub, desc = sample_scene(scene, int(rate * budget_s))
+    for _ in range(args.warmup):
+        run_cpu_oracle(scene, sub, threads)
+    tot_t, tot_b, tot_r = 0.0, 0, 0
+    for _ in range(args.steps):
+        dt, cnt = run_cpu_oracle(scene, sub, threads)
+        tot_t += dt; tot_b += cnt["bounces"]; tot_r += cnt["rays"]
+    value = tot_b / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / max(args.steps, 1) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": desc},
+        "rays_per_s": tot_r / tot_t,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    nx, ny, rpc, eb = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, nx, ny, rpc, eb)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, synthetic_inputs as si
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = _capi.load_library()
+
+    # ---- inputs: identical scene on every rank; rank-specific RNG streams -----------------------
+    scene = si.make_scene(nx, ny, rpc, eb=eb, seed=2024)
+    N = scene.rays.num_rays
+    scene.rays.rng_states = si.initial_rng_states(N, offset=rank * N)
+    host_args = list(scene.kernel_args(scene.new_matrix_EB()))
+
+    def to_dev(a):
+        if not isinstance(a, np.ndarray):
+            return a
+        v = a.view(np.float64) if a.dtype == np.complex128 else a
+        t = torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda()
+        return GRTF._TorchAlias(t, a.shape, a.dtype)
+
+    dev_args = [None if i in (2, 3, 4, 5) else to_dev(a) for i, a in enumerate(host_args)]
+    rng_t, eb_t = dev_args[12]._t, dev_args[32]._t
+    stream = torch.cuda.current_stream()
+    kern = GRTF.process_rays_kernel_pro_fullColor
+    launch = kern[(N + 255) // 256, 256, stream]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        launch(*dev_args)
+    torch.cuda.synchronize()
+    eb_t.zero_()
+    rng_saved = rng_t.clone()
+
+    # ---- timed region: K launches (+ one NCCL all-reduce of the bins when N > 1) -----------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 2)]
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ev[0].record(stream)
+        for k in range(args.steps):
+            launch(*dev_args)
+            ev[k + 1].record(stream)
+        if world > 1:
+            dist.all_reduce(eb_t)
+        ev[args.steps + 1].record(stream)
+        barrier()
+    total_ms = ev[0].elapsed_time(ev[args.steps + 1])
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    deposits_total = float(eb_t.sum(dtype=torch.float64).item())
+
+    # ---- exact event counts of the timed launches: replay them with device counters -------------
+    rng_t.copy_(rng_saved)
+    scratch_eb = torch.zeros_like(eb_t)
+    count_args = list(dev_args)
+    count_args[32] = GRTF._TorchAlias(scratch_eb, host_args[32].shape, np.float32)
+    _capi.reset_counters()
+    counted = kern.configured(counters=True)[1, 256, stream]
+    for _ in range(args.steps):
+        counted(*count_args)
+    cnt = _capi.read_counters()
+    del scratch_eb
+    bt = torch.tensor([cnt["bounces"], cnt["rays"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(bt)
+    bounces_all, rays_all = float(bt[0].item()), float(bt[1].item())
+    value = bounces_all / (total_ms_max * 1e-3)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "num_FOV_x": nx, "num_FOV_y": ny, "wavelengths": 3,
+                   "rays_per_FoV": rpc, "rays_per_launch_per_gpu": N, "eyebox_bins": list(eb),
+                   "l2_policy": "inputs (4.1 GB of ray state per launch) exceed the 126 MB L2; no flush needed",
+                   "partition": "replicated design, rank-specific RNG streams, one NCCL all-reduce of the bins"
+                   if world > 1 else "single GPU"},
+        "rays_per_s": rays_all / (total_ms_max * 1e-3),
+        "full_colour_wall_ms": total_ms_max,
+        "bounces_per_ray": bounces_all / max(rays_all, 1),
+        "deposits": deposits_total,
+        "step_ms_rank0": step_ms,
+        "gpu_launches": args.steps * 5,   # per launch: 3 region-index kernels, tile pick, walk
+        "clocks": clocks.summary(),
+    }
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (walk_fast_kernel) ---------------------------------
+        # literal-algorithm work per launch (straddling edges / cross products only exist in the
+        # literal scan): one strict launch with counters from the same RNG states
+        rng_t.copy_(rng_saved)
+        scratch_eb = torch.zeros_like(eb_t)
+        count_args[32] = GRTF._TorchAlias(scratch_eb, host_args[32].shape, np.float32)
+        _capi.reset_counters()
+        kern.configured(strict=True, counters=True)[1, 256, stream](*count_args)
+        cs = _capi.read_counters()
+        del scratch_eb
+        flops_per_launch = algorithmic_flops(cs)
+        p64, p32 = C.c_double(), C.c_double()
+        _capi.check(lib.wgrt_debug_fma_peak(C.byref(p64), C.byref(p32)), lib)
+        walk_ms = float(np.mean(step_ms))         # region-index + tile-pick kernels are < 0.1 % of it
+        ach = flops_per_launch / (walk_ms * 1e-3) / 1e12
+        line["roofline"] = {
+            "kernel": "walk_fast_kernel", "bound": "fp64", "achieved": ach, "peak": p64.value, "unit": "TFLOP/s",
+            "frac": ach / p64.value, "traffic": load_traffic(),
+            "peak_source": "DFMA chain micro-benchmark run live in this process (wgrt_debug_fma_peak)",
+            "algorithmic_flops_per_ray": flops_per_launch / max(cs["rays"], 1),
+            "fp32_peak_tflops": p32.value,
+        }
+        peaks, src = measured_peaks()
+        cells = nx * ny * 3
+        alg_bytes = 40.0 * N + cells * 93e3            # 40 B/ray + ~93 KB per cell
+        gbs = alg_bytes / (walk_ms * 1e-3) / 1e9
+        line["roofline_hbm"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": gbs / peaks["hbm_gbs"], "peak_source": src,
+                                "algorithmic_bytes_per_launch": alg_bytes}
+        rng_t.copy_(rng_saved)
+
+    # ---- end to end through the C ABI with pinned host buffers -----------------------------------
+    if not args.no_e2e:
+        rng_saved_host = None
+        del dev_args, count_args
+        torch.cuda.empty_cache()
+        pinned = []
+        e2e_args = []
+        for i, a in enumerate(host_args):
+            if isinstance(a, np.ndarray) and i not in (2, 3, 4, 5):
+                tpin, view = pinned_like(a)
+                pinned.append(tpin)
+                e2e_args.append(view)
+            elif i in (2, 3, 4, 5):
+                e2e_args.append(None)
+            else:
+                e2e_args.append(a)
+        rng_host0 = rng_saved.cpu().numpy().view(np.uint32).copy()   # same streams as the timed launches
+        prob, keep = GRTF.pack_problem(e2e_args, host=True)
+        h2d = sum(a.nbytes for i, a in enumerate(e2e_args) if isinstance(a, np.ndarray))
+        d2h = e2e_args[12].nbytes + e2e_args[32].nbytes
+        tms = (C.c_float * 3)()
+        for _ in range(2):
+            _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 1, tms), lib)
+        e2e_args[12][...] = rng_host0
+        e2e_args[32][...] = 0
+        _capi.reset_counters()
+        prob.flags = 0
+        barrier()
+        t0 = time.perf_counter()
+        parts = np.zeros(3)
+        for _ in range(args.steps):
+            _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 1, tms), lib)
+            parts += np.array(list(tms))
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        # same RNG streams as the timed device-resident launches -> same bounce count
+        line["e2e"] = {"value": bounces_all / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tw.item()) / max(args.steps, 1) * 1e3,
+                       "breakdown_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
+                                                       "d2h": parts[2] / args.steps},
+                       "api": "wgrt_trace_fullcolor_host (pinned host buffers, 1 launch per call)"}
+        e2e_deposits = float(e2e_args[32].sum(dtype=np.float64))
+        line["e2e"]["deposits_match_device_run"] = bool(world > 1 or e2e_deposits == deposits_total)
+
+    # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        threads = os.cpu_count() or 1
+        probe, _ = sample_scene(scene, 200_000)
+        dt, c0 = run_cpu_oracle(scene, probe, threads)
+        sub, desc = sample_scene(scene, int(c0["rays"] / dt * args.cpu_seconds))
+        dt, c1 = run_cpu_oracle(scene, sub, threads)
+        line["cpu_baseline"] = {"value": c1["bounces"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": desc, "seconds": dt, "rays_per_s": c1["rays"] / dt}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    """DRAM bytes per launch of walk_fast_kernel from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "walk_fast_traffic.json")) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except OSError:
+        return None
+
+
+if __name__ == "__main__":
+    main()

@@ -55,10 +55,10 @@ _lib: Optional[C.CDLL] = None
 
 # every symbol include/wgrt.h declares
 EXPORTED_SYMBOLS = (
-    "wgrt_version", "wgrt_last_error", "wgrt_device_count", "wgrt_release",
+    "wgrt_version", "wgrt_problem_size", "wgrt_last_error", "wgrt_device_count", "wgrt_release",
     "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host",
     "wgrt_counters_read", "wgrt_counters_reset",
-    "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift",
+    "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
     "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host",
 )
 
@@ -76,6 +76,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
             "(needs nvcc). There is no CPU fallback.")
     lib = C.CDLL(p)
     lib.wgrt_version.restype = C.c_int
+    lib.wgrt_problem_size.restype = C.c_int
+    if lib.wgrt_problem_size() != C.sizeof(WgrtProblem):
+        raise WgrtError("wgrt_problem_t layout mismatch between _capi.py and libwgrt.so")
     lib.wgrt_last_error.restype = C.c_char_p
     lib.wgrt_device_count.restype = C.c_int
     lib.wgrt_release.restype = C.c_int
@@ -93,6 +96,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_debug_efield.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
     lib.wgrt_debug_xorshift.restype = C.c_int
     lib.wgrt_debug_xorshift.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.wgrt_debug_fma_peak.restype = C.c_int
+    lib.wgrt_debug_fma_peak.argtypes = [C.c_void_p, C.c_void_p]
     lib.wgrt_eval_pupil_sums.restype = C.c_int
     lib.wgrt_eval_pupil_sums.argtypes = [C.c_void_p] + [C.c_int64] * 5 + [C.c_int] * 3 + \
         [C.c_void_p, C.c_void_p, C.c_void_p]

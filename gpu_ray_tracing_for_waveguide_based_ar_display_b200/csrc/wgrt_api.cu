@@ -139,7 +139,9 @@ int validate(const wgrt_problem_t* p) {
     return fail(WGRT_ERR_INVALID, "negative vertex count");
 #define NEED(f) \
   if (!p->f) return fail(WGRT_ERR_INVALID, "null pointer: " #f)
-  NEED(x); NEED(y); NEED(m); NEED(n); NEED(lmd_num); NEED(te); NEED(tm); NEED(delta_phase); NEED(rng_states);
+  if (p->num_rays > 0) {
+    NEED(x); NEED(y); NEED(m); NEED(n); NEED(lmd_num); NEED(te); NEED(tm); NEED(delta_phase); NEED(rng_states);
+  }
   NEED(IC); NEED(FC); NEED(FC_offset); NEED(OC); NEED(OC_offset); NEED(eff_reg1); NEED(eff_reg2);
   NEED(eff_reg_FOV); NEED(eff_reg_FOV_range); NEED(lut_ic1); NEED(lut_ic2); NEED(lut_ic3); NEED(lut_fc1);
   NEED(lut_fc2); NEED(lut_oc1); NEED(lut_oc2); NEED(lut_TIR); NEED(lut_gap); NEED(matrix_EB);
@@ -182,6 +184,8 @@ size_t padded(size_t b) { return ((b + 255) & ~size_t(255)) + 256; }
 extern "C" {
 
 int wgrt_version(void) { return WGRT_VERSION; }
+
+int wgrt_problem_size(void) { return static_cast<int>(sizeof(wgrt_problem_t)); }
 
 const char* wgrt_last_error(void) { return g_err; }
 
@@ -394,6 +398,17 @@ int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last
     CUDA_TRY(cudaMemcpy(states, d_s, (size_t)n * 4, cudaMemcpyDeviceToHost));
     if (out_last) CUDA_TRY(cudaMemcpy(out_last, d_u, (size_t)n * 8, cudaMemcpyDeviceToHost));
   }
+  return WGRT_OK;
+}
+
+int wgrt_debug_fma_peak(double* fp64_tflops, double* fp32_tflops) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!fp64_tflops || !fp32_tflops) return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(launch_fma_peak(w->num_sms, fp64_tflops, fp32_tflops));
   return WGRT_OK;
 }
 

@@ -266,6 +266,25 @@ __global__ void xorshift_kernel(uint32_t* states, int64_t n, int draws, double* 
   if (out_last) out_last[i] = u;
 }
 
+// Peak probes: 8 independent FMA chains per thread, long enough to be issue bound.  Explicit
+// fma intrinsics: this translation unit is built with -fmad=false.
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* sink, int iters, T a, T b) {
+  T acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = static_cast<T>(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = fma_t(acc[k], a, b);
+  }
+  T s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += acc[k];
+  if (s == static_cast<T>(-1234.5)) sink[0] = s;
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
 }  // namespace
@@ -292,6 +311,41 @@ cudaError_t launch_debug_efield(const double* ete, const double* etm, const doub
   if (n == 0) return cudaSuccess;
   efield_kernel<<<blocks_for(n, 128), 128, 0, s>>>(ete, etm, delta, jones, n, out);
   return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t time_fma(int num_sms, double* tflops) {
+  T* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(T));
+  if (e != cudaSuccess) return e;
+  const int blocks = num_sms * 8, threads = 256, iters = 8192;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a);
+    fma_peak_kernel<T><<<blocks, threads>>>(sink, iters, static_cast<T>(1.0000001), static_cast<T>(1e-7));
+    cudaEventRecord(b);
+    e = cudaEventSynchronize(b);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(sink);
+  if (e != cudaSuccess) return e;
+  const double flops = 2.0 * 8.0 * iters * static_cast<double>(blocks) * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflops) {
+  cudaError_t e = time_fma<double>(num_sms, fp64_tflops);
+  if (e != cudaSuccess) return e;
+  return time_fma<float>(num_sms, fp32_tflops);
 }
 
 cudaError_t launch_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last, cudaStream_t s) {

@@ -125,6 +125,8 @@ typedef struct wgrt_problem {
 
 /* Library / runtime ------------------------------------------------------------------------ */
 int wgrt_version(void);
+/* sizeof(wgrt_problem_t) as compiled into the library: ABI guard for FFI bindings */
+int wgrt_problem_size(void);
 const char* wgrt_last_error(void);
 /* number of CUDA devices visible, or WGRT_ERR_NO_DEVICE */
 int wgrt_device_count(void);
@@ -171,6 +173,13 @@ int wgrt_debug_efield(const double* ete, const double* etm, const double* delta,
 /* get_uniform_random_number (GPU_ray_tracing_functions.py:25-34): advance each state `draws`
  * times; out_last[i] = last uniform of stream i. */
 int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last);
+
+/*
+ * Roofline denominators measured on the current device: achieved FP64 FMA rate of a pure
+ * dependent-chain DFMA kernel that fills every SM (TFLOP/s, 2 flops per FMA) and the same for FP32.
+ * Used by bench.py because MEASURED_PEAKS.json records HBM and tensor peaks only.
+ */
+int wgrt_debug_fma_peak(double* fp64_tflops, double* fp32_tflops);
 
 /*
  * Evaluation reductions on the bin tensor:

@@ -1,0 +1,239 @@
+"""GPU parity tests: the CUDA engine (through the C ABI / the reference-shaped kernel object) against
+the CPU oracle, the committed golden vectors, and size-independent invariants.  Bar: bit-exact
+matrix_EB (integer counts stored in float32) and bit-exact final rng_states (=> identical number of
+draws per ray)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_bins, load_golden_walk
+
+pytestmark = pytest.mark.gpu
+
+from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
+from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, synthetic_inputs as si
+from gpu_ray_tracing_for_waveguide_based_ar_display_b200.couplers_coor import WaveguideDesign
+
+KERNEL = GRTF.process_rays_kernel_pro_fullColor
+STRICT = KERNEL.configured(strict=True)
+
+
+def run_engine(kernel, scene, num_iter=1, EB=None, rng=None):
+    EB = scene.new_matrix_EB() if EB is None else EB
+    rng = scene.rays.rng_states.copy() if rng is None else rng
+    for _ in range(num_iter):
+        kernel[(scene.rays.num_rays + 255) // 256, 256](*scene.kernel_args(EB, rng))
+    return EB, rng
+
+
+def run_oracle(oracle, scene, num_iter=1):
+    EB = scene.new_matrix_EB(); rng = scene.rays.rng_states.copy()
+    for _ in range(num_iter):
+        oracle.trace(*scene.kernel_args(EB, rng))
+    return EB, rng
+
+
+def assert_same(a, b, what):
+    EBa, ra = a; EBb, rb = b
+    bad = np.flatnonzero(ra != rb)
+    assert bad.size == 0, f"{what}: rng_states differ for {bad.size} rays, first {bad[:8]}"
+    assert np.array_equal(EBa, EBb), f"{what}: matrix_EB differs in {np.count_nonzero(EBa != EBb)} bins"
+
+
+# ---------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", ["walk_small", "walk_c1", "walk_mid", "walk_deep"])
+@pytest.mark.parametrize("mode", ["fast", "strict"])
+def test_golden_fixture(name, mode):
+    scene, g = load_golden_walk(name)
+    got = run_engine(KERNEL if mode == "fast" else STRICT, scene, int(g["num_iter"]))
+    assert_same(got, (golden_bins(g), g["rng_states"]), f"{name}/{mode}")
+    assert got[0].sum() > 0
+
+
+# ---------------------------------------------------------------------------- oracle, seeded inputs
+@pytest.mark.parametrize("cfg", [
+    dict(nx=5, ny=5, rays=64, seed=101, lmd=[1]),                 # BASELINE config 1 shape
+    dict(nx=7, ny=4, rays=300, seed=102, lmd=None),
+    dict(nx=3, ny=2, rays=2, seed=103, lmd=None),                 # ragged: one TE + one TM ray per cell
+    dict(nx=2, ny=2, rays=5000, seed=104, lmd=None),              # runner-sized cells
+])
+def test_against_oracle(cfg, oracle):
+    scene = si.make_scene(cfg["nx"], cfg["ny"], cfg["rays"], seed=cfg["seed"], lmd_subset=cfg["lmd"])
+    want = run_oracle(oracle, scene, 2)
+    assert_same(run_engine(KERNEL, scene, 2), want, "fast")
+    assert_same(run_engine(STRICT, scene, 2), want, "strict")
+
+
+def test_deep_walks_against_oracle(oracle):
+    """Divergence stress: thin plate, wide FoV, 15 fold slices, strong turn orders (BASELINE config 5)."""
+    d = WaveguideDesign(t=0.3, num_FC=15, fov_x_deg=24.0)
+    eff = dict(incouple=0.9, incouple_m1=0.08, ic_zero=0.9, ic_cross=0.05, fc_zero=0.6, fc_turn=0.3,
+               oc_zero=0.85, oc_cross=0.06, outcouple=0.05)
+    scene = si.make_scene(4, 3, 600, seed=7, design=d, eff=eff)
+    want = run_oracle(oracle, scene)
+    assert_same(run_engine(KERNEL, scene), want, "fast/deep")
+    assert_same(run_engine(STRICT, scene), want, "strict/deep")
+    assert want[0].sum() > 50
+
+
+def test_fine_eyebox_grid(oracle):
+    """BASELINE config 4: high-resolution bins."""
+    scene = si.make_scene(3, 3, 800, eb=(320, 480), seed=12,
+                          eff=dict(incouple=0.9, ic_zero=0.95, fc_zero=0.8, fc_turn=0.15, outcouple=0.1))
+    assert_same(run_engine(KERNEL, scene), run_oracle(oracle, scene), "fast/fine-eyebox")
+
+
+def test_shuffled_ray_order(oracle):
+    """Rays need not arrive cell by cell: any order must give the same per-ray results."""
+    scene = si.make_scene(4, 3, 40, seed=31)
+    perm = np.random.default_rng(0).permutation(scene.rays.num_rays)
+    rays = scene.rays
+    scene.rays = si.RaySet(*(a[perm].copy() for a in rays.arrays()), rays.rng_states[perm].copy())
+    want = run_oracle(oracle, scene)
+    assert_same(run_engine(KERNEL, scene), want, "fast/shuffled")
+
+
+def test_empty_and_invalid_inputs(oracle):
+    scene = si.make_scene(3, 2, 20, seed=8)
+    empty = scene.rays.take(slice(0, 0))
+    full = scene.rays
+    scene.rays = empty
+    EB, rng = run_engine(KERNEL, scene)
+    assert EB.sum() == 0 and rng.size == 0
+    scene.rays = full
+    # rays that point outside the LUT grid are skipped and leave their RNG state untouched
+    bad = full.take(slice(0, full.num_rays))
+    bad.m[:7] = 99.0
+    bad.lmd_num[7:11] = -1.0
+    scene.rays = bad
+    for k in (KERNEL, STRICT):
+        EB, rng = run_engine(k, scene)
+        assert np.array_equal(rng[:11], bad.rng_states[:11])
+    scene.rays = full
+    with pytest.raises(TypeError):
+        args = list(scene.kernel_args(scene.new_matrix_EB())); args[0] = args[0].astype(np.float64)
+        KERNEL[1, 256](*args)
+
+
+# ---------------------------------------------------------------------------- invariants
+def test_tile_size_and_launch_split_invariance():
+    scene = si.make_scene(5, 4, 500, seed=44)
+    base = run_engine(KERNEL, scene)
+    for tile in (32, 97, 1000, 100000):
+        assert_same(run_engine(KERNEL.configured(tile_hint=tile), scene), base, f"tile={tile}")
+    # two half launches == one launch (per-ray RNG, additive bins)
+    N = scene.rays.num_rays
+    EB = scene.new_matrix_EB(); rng = scene.rays.rng_states.copy()
+    full = scene.rays
+    for sl in (slice(0, N // 3), slice(N // 3, N)):
+        scene.rays = full.take(sl)
+        part_rng = scene.rays.rng_states
+        run_engine(KERNEL, scene, EB=EB, rng=part_rng)
+        rng[sl] = part_rng
+    scene.rays = full
+    assert_same((EB, rng), base, "split launches")
+
+
+def test_fast_equals_strict_at_scale():
+    """Too large for the CPU oracle in seconds: pin the fast engine on the literal GPU walk."""
+    scene = si.make_scene(20, 15, 2000, seed=77)          # 1.8 M rays
+    a = run_engine(KERNEL, scene, 2)
+    b = run_engine(STRICT, scene, 2)
+    assert_same(a, b, "fast vs strict, 1.8M rays x 2")
+    # conservation: one deposit at most per ray per launch
+    assert 0 < a[0].sum() <= 2 * scene.rays.num_rays
+    assert np.all(a[0] == np.round(a[0]))
+
+
+def test_counters_match_oracle(oracle):
+    scene = si.make_scene(4, 3, 100, seed=19)
+    EB = scene.new_matrix_EB(); rng = scene.rays.rng_states.copy()
+    want = oracle.trace(*scene.kernel_args(EB, rng), counters=True)
+    for kern, keys in ((KERNEL.configured(counters=True),
+                        ("rays", "bounces", "draws", "draw2", "draw3", "efield", "iters", "deposits")),
+                       (STRICT.configured(counters=True),
+                        ("rays", "bounces", "draws", "draw2", "draw3", "efield", "iters", "deposits",
+                         "poly_tests", "edge_visits", "straddle", "cross"))):
+        _capi.reset_counters()
+        run_engine(kern, scene)
+        got = _capi.read_counters()
+        for k in keys:
+            assert got[k] == want[k], (k, got[k], want[k])
+
+
+# ---------------------------------------------------------------------------- buffers / boundary
+def test_device_buffers_zero_copy_and_stream(oracle):
+    import torch
+    scene = si.make_scene(4, 3, 64, seed=3)
+    want = run_oracle(oracle, scene)
+    dev = []
+    for a in scene.kernel_args(scene.new_matrix_EB()):
+        if isinstance(a, np.ndarray):
+            v = a.view(np.float64) if a.dtype == np.complex128 else a
+            t = torch.from_numpy(v.view(np.int32) if v.dtype == np.uint32 else v).cuda()
+            dev.append(GRTF._TorchAlias(t, a.shape, a.dtype))
+        else:
+            dev.append(a)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        KERNEL[1, 256, s](*dev)
+    s.synchronize()
+    rng = dev[12]._t.cpu().numpy().view(np.uint32)
+    EB = dev[32]._t.cpu().numpy()
+    assert_same((EB, rng), want, "device buffers")
+
+
+def test_host_entry_point(oracle):
+    """wgrt_trace_fullcolor_host: the RUN:145-185 region for host buffers, num_iter launches."""
+    scene = si.make_scene(4, 3, 64, seed=3)
+    want = run_oracle(oracle, scene, 3)
+    EB = scene.new_matrix_EB(); rng = scene.rays.rng_states.copy()
+    prob, keep = GRTF.pack_problem(scene.kernel_args(EB, rng), host=True)
+    lib = _capi.load_library()
+    tms = (C.c_float * 3)()
+    _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 3, tms), lib)
+    assert_same((EB, rng), want, "host entry")
+    assert all(t >= 0 for t in tms)
+
+
+# ---------------------------------------------------------------------------- unit-level parity
+def test_xorshift_unit(oracle):
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    lib = _capi.load_library()
+    st = g["xs_in"].copy(); last = np.zeros(len(st))
+    _capi.check(lib.wgrt_debug_xorshift(st.ctypes.data, len(st), 7, last.ctypes.data), lib)
+    assert np.array_equal(st, g["xs_out"]) and np.array_equal(last, g["xs_last"])
+
+
+def test_efield_unit():
+    """libdevice vs the reference's CPU libm: same algebra, last-bit differences allowed.
+    Tolerance 1e-12 absolute on amplitudes, 1e-9 on the wrapped phase away from the +-pi seam."""
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    lib = _capi.load_library()
+    ete, etm, delta = (np.ascontiguousarray(g[k]) for k in ("ef_ete", "ef_etm", "ef_delta"))
+    n = len(ete)
+    out = np.zeros((n, 3))
+    jones = np.ascontiguousarray(g["ef_jones"])
+    _capi.check(lib.wgrt_debug_efield(ete.ctypes.data, etm.ctypes.data, delta.ctypes.data,
+                                      jones.ctypes.data, n, out.ctypes.data), lib)
+    ref = g["ef_out"]
+    np.testing.assert_allclose(out[:, :2], ref[:, :2], rtol=0, atol=1e-12)
+    d = np.abs(out[:, 2] - ref[:, 2])
+    d = np.minimum(d, 2 * np.pi - d)
+    assert np.all(d < 1e-9)
+
+
+@pytest.mark.parametrize("ring", ["IC", "FC", "OC", "eff_reg1", "eff_reg2"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_polygon_unit_golden(ring, mode):
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    lib = _capi.load_library()
+    verts = np.ascontiguousarray(g[ring + "_verts"]); off = np.ascontiguousarray(g[ring + "_off"])
+    pts = g[ring + "_pts"]
+    px = np.ascontiguousarray(pts[:, 0]); py = np.ascontiguousarray(pts[:, 1])
+    out = np.zeros(len(px), dtype=np.int32)
+    _capi.check(lib.wgrt_debug_locate(verts.ctypes.data, len(verts), off.ctypes.data, len(off) - 1,
+                                      px.ctypes.data, py.ctypes.data, len(px), out.ctypes.data, mode), lib)
+    assert np.array_equal(out, g[ring + "_hit"])
