@@ -57,7 +57,7 @@ struct DeviceBuf {
 struct Workspace {
   int device = -1;
   int num_sms = 0;
-  DeviceBuf cells[NUM_REGIONS], rowmask[NUM_REGIONS];
+  DeviceBuf cells[NUM_REGIONS], detail[NUM_REGIONS], rowmask[NUM_REGIONS];
   DeviceBuf small;   // RegionDyn[NUM_REGIONS] | work counter + tile size | counters
   DeviceBuf arena;   // staging for the host entry points
   RegionDyn* dyn() { return static_cast<RegionDyn*>(small.ptr); }
@@ -66,7 +66,7 @@ struct Workspace {
     return reinterpret_cast<unsigned long long*>(static_cast<char*>(small.ptr) + 1024);
   }
   void release() {
-    for (int r = 0; r < NUM_REGIONS; ++r) { cells[r].release(); rowmask[r].release(); }
+    for (int r = 0; r < NUM_REGIONS; ++r) { cells[r].release(); detail[r].release(); rowmask[r].release(); }
     small.release();
     arena.release();
   }
@@ -78,7 +78,7 @@ std::vector<Workspace> g_ws;
 int grid_resolution() {
   static int res = [] {
     const char* e = getenv("WGRT_GRID");
-    int v = e ? atoi(e) : 256;
+    int v = e ? atoi(e) : 1024;
     if (v < 8) v = 8;
     if (v > 4096) v = 4096;
     return v;
@@ -118,8 +118,10 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
     st.ny = res;
     st.words = (st.nverts + 31) / 32;
     CUDA_TRY(w.cells[r].reserve(static_cast<size_t>(st.nx) * st.ny));
+    CUDA_TRY(w.detail[r].reserve(static_cast<size_t>(st.nx) * st.ny * sizeof(uint32_t)));
     CUDA_TRY(w.rowmask[r].reserve(static_cast<size_t>(st.ny) * (st.words > 0 ? st.words : 1) * sizeof(uint32_t)));
     st.cells = static_cast<uint8_t*>(w.cells[r].ptr);
+    st.detail = static_cast<uint32_t*>(w.detail[r].ptr);
     st.rowmask = static_cast<uint32_t*>(w.rowmask[r].ptr);
   }
   rs.dyn = w.dyn();

@@ -145,6 +145,7 @@ struct RegionStatic {          // host-known part of one region set
   const double* verts;         // [V,2]
   const int64_t* offsets;      // [npoly+1]; nullptr = one ring [0, nverts)
   uint8_t* cells;              // [ny*nx] cell codes
+  uint32_t* detail;            // [ny*nx] ring range to test exactly in ambiguous cells
   uint32_t* rowmask;           // [ny][words] edges relevant to each cell row
   int nverts, npoly, nx, ny, words;
 };

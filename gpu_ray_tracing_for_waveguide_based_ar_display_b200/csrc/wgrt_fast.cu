@@ -78,8 +78,25 @@ struct alignas(16) CellConst {
   double rect[8];   // eff_reg_FOV[m, n, :, :]
   double range[4];  // eff_reg_FOV_range[m, n, :]
   double inv_cos_in;
-  int rowbase[8];   // first table row of each region state (index ST_INIT = in-coupling)
+  int sinfo[8];     // per region state (index ST_INIT = in-coupling): see SI_* below
 };
+
+// sinfo bit layout: which region set decides the event, where the state's rows start, how many rows
+// per coupler slice, whether the walk loop's effective-region test applies, what a miss means.
+enum : int {
+  SI_REGION_MASK = 7, SI_REGION_NONE = 7,       // bits 0-2
+  SI_ROWBASE_SHIFT = 3, SI_ROWBASE_MASK = 0xfff,   // bits 3-14
+  SI_STRIDE_SHIFT = 15,                            // bits 15-16
+  SI_MISS_SHIFT = 17,                              // bits 17-18: 0 bounce on, 1 test eff_reg2 first, 2 lost
+  SI_PHASE_SHIFT = 19,                             // bit 19: which doubled TIR phase a free bounce adds
+  SI_IN_LOOP = 1 << 20                             // bit 20: GRTF:906 applies (every state but in-coupling)
+};
+__host__ __device__ constexpr int make_sinfo(int region, int rowbase, int stride, int miss, int phase, bool in_loop) {
+  return region | (rowbase << SI_ROWBASE_SHIFT) | (stride << SI_STRIDE_SHIFT) | (miss << SI_MISS_SHIFT) |
+         (phase << SI_PHASE_SHIFT) | (in_loop ? SI_IN_LOOP : 0);
+}
+constexpr long long META_THREE = 1ll << 9;   // on the first row of an event: the event has three orders
+constexpr long long META_GATED = 1ll << 10;  // ... and its branches carry `and ener_k > threshold`
 
 struct WalkShared {
   Region reg[NUM_REGIONS];
@@ -144,7 +161,9 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     if (sp.fmode == 2) f = c_new / p.n_g;
     row[8] = f;
     row[9] = 1.0 / c_new;
-    const long long meta = (sp.tir & 3) | ((sp.gap & 3) << 2) | ((sp.nstate & 7) << 4) | ((sp.post & 3) << 7);
+    long long meta = (sp.tir & 3) | ((sp.gap & 3) << 2) | ((sp.nstate & 7) << 4) | ((sp.post & 3) << 7);
+    if (ev >= EV_S4) meta |= META_THREE;
+    if (ev >= EV_S2) meta |= META_GATED;
     row[10] = __longlong_as_double(meta);
     row[11] = 0.0;
   }
@@ -165,9 +184,14 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
   } else if (t == 24) {
     cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
   } else if (t == 25) {
-    cc.rowbase[0] = 2; cc.rowbase[1] = 4; cc.rowbase[2] = 6; cc.rowbase[3] = 6 + 2 * nFC;
-    cc.rowbase[4] = 6 + 4 * nFC; cc.rowbase[5] = 6 + 4 * nFC + 3 * nOC; cc.rowbase[ST_INIT] = 0;
-    cc.rowbase[7] = 0;
+    cc.sinfo[0] = make_sinfo(SI_REGION_NONE, 2, 0, 0, 0, true);
+    cc.sinfo[1] = make_sinfo(SI_REGION_NONE, 4, 0, 0, 0, true);
+    cc.sinfo[2] = make_sinfo(REG_FC, 6, 2, 0, 0, true);                         // miss: bounce, 2 T[0]
+    cc.sinfo[3] = make_sinfo(REG_FC, 6 + 2 * nFC, 2, 1, 1, true);               // miss: eff_reg2 test, 2 T[1]
+    cc.sinfo[4] = make_sinfo(REG_OC, 6 + 4 * nFC, 3, 0, 1, true);               // miss: bounce, 2 T[1]
+    cc.sinfo[5] = make_sinfo(REG_OC, 6 + 4 * nFC + 3 * nOC, 3, 2, 0, true);     // miss: lost
+    cc.sinfo[ST_INIT] = make_sinfo(SI_REGION_NONE, 0, 0, 0, 0, false);
+    cc.sinfo[7] = 0;
   }
 }
 
@@ -190,109 +214,153 @@ __device__ __forceinline__ void jones_apply(const double* __restrict__ e, double
   otm = cplx{L1.re * a + (L3.re * w.re - L3.im * w.im), L1.im * a + (L3.re * w.im + L3.im * w.re)};
 }
 
+// One step of every ray a warp holds.  ALL 32 lanes call this (lanes without a ray idle through
+// it): the step is cut into phases separated by __syncwarp(), so that after each divergent piece --
+// a region query that fell back to the exact edge scan, the free-bounce branch, three-order events
+// -- the warp is whole again before the next piece.  Everything state dependent comes out of
+// shared-memory tables (sinfo, the event rows and their meta words): lanes run the same
+// instructions whatever region state their rays are in.
 template <bool COUNT>
 __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& sh, const double* __restrict__ tab,
                                           int64_t lm, int64_t m, int64_t n, Ray& r, Counts* cn) {
   const CellConst& cc = sh.cc;
-  if (r.state != ST_INIT) {
-    if (++r.iter > 100000) { r.state = ST_DEAD; return; }  // GRTF:905
+  const bool live = r.state != ST_DEAD;
+  const int sinfo = live ? cc.sinfo[r.state] : 0;
+  bool lost = false;  // the ray ends in this step
+
+  // ---- phase 1: the loop's effective-region test (GRTF:905-907) -----------------------------
+  if (live && (sinfo & SI_IN_LOOP)) {
     if (COUNT) cn->c[WGRT_CNT_ITERS]++;
-    if (region_locate<COUNT>(sh.reg[REG_R1], r.x, r.y, cn) < 0) { r.state = ST_DEAD; return; }  // GRTF:906
+    if (++r.iter > 100000 || region_locate<COUNT>(sh.reg[REG_R1], r.x, r.y, cn) < 0) lost = true;
   }
-  int row;
-  if (r.state == ST_INIT || r.state <= 1) {
-    row = cc.rowbase[r.state];
-  } else {
-    const int hit = region_locate<COUNT>(sh.reg[r.state <= 3 ? REG_FC : REG_OC], r.x, r.y, cn);
-    row = hit < 0 ? -1 : cc.rowbase[r.state] + (r.state <= 3 ? 2 : 3) * hit;
-  }
+  __syncwarp();
 
-  if (row < 0) {
-    // no grating under the ray: free TIR bounce (GRTF:1049-1052, 1102-1108, 1175-1178, 1244-1246)
-    if (r.state == 5) { r.state = ST_DEAD; return; }
-    if (r.state == 3 && region_locate<COUNT>(sh.reg[REG_R2], r.x, r.y, cn) < 0) { r.state = 4; return; }
-    r.x += r.gx;
-    r.y += r.gy;
-    r.w = cmul(r.w, cc.ph2[r.state == 2 ? 0 : 1]);
-    if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
-    return;
-  }
+  // ---- phase 2: which coupler slice is under the ray ------------------------------------------
+  int hit = 0;
+  const int region = sinfo & SI_REGION_MASK;
+  if (live && !lost && region != SI_REGION_NONE) hit = region_locate<COUNT>(sh.reg[region], r.x, r.y, cn);
+  __syncwarp();
 
-  const bool three = r.state == 4 || r.state == 5;
-  const bool gated = r.state >= 2 && r.state <= 5;  // `and ener_k > threshold` only in these states
-  const double* e = tab + row * ENTRY_DOUBLES;
-  cplx ote, otm;
-  jones_apply(e, r.a, r.w, ote, otm);
-  const double e1 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[8] * r.inv_cos;
-  jones_apply(e + ENTRY_DOUBLES, r.a, r.w, ote, otm);
-  const double e2 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[ENTRY_DOUBLES + 8] * r.inv_cos;
-  double e3 = 0.0;
-  if (three) {
-    jones_apply(e + 2 * ENTRY_DOUBLES, r.a, r.w, ote, otm);
-    e3 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[2 * ENTRY_DOUBLES + 8] * r.inv_cos;
-  }
-  const double u = xorshift_draw(r.rng, r.idx);
-  if (COUNT) {
-    cn->c[WGRT_CNT_DRAWS]++;
-    cn->c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
-    cn->c[WGRT_CNT_EFIELD] += three ? 3 : 2;
-  }
-  int sel;
-  double esel;
-  if (u <= e1 && (!gated || r.ener * e1 > 0.0)) { sel = 0; esel = e1; }
-  else if (u <= e1 + e2 && (!gated || r.ener * e2 > 0.0)) { sel = 1; esel = e2; }
-  else if (three && u <= e1 + e2 + e3 && r.ener * e3 > 0.0) { sel = 2; esel = e3; }
-  else { r.state = ST_DEAD; return; }
-
-  e += sel * ENTRY_DOUBLES;
-  const long long meta = __double_as_longlong(e[10]);
-  const int post = static_cast<int>((meta >> 7) & 3);
-  if (post == POST_DEPOSIT) {
-    // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
-    if (inside_or_on_edge_literal<COUNT>(r.x, r.y, cc.rect, 0, 4, cn)) {
-      deposit_bin(p, lm, m, n, r.x, r.y, cc.range[0], cc.range[1], cc.range[2], cc.range[3]);
-      if (COUNT) cn->c[WGRT_CNT_DEPOSITS]++;
-    }
-    r.state = ST_DEAD;
-    return;
-  }
-  if (three || sel == 0) jones_apply(e, r.a, r.w, ote, otm);  // otherwise (ote, otm) still hold order 1
-  {
-    const double te2 = ote.re * ote.re + ote.im * ote.im;
-    const double tm2 = otm.re * otm.re + otm.im * otm.im;
-    const double inv_norm = rsqrt(te2 + tm2);
-    const cplx ph = cc.ph1[meta & 3];
-    cplx num;
-    const double eps2 = 1e-40;  // (1e-20)^2: E_field_cal zeroes a phase when its amplitude < 1e-20
-    if (te2 >= eps2 && tm2 >= eps2) {
-      const double inv_te = rsqrt(te2);
-      r.a = te2 * inv_te * inv_norm;
-      // E_tm * conj(E_te) / |E_te|: amplitude |E_tm|, phase phi_tm - phi_te
-      num = cplx{(otm.re * ote.re + otm.im * ote.im) * inv_te, (otm.im * ote.re - otm.re * ote.im) * inv_te};
+  // ---- phase 3: no grating: free TIR bounce (GRTF:1049-1052, 1102-1108, 1175-1178, 1244-1246) ---
+  int query = -1;  // region set to consult in phase 6
+  const bool event = live && !lost && hit >= 0;
+  if (live && !lost && hit < 0) {
+    const int miss = (sinfo >> SI_MISS_SHIFT) & 3;
+    if (miss == 2) {
+      lost = true;
+    } else if (miss == 1) {
+      query = REG_R2;  // state 3 leaves the fold zone only when outside eff_reg2
     } else {
-      const double te_abs = sqrt(te2), tm_abs = sqrt(tm2);
-      r.a = te_abs * inv_norm;
-      if (te2 < eps2 && tm2 >= eps2) num = otm;                                                // phi_te := 0
-      else if (te2 >= eps2) num = cplx{tm_abs * ote.re / te_abs, -tm_abs * ote.im / te_abs};  // phi_tm := 0
-      else num = cplx{tm_abs, 0.0};
+      r.x += r.gx;
+      r.y += r.gy;
+      r.w = cmul(r.w, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
+      if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
     }
-    num.re *= inv_norm;
-    num.im *= inv_norm;
-    r.w = cmul(num, ph);
   }
-  const int g = static_cast<int>((meta >> 2) & 3);
-  r.gx = cc.gap[2 * g];
-  r.gy = cc.gap[2 * g + 1];
-  r.x += r.gx;
-  r.y += r.gy;
-  r.inv_cos = e[9];
-  r.ener *= esel;
-  r.state = static_cast<int>((meta >> 4) & 7);
-  if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
-  if (post != POST_NONE) {
-    const bool in_ic = region_locate<COUNT>(sh.reg[REG_IC], r.x, r.y, cn) >= 0;
-    if (post == POST_IC_FWD) r.state = in_ic ? 0 : 2;       // GRTF:883-886
-    else if (!in_ic) r.state = ST_DEAD;                      // GRTF:899-902
+  __syncwarp();
+
+  // ---- phase 4: grating event: draw once, then try the orders in the reference's order ----------
+  int post = POST_NONE;
+  if (event) {
+    const double* e = tab + (((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * hit) * ENTRY_DOUBLES;
+    const long long meta0 = __double_as_longlong(e[10]);
+    const bool three = (meta0 & META_THREE) != 0;
+    const bool gated = (meta0 & META_GATED) != 0;  // `and ener_k > threshold` (GRTF:1020 ff.), absent in GRTF:871-999
+    const double u = xorshift_draw(r.rng, r.idx);
+    if (COUNT) {
+      cn->c[WGRT_CNT_DRAWS]++;
+      cn->c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
+      cn->c[WGRT_CNT_EFIELD] += three ? 3 : 2;
+    }
+    cplx ote, otm, kte, ktm;   // k*: amplitudes of the chosen order
+    double esum, esel = 0.0;
+    const double* esel_row = nullptr;
+    jones_apply(e, r.a, r.w, ote, otm);
+    const double e1 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[8] * r.inv_cos;
+    if (u <= e1 && (!gated || r.ener * e1 > 0.0)) { esel_row = e; esel = e1; kte = ote; ktm = otm; }
+    esum = e1;
+    if (esel_row == nullptr) {
+      jones_apply(e + ENTRY_DOUBLES, r.a, r.w, ote, otm);
+      const double e2 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[ENTRY_DOUBLES + 8] * r.inv_cos;
+      esum = e1 + e2;
+      if (u <= esum && (!gated || r.ener * e2 > 0.0)) { esel_row = e + ENTRY_DOUBLES; esel = e2; kte = ote; ktm = otm; }
+      if (esel_row == nullptr && three) {
+        jones_apply(e + 2 * ENTRY_DOUBLES, r.a, r.w, ote, otm);
+        const double e3 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[2 * ENTRY_DOUBLES + 8] * r.inv_cos;
+        if (u <= esum + e3 && r.ener * e3 > 0.0) { esel_row = e + 2 * ENTRY_DOUBLES; esel = e3; kte = ote; ktm = otm; }
+      }
+    }
+    if (esel_row == nullptr) {
+      lost = true;  // absorbed: u above every cumulative efficiency
+    } else {
+      const long long meta = __double_as_longlong(esel_row[10]);
+      post = static_cast<int>((meta >> 7) & 3);
+      if (post == POST_DEPOSIT) {
+        // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
+        if (inside_or_on_edge_literal<COUNT>(r.x, r.y, cc.rect, 0, 4, cn)) {
+          deposit_bin(p, lm, m, n, r.x, r.y, cc.range[0], cc.range[1], cc.range[2], cc.range[3]);
+          if (COUNT) cn->c[WGRT_CNT_DEPOSITS]++;
+        }
+        lost = true;
+      } else {
+        const double te2 = kte.re * kte.re + kte.im * kte.im;
+        const double tm2 = ktm.re * ktm.re + ktm.im * ktm.im;
+        const double inv_norm = rsqrt(te2 + tm2);
+        const cplx ph = cc.ph1[meta & 3];
+        cplx num;
+        const double eps2 = 1e-40;  // (1e-20)^2: E_field_cal zeroes a phase when its amplitude < 1e-20
+        if (te2 >= eps2 && tm2 >= eps2) {
+          const double inv_te = rsqrt(te2);
+          r.a = te2 * inv_te * inv_norm;
+          // E_tm * conj(E_te) / |E_te|: amplitude |E_tm|, phase phi_tm - phi_te
+          num = cplx{(ktm.re * kte.re + ktm.im * kte.im) * inv_te, (ktm.im * kte.re - ktm.re * kte.im) * inv_te};
+        } else {
+          const double te_abs = sqrt(te2), tm_abs = sqrt(tm2);
+          r.a = te_abs * inv_norm;
+          if (te2 < eps2 && tm2 >= eps2) num = ktm;                                                // phi_te := 0
+          else if (te2 >= eps2) num = cplx{tm_abs * kte.re / te_abs, -tm_abs * kte.im / te_abs};  // phi_tm := 0
+          else num = cplx{tm_abs, 0.0};
+        }
+        num.re *= inv_norm;
+        num.im *= inv_norm;
+        r.w = cmul(num, ph);
+        const int g = static_cast<int>((meta >> 2) & 3);
+        r.gx = cc.gap[2 * g];
+        r.gy = cc.gap[2 * g + 1];
+        r.x += r.gx;
+        r.y += r.gy;
+        r.inv_cos = esel_row[9];
+        r.ener *= esel;
+        r.state = static_cast<int>((meta >> 4) & 7);
+        if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
+        if (post != POST_NONE) query = REG_IC;
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase 6: follow-up region queries --------------------------------------------------------
+  if (query >= 0) {
+    const bool in = region_locate<COUNT>(sh.reg[query], r.x, r.y, cn) >= 0;
+    if (query == REG_R2) {
+      if (!in) {
+        r.state = 4;  // GRTF:1103-1104: no move in this iteration
+      } else {
+        r.x += r.gx;
+        r.y += r.gy;
+        r.w = cmul(r.w, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
+        if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
+      }
+    } else if (post == POST_IC_FWD) {
+      r.state = in ? 0 : 2;  // GRTF:883-886
+    } else if (!in) {
+      lost = true;  // GRTF:899-902
+    }
+  }
+  __syncwarp();
+  if (lost) {
+    p.rng_states[r.idx] = r.rng;
+    r.state = ST_DEAD;
   }
 }
 
@@ -393,10 +461,7 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             if (base + cnt >= run_len) queue_open = false;
           }
           if (__ballot_sync(FULL_MASK, r.state != ST_DEAD) == 0u) break;
-          if (r.state != ST_DEAD) {
-            walk_step<COUNT>(p, sh, tab, lm, m, n, r, &cn);
-            if (r.state == ST_DEAD) p.rng_states[r.idx] = r.rng;
-          }
+          walk_step<COUNT>(p, sh, tab, lm, m, n, r, &cn);
         }
       }
       run_begin = run_end;
@@ -521,7 +586,8 @@ __global__ void region_cells_kernel(const __grid_constant__ RegionSet rs) {
   const double cx = d.x0 + (ix + 0.5) * d.cell_dx, cy = d.y0 + (iy + 0.5) * d.cell_dy;
   const uint32_t* mask = st.rowmask + static_cast<size_t>(iy) * st.words;
   uint8_t code = CELL_NONE;
-  for (int k = 0; k < st.npoly && code == CELL_NONE; ++k) {
+  int first_unc = -1, last_unc = -1, hit_ring = -1;
+  for (int k = 0; k < st.npoly && hit_ring < 0; ++k) {
     const int s = ring_begin(st.offsets, st.nverts, k), e = ring_begin(st.offsets, st.nverts, k + 1);
     if (e <= s) continue;
     bool near_edge = false, inside = false;
@@ -551,9 +617,21 @@ __global__ void region_cells_kernel(const __grid_constant__ RegionSet rs) {
           if (cx < (xj - xi) * (cy - yi) / (yj - yi + 1e-20) + xi) inside = !inside;
       }
     }
-    if (near_edge) code = CELL_AMBIG;
-    else if (inside) code = static_cast<uint8_t>(k);
+    if (near_edge) {
+      if (first_unc < 0) first_unc = k;
+      last_unc = k;
+    } else if (inside) {
+      hit_ring = k;   // certainly inside ring k: later rings can never be the first hit
+    }
   }
+  uint32_t detail = 0;
+  if (first_unc >= 0) {
+    code = CELL_AMBIG;
+    detail = hit_ring >= 0 ? pack_detail(first_unc, hit_ring, hit_ring) : pack_detail(first_unc, last_unc + 1, 255);
+  } else if (hit_ring >= 0) {
+    code = static_cast<uint8_t>(hit_ring);
+  }
+  st.detail[t] = detail;
   st.cells[t] = code;
 }
 

@@ -13,7 +13,11 @@
 //                       cell -> run the reference's own expressions, but only on the edges whose
 //                       y-range meets this cell row (a per-row edge bit mask).  Edges outside that
 //                       mask cannot satisfy (yi>y)!=(yj>y) nor the tolerance box of
-//                       point_on_segment, so skipping them cannot change either pass.
+//                       point_on_segment, so skipping them cannot change either pass.  A detail
+//                       word per cell narrows the scan further: rings before `first` are certainly
+//                       missed, rings [first, stop) are tested exactly in order, and if none
+//                       contains the point the answer is `dflt` (the first ring certainly hit after
+//                       them, or none).
 //
 // Booleans are therefore identical to the literal scan for every input point; only the amount of
 // work differs.  tests/test_region_index.py checks this against the oracle on adversarial points
@@ -28,17 +32,18 @@ namespace wgrt {
 struct alignas(16) Region {
   double x0, y0, inv_dx, inv_dy;
   const uint8_t* cells;
+  const uint32_t* detail;
   const uint32_t* rowmask;
   const double* verts;
   const int64_t* offsets;
   int nverts, npoly, nx, ny, words;
-  int pad_;
+  int pad_[3];
 };
 
 __device__ __forceinline__ void region_load(Region& r, const RegionStatic& st, const RegionDyn& dy) {
   r.x0 = dy.x0; r.y0 = dy.y0; r.inv_dx = dy.inv_dx; r.inv_dy = dy.inv_dy;
-  r.cells = st.cells; r.rowmask = st.rowmask; r.verts = st.verts; r.offsets = st.offsets;
-  r.nverts = st.nverts; r.npoly = st.npoly; r.nx = st.nx; r.ny = st.ny; r.words = st.words; r.pad_ = 0;
+  r.cells = st.cells; r.detail = st.detail; r.rowmask = st.rowmask; r.verts = st.verts; r.offsets = st.offsets;
+  r.nverts = st.nverts; r.npoly = st.npoly; r.nx = st.nx; r.ny = st.ny; r.words = st.words;
 }
 
 __device__ __forceinline__ int ring_begin(const int64_t* off, int nverts, int k) {
@@ -76,15 +81,22 @@ __device__ __forceinline__ bool ring_test_masked(double px, double py, const dou
   return on_edge || inside;
 }
 
+// detail word of an ambiguous cell: first | stop << 8 | dflt << 16  (dflt 255 = none)
+__host__ __device__ __forceinline__ uint32_t pack_detail(int first, int stop, int dflt) {
+  return static_cast<uint32_t>(first) | (static_cast<uint32_t>(stop) << 8) | (static_cast<uint32_t>(dflt) << 16);
+}
+
 template <bool COUNT>
-__device__ __noinline__ int region_locate_exact(const Region& r, double x, double y, int iy, Counts* cn) {
+__device__ __noinline__ int region_locate_exact(const Region& r, double x, double y, int cell, int iy, Counts* cn) {
   if (COUNT) cn->c[WGRT_CNT_EXACT_FALLBACK]++;
+  const uint32_t d = __ldg(r.detail + cell);
+  const int first = d & 0xff, stop = (d >> 8) & 0xff, dflt = (d >> 16) & 0xff;
   const uint32_t* mask = r.rowmask + static_cast<size_t>(iy) * r.words;
-  for (int k = 0; k < r.npoly; ++k) {
+  for (int k = first; k < stop; ++k) {
     const int s = ring_begin(r.offsets, r.nverts, k), e = ring_begin(r.offsets, r.nverts, k + 1);
     if (ring_test_masked<COUNT>(x, y, r.verts, s, e, mask, cn)) return k;
   }
-  return -1;
+  return dflt == 255 ? -1 : dflt;
 }
 
 // Index of the first ring of the set containing (x, y) -- what the reference's
@@ -97,10 +109,11 @@ __device__ __forceinline__ int region_locate(const Region& r, double x, double y
   // also rejects NaN coordinates, which the literal test classifies as outside
   if (!(fx >= 0.0 && fy >= 0.0 && fx < static_cast<double>(r.nx) && fy < static_cast<double>(r.ny))) return -1;
   const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
-  const uint8_t code = __ldg(r.cells + iy * r.nx + ix);
+  const int cell = iy * r.nx + ix;
+  const uint8_t code = __ldg(r.cells + cell);
   if (code == CELL_NONE) return -1;
   if (code != CELL_AMBIG) return code;
-  return region_locate_exact<COUNT>(r, x, y, iy, cn);
+  return region_locate_exact<COUNT>(r, x, y, cell, iy, cn);
 }
 
 }  // namespace wgrt
