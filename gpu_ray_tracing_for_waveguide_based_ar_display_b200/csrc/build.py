@@ -19,7 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # literal restatement that is compared with the CPU oracle.
 UNITS = {
     "wgrt_strict.cu": ["-fmad=false"],
-    "wgrt_fast.cu": [],
+    "wgrt_fast.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WALK_THREADS", "WGRT_WALK_MIN_BLOCKS") if k in os.environ],
     "wgrt_api.cu": [],
 }
 HEADERS = ["wgrt_device.cuh", "wgrt_region.cuh", os.path.join("..", "..", "include", "wgrt.h")]

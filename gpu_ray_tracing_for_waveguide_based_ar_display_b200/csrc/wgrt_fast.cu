@@ -26,9 +26,14 @@ namespace wgrt {
 
 namespace {
 
-constexpr int WALK_THREADS = 128;
+#ifndef WGRT_WALK_THREADS
+#define WGRT_WALK_THREADS 128
+#endif
+#ifndef WGRT_WALK_MIN_BLOCKS
+#define WGRT_WALK_MIN_BLOCKS 5
+#endif
+constexpr int WALK_THREADS = WGRT_WALK_THREADS;
 constexpr int ENTRY_DOUBLES = 12;  // 8 Jones + factor + inv_cos_new + meta + spare
-constexpr int ST_INIT = 6;
 constexpr int ST_DEAD = -1;
 enum { POST_NONE = 0, POST_IC_FWD = 1, POST_IC_BACK = 2, POST_DEPOSIT = 3 };
 enum { EV_INIT = 0, EV_S0, EV_S1, EV_S2, EV_S3, EV_S4, EV_S5, NUM_EV };
@@ -78,7 +83,7 @@ struct alignas(16) CellConst {
   double rect[8];   // eff_reg_FOV[m, n, :, :]
   double range[4];  // eff_reg_FOV_range[m, n, :]
   double inv_cos_in;
-  int sinfo[8];     // per region state (index ST_INIT = in-coupling): see SI_* below
+  int sinfo[8];     // per region state 0..5: see SI_* below
 };
 
 // sinfo bit layout: which region set decides the event, where the state's rows start, how many rows
@@ -89,11 +94,11 @@ enum : int {
   SI_STRIDE_SHIFT = 15,                            // bits 15-16
   SI_MISS_SHIFT = 17,                              // bits 17-18: 0 bounce on, 1 test eff_reg2 first, 2 lost
   SI_PHASE_SHIFT = 19,                             // bit 19: which doubled TIR phase a free bounce adds
-  SI_IN_LOOP = 1 << 20                             // bit 20: GRTF:906 applies (every state but in-coupling)
+  SI_GAP_SHIFT = 20                                // bits 20-21: lut_gap pair of the state's direction of travel
 };
-__host__ __device__ constexpr int make_sinfo(int region, int rowbase, int stride, int miss, int phase, bool in_loop) {
+__host__ __device__ constexpr int make_sinfo(int region, int rowbase, int stride, int miss, int phase, int gap) {
   return region | (rowbase << SI_ROWBASE_SHIFT) | (stride << SI_STRIDE_SHIFT) | (miss << SI_MISS_SHIFT) |
-         (phase << SI_PHASE_SHIFT) | (in_loop ? SI_IN_LOOP : 0);
+         (phase << SI_PHASE_SHIFT) | (gap << SI_GAP_SHIFT);
 }
 constexpr long long META_THREE = 1ll << 9;   // on the first row of an event: the event has three orders
 constexpr long long META_GATED = 1ll << 10;  // ... and its branches carry `and ener_k > threshold`
@@ -103,8 +108,14 @@ struct WalkShared {
   CellConst cc;
   int tile;        // current tile index
   int run_end;     // end of the current run (ray index, exclusive)
-  int q_next;      // next unclaimed ray of the run
+  int run_cursor;  // next ray of the run nobody has in-coupled yet (warps claim 32 at a time)
 };
+
+struct WarpQueue;
+__host__ __device__ constexpr size_t walk_smem_table_offset() { return (sizeof(WalkShared) + 15) & ~size_t(15); }
+__host__ __device__ inline size_t walk_smem_queue_offset(int rows) {
+  return walk_smem_table_offset() + ((static_cast<size_t>(rows) * ENTRY_DOUBLES * sizeof(double) + 15) & ~size_t(15));
+}
 
 __device__ __forceinline__ const double* lut_slice(const wgrt_problem_t& p, int which, int i, int64_t cell,
                                                    int64_t cells_per_poly, int32_t& C) {
@@ -184,27 +195,42 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
   } else if (t == 24) {
     cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
   } else if (t == 25) {
-    cc.sinfo[0] = make_sinfo(SI_REGION_NONE, 2, 0, 0, 0, true);
-    cc.sinfo[1] = make_sinfo(SI_REGION_NONE, 4, 0, 0, 0, true);
-    cc.sinfo[2] = make_sinfo(REG_FC, 6, 2, 0, 0, true);                         // miss: bounce, 2 T[0]
-    cc.sinfo[3] = make_sinfo(REG_FC, 6 + 2 * nFC, 2, 1, 1, true);               // miss: eff_reg2 test, 2 T[1]
-    cc.sinfo[4] = make_sinfo(REG_OC, 6 + 4 * nFC, 3, 0, 1, true);               // miss: bounce, 2 T[1]
-    cc.sinfo[5] = make_sinfo(REG_OC, 6 + 4 * nFC + 3 * nOC, 3, 2, 0, true);     // miss: lost
-    cc.sinfo[ST_INIT] = make_sinfo(SI_REGION_NONE, 0, 0, 0, 0, false);
+    // the bounce vector a ray travels with is a function of its state: states 0 and 2 follow the
+    // +1 in-coupled direction (gap pair 0), state 1 the -1 direction (2), states 3 and 4 the folded
+    // direction (1), state 5 the conjugate out-coupler direction (3)
+    cc.sinfo[0] = make_sinfo(SI_REGION_NONE, 2, 0, 0, 0, 0);
+    cc.sinfo[1] = make_sinfo(SI_REGION_NONE, 4, 0, 0, 0, 2);
+    cc.sinfo[2] = make_sinfo(REG_FC, 6, 2, 0, 0, 0);                         // miss: bounce, 2 T[0]
+    cc.sinfo[3] = make_sinfo(REG_FC, 6 + 2 * nFC, 2, 1, 1, 1);               // miss: eff_reg2 test, 2 T[1]
+    cc.sinfo[4] = make_sinfo(REG_OC, 6 + 4 * nFC, 3, 0, 1, 1);               // miss: bounce, 2 T[1]
+    cc.sinfo[5] = make_sinfo(REG_OC, 6 + 4 * nFC + 3 * nOC, 3, 2, 0, 3);     // miss: lost
+    cc.sinfo[6] = 0;
     cc.sinfo[7] = 0;
   }
 }
 
 struct Ray {
-  double x, y, gx, gy;  // position and current bounce vector
-  double a;             // |E_te|
-  cplx w;               // |E_tm| e^{i delta}
-  double inv_cos;       // 1 / cos(theta_current.real)
+  double x, y;     // position
+  double a;        // |E_te|
+  cplx w;          // |E_tm| e^{i delta}
+  double inv_cos;  // 1 / cos(theta_current.real)
   double ener;
   uint32_t rng;
   int state;
   int iter;
-  int64_t idx;          // global ray index
+  int idx;         // ray index relative to the start of the run
+};
+
+// Rays that survived in-coupling wait here until a lane of the owning warp is free.  One queue per
+// warp (a stack: the warp-uniform fill count lives in a register), filled and drained with
+// ballot / popc prefix ranks, so no atomics and no block-wide barrier are involved.
+constexpr int QUEUE_CAP = 64;
+struct WarpQueue {
+  double x[QUEUE_CAP], y[QUEUE_CAP], a[QUEUE_CAP], wre[QUEUE_CAP], wim[QUEUE_CAP], inv_cos[QUEUE_CAP],
+      ener[QUEUE_CAP];
+  uint32_t rng[QUEUE_CAP];
+  int idx[QUEUE_CAP];
+  int state[QUEUE_CAP];
 };
 
 __device__ __forceinline__ void jones_apply(const double* __restrict__ e, double a, cplx w, cplx& ote, cplx& otm) {
@@ -214,22 +240,134 @@ __device__ __forceinline__ void jones_apply(const double* __restrict__ e, double
   otm = cplx{L1.re * a + (L3.re * w.re - L3.im * w.im), L1.im * a + (L3.re * w.im + L3.im * w.re)};
 }
 
-// One step of every ray a warp holds.  ALL 32 lanes call this (lanes without a ray idle through
-// it): the step is cut into phases separated by __syncwarp(), so that after each divergent piece --
-// a region query that fell back to the exact edge scan, the free-bounce branch, three-order events
-// -- the warp is whole again before the next piece.  Everything state dependent comes out of
-// shared-memory tables (sinfo, the event rows and their meta words): lanes run the same
-// instructions whatever region state their rays are in.
+__device__ __forceinline__ double power_of(cplx ote, cplx otm) {
+  return ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im);
+}
+
+// The ray takes the order whose table row is `row` and whose output amplitudes are (kte, ktm):
+// normalise, add the TIR phase, advance by the new bounce vector, switch region state.
+// (GRTF:872-882 and its eleven siblings; E_field_cal's |.| / atan2 / wrap in Jones-vector form.)
+__device__ __forceinline__ void take_order(const CellConst& cc, const double* __restrict__ row, long long meta,
+                                           cplx kte, cplx ktm, double esel, Ray& r) {
+  const double te2 = kte.re * kte.re + kte.im * kte.im;
+  const double tm2 = ktm.re * ktm.re + ktm.im * ktm.im;
+  const double inv_norm = rsqrt(te2 + tm2);
+  const cplx ph = cc.ph1[meta & 3];
+  cplx num;
+  const double eps2 = 1e-40;  // (1e-20)^2: E_field_cal zeroes a phase when its amplitude < 1e-20
+  if (te2 >= eps2 && tm2 >= eps2) {
+    const double inv_te = rsqrt(te2);
+    r.a = te2 * inv_te * inv_norm;
+    // E_tm * conj(E_te) / |E_te|: amplitude |E_tm|, phase phi_tm - phi_te
+    num = cplx{(ktm.re * kte.re + ktm.im * kte.im) * inv_te, (ktm.im * kte.re - ktm.re * kte.im) * inv_te};
+  } else {
+    const double te_abs = sqrt(te2), tm_abs = sqrt(tm2);
+    r.a = te_abs * inv_norm;
+    if (te2 < eps2 && tm2 >= eps2) num = ktm;                                                // phi_te := 0
+    else if (te2 >= eps2) num = cplx{tm_abs * kte.re / te_abs, -tm_abs * kte.im / te_abs};  // phi_tm := 0
+    else num = cplx{tm_abs, 0.0};
+  }
+  num.re *= inv_norm;
+  num.im *= inv_norm;
+  r.w = cmul(num, ph);
+  const int g = static_cast<int>((meta >> 2) & 3);
+  r.x += cc.gap[2 * g];
+  r.y += cc.gap[2 * g + 1];
+  r.inv_cos = row[9];
+  r.ener *= esel;
+  r.state = static_cast<int>((meta >> 4) & 7);
+}
+
+// In-coupling (GRTF:842-904) for 32 consecutive rays of the run: one ray per lane, fully coalesced
+// loads, every lane busy.  Rays that enter the waveguide are pushed on the warp's queue; the others
+// (about three quarters with realistic gratings) are finished here.  Returns the new queue fill.
+template <bool COUNT>
+__device__ __forceinline__ int incouple_batch(const wgrt_problem_t& p, WalkShared& sh, const double* __restrict__ tab,
+                                              int64_t run_begin, int first, int run_len, WarpQueue& q, int qn,
+                                              int lane, unsigned lt_mask, Counts* cn) {
+  const CellConst& cc = sh.cc;
+  const int i = first + lane;
+  bool survived = false;
+  Ray r;
+  if (i < run_len) {
+    const int64_t idx = run_begin + i;
+    r.idx = i;
+    r.x = static_cast<double>(__ldg(p.x + idx));
+    r.y = static_cast<double>(__ldg(p.y + idx));
+    r.a = static_cast<double>(__ldg(p.te + idx));
+    const double tm = static_cast<double>(__ldg(p.tm + idx));
+    const float dlf = __ldg(p.delta_phase + idx);
+    r.rng = p.rng_states[idx];
+    if (dlf == 0.0f) {
+      r.w = cplx{tm, 0.0};
+    } else {
+      double sn, cs;
+      sincos(static_cast<double>(dlf), &sn, &cs);
+      r.w = cplx{tm * cs, tm * sn};
+    }
+    r.ener = 1.0;
+    r.iter = 0;
+    if (COUNT) {
+      cn->c[WGRT_CNT_RAYS]++;
+      cn->c[WGRT_CNT_DRAWS]++;
+      cn->c[WGRT_CNT_DRAW2]++;
+      cn->c[WGRT_CNT_EFIELD] += 2;
+    }
+    const double u = xorshift_draw(r.rng, idx);
+    cplx ote, otm;
+    const double* row = tab;  // rows 0 and 1: the two in-coupled orders
+    jones_apply(row, r.a, r.w, ote, otm);
+    const double e1 = power_of(ote, otm) * row[8] * cc.inv_cos_in;
+    double esel = e1;
+    bool taken = u <= e1;  // GRTF:871: no energy gate on the in-coupling branches
+    if (!taken) {
+      row += ENTRY_DOUBLES;
+      jones_apply(row, r.a, r.w, ote, otm);
+      esel = power_of(ote, otm) * row[8] * cc.inv_cos_in;
+      taken = u <= e1 + esel;  // GRTF:887
+    }
+    if (taken) {
+      const long long meta = __double_as_longlong(row[10]);
+      take_order(cc, row, meta, ote, otm, esel, r);
+      if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
+      const bool in_ic = region_locate<COUNT>(sh.reg[REG_IC], r.x, r.y, cn) >= 0;
+      if (((meta >> 7) & 3) == POST_IC_FWD) {
+        r.state = in_ic ? 0 : 2;  // GRTF:883-886
+        survived = true;
+      } else {
+        survived = in_ic;         // GRTF:899-902
+      }
+    }
+    if (!survived) p.rng_states[idx] = r.rng;
+  }
+  __syncwarp();
+  const unsigned surv = __ballot_sync(FULL_MASK, survived);
+  if (survived) {
+    const int slot = qn + __popc(surv & lt_mask);
+    q.x[slot] = r.x; q.y[slot] = r.y; q.a[slot] = r.a; q.wre[slot] = r.w.re; q.wim[slot] = r.w.im;
+    q.inv_cos[slot] = r.inv_cos; q.ener[slot] = r.ener; q.rng[slot] = r.rng; q.idx[slot] = r.idx;
+    q.state[slot] = r.state;
+  }
+  __syncwarp();
+  return qn + __popc(surv);
+}
+
+// One loop iteration (GRTF:905-1246) for every ray a warp holds.  ALL 32 lanes call this (lanes
+// without a ray idle through it): the step is cut into phases separated by __syncwarp(), so that
+// after each divergent piece -- a region query that fell back to the exact edge scan, the
+// free-bounce branch, three-order events -- the warp is whole again before the next piece.
+// Everything state dependent comes out of shared-memory tables (sinfo, the event rows and their
+// meta words): lanes run the same instructions whatever region state their rays are in.
 template <bool COUNT>
 __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& sh, const double* __restrict__ tab,
-                                          int64_t lm, int64_t m, int64_t n, Ray& r, Counts* cn) {
+                                          int64_t run_begin, int64_t lm, int64_t m, int64_t n, Ray& r, Counts* cn) {
   const CellConst& cc = sh.cc;
   const bool live = r.state != ST_DEAD;
   const int sinfo = live ? cc.sinfo[r.state] : 0;
   bool lost = false;  // the ray ends in this step
 
   // ---- phase 1: the loop's effective-region test (GRTF:905-907) -----------------------------
-  if (live && (sinfo & SI_IN_LOOP)) {
+  if (live) {
     if (COUNT) cn->c[WGRT_CNT_ITERS]++;
     if (++r.iter > 100000 || region_locate<COUNT>(sh.reg[REG_R1], r.x, r.y, cn) < 0) lost = true;
   }
@@ -242,7 +380,7 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
   __syncwarp();
 
   // ---- phase 3: no grating: free TIR bounce (GRTF:1049-1052, 1102-1108, 1175-1178, 1244-1246) ---
-  int query = -1;  // region set to consult in phase 6
+  int query = -1;  // region set to consult in phase 5
   const bool event = live && !lost && hit >= 0;
   if (live && !lost && hit < 0) {
     const int miss = (sinfo >> SI_MISS_SHIFT) & 3;
@@ -251,8 +389,9 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
     } else if (miss == 1) {
       query = REG_R2;  // state 3 leaves the fold zone only when outside eff_reg2
     } else {
-      r.x += r.gx;
-      r.y += r.gy;
+      const int g = (sinfo >> SI_GAP_SHIFT) & 3;
+      r.x += cc.gap[2 * g];
+      r.y += cc.gap[2 * g + 1];
       r.w = cmul(r.w, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
       if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
     }
@@ -266,34 +405,35 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
     const long long meta0 = __double_as_longlong(e[10]);
     const bool three = (meta0 & META_THREE) != 0;
     const bool gated = (meta0 & META_GATED) != 0;  // `and ener_k > threshold` (GRTF:1020 ff.), absent in GRTF:871-999
-    const double u = xorshift_draw(r.rng, r.idx);
+    const double u = xorshift_draw(r.rng, run_begin + r.idx);
     if (COUNT) {
       cn->c[WGRT_CNT_DRAWS]++;
       cn->c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
       cn->c[WGRT_CNT_EFIELD] += three ? 3 : 2;
     }
-    cplx ote, otm, kte, ktm;   // k*: amplitudes of the chosen order
-    double esum, esel = 0.0;
-    const double* esel_row = nullptr;
-    jones_apply(e, r.a, r.w, ote, otm);
-    const double e1 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[8] * r.inv_cos;
-    if (u <= e1 && (!gated || r.ener * e1 > 0.0)) { esel_row = e; esel = e1; kte = ote; ktm = otm; }
-    esum = e1;
-    if (esel_row == nullptr) {
-      jones_apply(e + ENTRY_DOUBLES, r.a, r.w, ote, otm);
-      const double e2 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[ENTRY_DOUBLES + 8] * r.inv_cos;
-      esum = e1 + e2;
-      if (u <= esum && (!gated || r.ener * e2 > 0.0)) { esel_row = e + ENTRY_DOUBLES; esel = e2; kte = ote; ktm = otm; }
-      if (esel_row == nullptr && three) {
-        jones_apply(e + 2 * ENTRY_DOUBLES, r.a, r.w, ote, otm);
-        const double e3 = (ote.re * ote.re + ote.im * ote.im + (otm.re * otm.re + otm.im * otm.im)) * e[2 * ENTRY_DOUBLES + 8] * r.inv_cos;
-        if (u <= esum + e3 && r.ener * e3 > 0.0) { esel_row = e + 2 * ENTRY_DOUBLES; esel = e3; kte = ote; ktm = otm; }
+    cplx ote, otm;
+    const double* row = e;
+    jones_apply(row, r.a, r.w, ote, otm);
+    double esel = power_of(ote, otm) * row[8] * r.inv_cos;
+    double esum = esel;
+    bool taken = u <= esum && (!gated || r.ener * esel > 0.0);
+    if (!taken) {
+      row = e + ENTRY_DOUBLES;
+      jones_apply(row, r.a, r.w, ote, otm);
+      esel = power_of(ote, otm) * row[8] * r.inv_cos;
+      esum += esel;
+      taken = u <= esum && (!gated || r.ener * esel > 0.0);
+      if (!taken && three) {
+        row = e + 2 * ENTRY_DOUBLES;
+        jones_apply(row, r.a, r.w, ote, otm);
+        esel = power_of(ote, otm) * row[8] * r.inv_cos;
+        taken = u <= esum + esel && r.ener * esel > 0.0;
       }
     }
-    if (esel_row == nullptr) {
+    if (!taken) {
       lost = true;  // absorbed: u above every cumulative efficiency
     } else {
-      const long long meta = __double_as_longlong(esel_row[10]);
+      const long long meta = __double_as_longlong(row[10]);
       post = static_cast<int>((meta >> 7) & 3);
       if (post == POST_DEPOSIT) {
         // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
@@ -303,35 +443,7 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
         }
         lost = true;
       } else {
-        const double te2 = kte.re * kte.re + kte.im * kte.im;
-        const double tm2 = ktm.re * ktm.re + ktm.im * ktm.im;
-        const double inv_norm = rsqrt(te2 + tm2);
-        const cplx ph = cc.ph1[meta & 3];
-        cplx num;
-        const double eps2 = 1e-40;  // (1e-20)^2: E_field_cal zeroes a phase when its amplitude < 1e-20
-        if (te2 >= eps2 && tm2 >= eps2) {
-          const double inv_te = rsqrt(te2);
-          r.a = te2 * inv_te * inv_norm;
-          // E_tm * conj(E_te) / |E_te|: amplitude |E_tm|, phase phi_tm - phi_te
-          num = cplx{(ktm.re * kte.re + ktm.im * kte.im) * inv_te, (ktm.im * kte.re - ktm.re * kte.im) * inv_te};
-        } else {
-          const double te_abs = sqrt(te2), tm_abs = sqrt(tm2);
-          r.a = te_abs * inv_norm;
-          if (te2 < eps2 && tm2 >= eps2) num = ktm;                                                // phi_te := 0
-          else if (te2 >= eps2) num = cplx{tm_abs * kte.re / te_abs, -tm_abs * kte.im / te_abs};  // phi_tm := 0
-          else num = cplx{tm_abs, 0.0};
-        }
-        num.re *= inv_norm;
-        num.im *= inv_norm;
-        r.w = cmul(num, ph);
-        const int g = static_cast<int>((meta >> 2) & 3);
-        r.gx = cc.gap[2 * g];
-        r.gy = cc.gap[2 * g + 1];
-        r.x += r.gx;
-        r.y += r.gy;
-        r.inv_cos = esel_row[9];
-        r.ener *= esel;
-        r.state = static_cast<int>((meta >> 4) & 7);
+        take_order(cc, row, meta, ote, otm, esel, r);
         if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
         if (post != POST_NONE) query = REG_IC;
       }
@@ -339,40 +451,42 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
   }
   __syncwarp();
 
-  // ---- phase 6: follow-up region queries --------------------------------------------------------
+  // ---- phase 5: follow-up region queries --------------------------------------------------------
   if (query >= 0) {
     const bool in = region_locate<COUNT>(sh.reg[query], r.x, r.y, cn) >= 0;
     if (query == REG_R2) {
       if (!in) {
         r.state = 4;  // GRTF:1103-1104: no move in this iteration
       } else {
-        r.x += r.gx;
-        r.y += r.gy;
+        const int g = (sinfo >> SI_GAP_SHIFT) & 3;
+        r.x += cc.gap[2 * g];
+        r.y += cc.gap[2 * g + 1];
         r.w = cmul(r.w, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
         if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
       }
     } else if (post == POST_IC_FWD) {
-      r.state = in ? 0 : 2;  // GRTF:883-886
+      r.state = in ? 0 : 2;  // GRTF:932-935
     } else if (!in) {
-      lost = true;  // GRTF:899-902
+      lost = true;  // GRTF:948-951
     }
   }
   __syncwarp();
   if (lost) {
-    p.rng_states[r.idx] = r.rng;
+    p.rng_states[run_begin + r.idx] = r.rng;
     r.state = ST_DEAD;
   }
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(WALK_THREADS, 4)
+__global__ void __launch_bounds__(WALK_THREADS, WGRT_WALK_MIN_BLOCKS)
 walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
                  int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
                  unsigned long long* counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WalkShared& sh = *reinterpret_cast<WalkShared*>(smem_raw);
-  double* tab = reinterpret_cast<double*>(smem_raw + ((sizeof(WalkShared) + 15) & ~size_t(15)));
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
+  double* tab = reinterpret_cast<double*>(smem_raw + walk_smem_table_offset());
+  WarpQueue& queue = reinterpret_cast<WarpQueue*>(smem_raw + walk_smem_queue_offset(rows))[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   Counts cn;
@@ -416,52 +530,47 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
       if (valid) {
         build_cell_tables(p, lm, m, n, tab, sh.cc, rows);
-        if (threadIdx.x == 0) sh.q_next = 0;
+        if (threadIdx.x == 0) sh.run_cursor = 0;
         __syncthreads();
         const int run_len = static_cast<int>(run_end - run_begin);
 
-        // ---- walk the run: every lane owns at most one ray, refilled from the run queue -----
+        // ---- each warp on its own: in-couple batches of 32 rays whenever more lanes are free
+        //      than rays are queued, refill free lanes from the queue, step the rays it holds ----
         Ray r;
         r.state = ST_DEAD;
-        bool queue_open = true;
+        int qn = 0;            // rays waiting in this warp's queue (warp uniform)
+        bool run_open = true;  // the run still has rays nobody in-coupled
         for (;;) {
-          const unsigned need = __ballot_sync(FULL_MASK, r.state == ST_DEAD);
-          if (need && queue_open) {
-            const int cnt = __popc(need);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sh.q_next, cnt);
-            base = __shfl_sync(FULL_MASK, base, 0);
-            if (r.state == ST_DEAD) {
-              const int q = base + __popc(need & lt_mask);
-              if (q < run_len) {
-                const int64_t idx = run_begin + q;
-                r.idx = idx;
-                r.x = static_cast<double>(__ldg(p.x + idx));
-                r.y = static_cast<double>(__ldg(p.y + idx));
-                const double te = static_cast<double>(__ldg(p.te + idx));
-                const double tm = static_cast<double>(__ldg(p.tm + idx));
-                const float dlf = __ldg(p.delta_phase + idx);
-                r.rng = p.rng_states[idx];
-                r.a = te;
-                if (dlf == 0.0f) {
-                  r.w = cplx{tm, 0.0};
-                } else {
-                  double s, c;
-                  sincos(static_cast<double>(dlf), &s, &c);
-                  r.w = cplx{tm * c, tm * s};
-                }
-                r.gx = 0.0; r.gy = 0.0;
-                r.inv_cos = sh.cc.inv_cos_in;
-                r.ener = 1.0;
-                r.iter = 0;
-                r.state = ST_INIT;
-                if (COUNT) cn.c[WGRT_CNT_RAYS]++;
-              }
+          const unsigned dead = __ballot_sync(FULL_MASK, r.state == ST_DEAD);
+          const int nd = __popc(dead);
+          while (run_open && qn < nd) {
+            int first = 0;
+            if (lane == 0) first = atomicAdd(&sh.run_cursor, 32);
+            first = __shfl_sync(FULL_MASK, first, 0);
+            if (first >= run_len) {
+              run_open = false;
+              break;
             }
-            if (base + cnt >= run_len) queue_open = false;
+            qn = incouple_batch<COUNT>(p, sh, tab, run_begin, first, run_len, queue, qn, lane, lt_mask, &cn);
           }
-          if (__ballot_sync(FULL_MASK, r.state != ST_DEAD) == 0u) break;
-          walk_step<COUNT>(p, sh, tab, lm, m, n, r, &cn);
+          if (nd && qn) {
+            const int take = min(nd, qn);
+            const int rank = __popc(dead & lt_mask);
+            if (r.state == ST_DEAD && rank < take) {
+              const int slot = qn - 1 - rank;
+              r.x = queue.x[slot]; r.y = queue.y[slot]; r.a = queue.a[slot];
+              r.w = cplx{queue.wre[slot], queue.wim[slot]};
+              r.inv_cos = queue.inv_cos[slot]; r.ener = queue.ener[slot]; r.rng = queue.rng[slot];
+              r.idx = queue.idx[slot]; r.state = queue.state[slot]; r.iter = 0;
+            }
+            qn -= take;
+            __syncwarp();
+          }
+          if (__ballot_sync(FULL_MASK, r.state != ST_DEAD) == 0u) {
+            if (!run_open) break;  // queue is empty too: every queued ray found a free lane above
+            continue;
+          }
+          walk_step<COUNT>(p, sh, tab, run_begin, lm, m, n, r, &cn);
         }
       }
       run_begin = run_end;
@@ -711,7 +820,7 @@ cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* 
   int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
   pick_tile_kernel<<<1, 32, 0, s>>>(p, tile_size, work_counter);
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
-  const size_t smem = ((sizeof(WalkShared) + 15) & ~size_t(15)) + static_cast<size_t>(rows) * ENTRY_DOUBLES * sizeof(double);
+  const size_t smem = walk_smem_queue_offset(rows) + (WALK_THREADS / 32) * sizeof(WarpQueue);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
   auto kern = count ? walk_fast_kernel<true> : walk_fast_kernel<false>;
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
