@@ -311,7 +311,7 @@ def main():
         "bounces_per_ray": bounces_all / max(rays_all, 1),
         "deposits": deposits_total,
         "step_ms_rank0": step_ms,
-        "gpu_launches": args.steps * 5,   # per launch: 3 region-index kernels, tile pick, walk
+        "gpu_launches": args.steps * 7,   # per launch: geometry hash, 4 region-index kernels (no-ops when unchanged), tile pick, walk
         "clocks": clocks.summary(),
     }
 

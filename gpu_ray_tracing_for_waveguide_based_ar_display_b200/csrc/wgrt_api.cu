@@ -57,16 +57,22 @@ struct DeviceBuf {
 struct Workspace {
   int device = -1;
   int num_sms = 0;
-  DeviceBuf cells[NUM_REGIONS], detail[NUM_REGIONS], rowmask[NUM_REGIONS];
-  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | work counter + tile size | counters
+  DeviceBuf cells[NUM_REGIONS], detail[NUM_REGIONS], rowmask[NUM_REGIONS], coarse[NUM_REGIONS], rowmask_c[NUM_REGIONS];
+  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | work counter + tile size | hash state | counters
+  bool index_stale = true;  // the index buffers were (re)allocated or used by a debug call
   DeviceBuf arena;   // staging for the host entry points
   RegionDyn* dyn() { return static_cast<RegionDyn*>(small.ptr); }
   int* work() { return reinterpret_cast<int*>(static_cast<char*>(small.ptr) + 512); }
+  unsigned long long* hash_state() {
+    return reinterpret_cast<unsigned long long*>(static_cast<char*>(small.ptr) + 768);
+  }
   unsigned long long* counters() {
     return reinterpret_cast<unsigned long long*>(static_cast<char*>(small.ptr) + 1024);
   }
   void release() {
-    for (int r = 0; r < NUM_REGIONS; ++r) { cells[r].release(); detail[r].release(); rowmask[r].release(); }
+    for (int r = 0; r < NUM_REGIONS; ++r) {
+      cells[r].release(); detail[r].release(); rowmask[r].release(); coarse[r].release(); rowmask_c[r].release();
+    }
     small.release();
     arena.release();
   }
@@ -75,15 +81,23 @@ struct Workspace {
 std::mutex g_mu;
 std::vector<Workspace> g_ws;
 
-int grid_resolution() {
-  static int res = [] {
-    const char* e = getenv("WGRT_GRID");
-    int v = e ? atoi(e) : 1024;
-    if (v < 8) v = 8;
-    if (v > 4096) v = 4096;
-    return v;
-  }();
-  return res;
+// Region grid geometry: nc x nc coarse cells, each split into 2^shift x 2^shift fine cells.
+// WGRT_COARSE / WGRT_GRID override the defaults (64 coarse, 4096 fine cells per axis).
+void grid_geometry(int* nc, int* shift) {
+  static int g_nc = 0, g_shift = 0;
+  if (!g_nc) {
+    const char* ec = getenv("WGRT_COARSE");
+    const char* ef = getenv("WGRT_GRID");
+    int c = ec ? atoi(ec) : 64, f = ef ? atoi(ef) : 4096;
+    if (c < 4) c = 4;
+    if (c > 256) c = 256;
+    int sh = 0;
+    while ((c << (sh + 1)) <= f && sh < 8) ++sh;
+    g_nc = c;
+    g_shift = sh;
+  }
+  *nc = g_nc;
+  *shift = g_shift;
 }
 
 int get_workspace(Workspace** out) {
@@ -106,7 +120,8 @@ int get_workspace(Workspace** out) {
 int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REGIONS],
                   const int64_t* const offsets[NUM_REGIONS], const int64_t nverts[NUM_REGIONS],
                   const int64_t npoly[NUM_REGIONS]) {
-  const int res = grid_resolution();
+  int nc, shift;
+  grid_geometry(&nc, &shift);
   for (int r = 0; r < NUM_REGIONS; ++r) {
     RegionStatic& st = rs.st[r];
     if (nverts[r] > (1 << 24)) return fail(WGRT_ERR_UNSUPPORTED, "region %d: too many vertices", r);
@@ -114,17 +129,29 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
     st.offsets = offsets[r];
     st.nverts = static_cast<int>(nverts[r]);
     st.npoly = static_cast<int>(npoly[r]);
-    st.nx = res;
-    st.ny = res;
+    st.nc = nc;
+    st.shift = shift;
+    st.n = nc << shift;
     st.words = (st.nverts + 31) / 32;
-    CUDA_TRY(w.cells[r].reserve(static_cast<size_t>(st.nx) * st.ny));
-    CUDA_TRY(w.detail[r].reserve(static_cast<size_t>(st.nx) * st.ny * sizeof(uint32_t)));
-    CUDA_TRY(w.rowmask[r].reserve(static_cast<size_t>(st.ny) * (st.words > 0 ? st.words : 1) * sizeof(uint32_t)));
+    const size_t fine = static_cast<size_t>(st.n) * st.n, wd = st.words > 0 ? st.words : 1;
+    const void* before[5] = {w.coarse[r].ptr, w.cells[r].ptr, w.detail[r].ptr, w.rowmask[r].ptr, w.rowmask_c[r].ptr};
+    CUDA_TRY(w.coarse[r].reserve(static_cast<size_t>(nc) * nc));
+    CUDA_TRY(w.cells[r].reserve(fine));
+    CUDA_TRY(w.detail[r].reserve(fine * sizeof(uint32_t)));
+    CUDA_TRY(w.rowmask[r].reserve(static_cast<size_t>(st.n) * wd * sizeof(uint32_t)));
+    CUDA_TRY(w.rowmask_c[r].reserve(static_cast<size_t>(nc) * wd * sizeof(uint32_t)));
+    st.coarse = static_cast<uint8_t*>(w.coarse[r].ptr);
     st.cells = static_cast<uint8_t*>(w.cells[r].ptr);
     st.detail = static_cast<uint32_t*>(w.detail[r].ptr);
     st.rowmask = static_cast<uint32_t*>(w.rowmask[r].ptr);
+    st.rowmask_coarse = static_cast<uint32_t*>(w.rowmask_c[r].ptr);
+    const void* after[5] = {w.coarse[r].ptr, w.cells[r].ptr, w.detail[r].ptr, w.rowmask[r].ptr, w.rowmask_c[r].ptr};
+    for (int k = 0; k < 5; ++k)
+      if (before[k] != after[k]) w.index_stale = true;
   }
   rs.dyn = w.dyn();
+  rs.hash_state = w.hash_state();
+  rs.dirty = w.hash_state() + 1;
   return WGRT_OK;
 }
 
@@ -164,7 +191,8 @@ int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
   const int64_t np[NUM_REGIONS] = {1, 1, 1, p.n_FC, p.n_OC};
   int rc = setup_regions(w, rs, verts, offs, nv, np);
   if (rc != WGRT_OK) return rc;
-  CUDA_TRY(launch_region_build(rs, stream));
+  CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
+  w.index_stale = false;
   CUDA_TRY(launch_walk_fast(p, rs, w.work(), w.counters(), w.num_sms, stream));
   return WGRT_OK;
 }
@@ -348,7 +376,8 @@ int wgrt_debug_locate(const double* verts, int64_t n_verts, const int64_t* offse
     const int64_t np[NUM_REGIONS] = {0, 0, 0, n_polys, 0};
     rc = setup_regions(*w, rs, vs, os, nv, np);
     if (rc != WGRT_OK) return rc;
-    CUDA_TRY(launch_region_build(rs, nullptr));
+    CUDA_TRY(launch_region_build(rs, true, nullptr));
+    w->index_stale = true;  // the walk's index was overwritten
     CUDA_TRY(launch_debug_locate_grid(rs, REG_FC, d_x, d_y, n_points, d_out, w->counters(), nullptr));
   }
   CUDA_TRY(cudaDeviceSynchronize());

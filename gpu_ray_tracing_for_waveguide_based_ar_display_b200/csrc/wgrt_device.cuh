@@ -144,10 +144,12 @@ __device__ __forceinline__ void deposit_bin(const wgrt_problem_t& p, int64_t lm,
 struct RegionStatic {          // host-known part of one region set
   const double* verts;         // [V,2]
   const int64_t* offsets;      // [npoly+1]; nullptr = one ring [0, nverts)
-  uint8_t* cells;              // [ny*nx] cell codes
-  uint32_t* detail;            // [ny*nx] ring range to test exactly in ambiguous cells
-  uint32_t* rowmask;           // [ny][words] edges relevant to each cell row
-  int nverts, npoly, nx, ny, words;
+  uint8_t* coarse;             // [nc*nc] coarse cell codes (small: stays in L1)
+  uint8_t* cells;              // [n*n] fine cell codes; only cells under MIXED coarse cells are valid
+  uint32_t* detail;            // [n*n] ring range to test exactly in ambiguous fine cells
+  uint32_t* rowmask;           // [n][words] edges relevant to each fine cell row
+  uint32_t* rowmask_coarse;    // [nc][words] same per coarse row (used while building)
+  int nverts, npoly, n, nc, shift, words;  // n = nc << shift fine cells per axis
 };
 struct RegionDyn {             // computed on the device from the vertex data
   double x0, y0, inv_dx, inv_dy, cell_dx, cell_dy;
@@ -157,11 +159,13 @@ constexpr uint8_t CELL_NONE = 255, CELL_AMBIG = 254;
 
 struct RegionSet {
   RegionStatic st[NUM_REGIONS];
-  RegionDyn* dyn;              // device array [NUM_REGIONS]
+  RegionDyn* dyn;                   // device array [NUM_REGIONS]
+  unsigned long long* hash_state;   // device: {hash of the index now built, dirty flag of this launch}
+  const unsigned long long* dirty;  // = hash_state + 1
 };
 
 cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* counters, cudaStream_t s);
-cudaError_t launch_region_build(const RegionSet& rs, cudaStream_t s);
+cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s);
 cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
                              unsigned long long* counters, int num_sms, cudaStream_t s);
 cudaError_t launch_debug_locate_literal(const double* verts, const int64_t* off, int64_t npoly, const double* px,

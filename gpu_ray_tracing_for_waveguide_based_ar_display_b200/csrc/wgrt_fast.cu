@@ -582,23 +582,29 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // tile size: one work tile should hold whole runs.  A single warp measures the first run.
 // ---------------------------------------------------------------------------------------------
-__global__ void pick_tile_kernel(const __grid_constant__ wgrt_problem_t p, int* tile_size, int* work_counter) {
-  const int lane = threadIdx.x;
-  if (lane == 0) *work_counter = 0;
+__global__ void __launch_bounds__(1024) pick_tile_kernel(const __grid_constant__ wgrt_problem_t p, int* tile_size,
+                                                         int* work_counter) {
+  __shared__ int s_run;
+  if (threadIdx.x == 0) {
+    *work_counter = 0;
+    s_run = INT_MAX;
+  }
   if (p.tile_hint) {
-    if (lane == 0) *tile_size = static_cast<int>(p.tile_hint);
+    if (threadIdx.x == 0) *tile_size = static_cast<int>(p.tile_hint);
     return;
   }
-  const int64_t limit = p.num_rays < (1 << 16) ? p.num_rays : (1 << 16);
+  __syncthreads();
+  const int limit = static_cast<int>(p.num_rays < (1 << 16) ? p.num_rays : (1 << 16));
   const float km = p.m[0], kn = p.n[0], kl = p.lmd_num[0];
-  int64_t run = limit;
-  for (int64_t base = 1; base < limit; base += 32) {
-    const int64_t i = base + lane;
-    const bool bad = i < limit && (p.m[i] != km || p.n[i] != kn || p.lmd_num[i] != kl);
-    const unsigned b = __ballot_sync(FULL_MASK, bad);
-    if (b) { run = base + __ffs(b) - 1; break; }
+  for (int i = 1 + threadIdx.x; i < limit; i += blockDim.x) {
+    if (p.m[i] != km || p.n[i] != kn || p.lmd_num[i] != kl) {
+      atomicMin(&s_run, i);
+      break;  // later indices of this thread are larger
+    }
   }
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t run = s_run == INT_MAX ? limit : s_run;
     const int64_t target = 2560;  // rays per tile: ~20 per lane keeps the end-of-run tail small
     int64_t t;
     if (run >= target) {
@@ -618,7 +624,47 @@ __device__ __forceinline__ int total_ring_verts(const RegionStatic& st) {
   return st.offsets ? static_cast<int>(st.offsets[st.npoly]) : st.nverts;
 }
 
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// The region index depends only on the vertex / offset CONTENT and the grid geometry.  Hash them on
+// the device at every launch (a few KB) and rebuild the index only when the hash changed: the
+// runner launches the kernel num_iter times on the same design (gpu_ray_tracing_pro_fullColor.py:
+// 169-177).  state[0] = hash of the index currently built, state[1] = dirty flag for this launch.
+__global__ void region_hash_kernel(const __grid_constant__ RegionSet rs, unsigned long long* state, int force) {
+  __shared__ unsigned long long s_acc[256];
+  unsigned long long acc = 0;
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    const RegionStatic& st = rs.st[r];
+    const unsigned long long tag = mix64(0x1000ull * (r + 1));
+    if (threadIdx.x == 0)
+      acc += mix64(tag ^ mix64((static_cast<unsigned long long>(st.nverts) << 32) ^ st.npoly) ^
+                   mix64((static_cast<unsigned long long>(st.n) << 32) ^ (st.nc << 8) ^ st.shift));
+    const unsigned long long* v = reinterpret_cast<const unsigned long long*>(st.verts);
+    for (int i = threadIdx.x; i < 2 * st.nverts; i += blockDim.x) acc += mix64(v[i] ^ mix64(tag + i));
+    if (st.offsets)
+      for (int i = threadIdx.x; i <= st.npoly; i += blockDim.x)
+        acc += mix64(static_cast<unsigned long long>(st.offsets[i]) ^ mix64(tag + 0x80000000ull + i));
+  }
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_acc[threadIdx.x] += s_acc[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long h = s_acc[0] | 1ull;  // never 0, the "nothing built" value
+    state[1] = (force || state[0] != h) ? 1ull : 0ull;
+    state[0] = h;
+  }
+}
+
 __global__ void region_bbox_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
   const RegionStatic& st = rs.st[blockIdx.x];
   __shared__ double s_min[2][256], s_max[2][256];
   const int nv = min(total_ring_verts(st), st.nverts);
@@ -649,8 +695,8 @@ __global__ void region_bbox_kernel(const __grid_constant__ RegionSet rs) {
     const double pad_x = 1e-3 * (xmax - xmin) + 1e-9, pad_y = 1e-3 * (ymax - ymin) + 1e-9;
     d.x0 = xmin - pad_x;
     d.y0 = ymin - pad_y;
-    d.cell_dx = (xmax - xmin + 2.0 * pad_x) / st.nx;
-    d.cell_dy = (ymax - ymin + 2.0 * pad_y) / st.ny;
+    d.cell_dx = (xmax - xmin + 2.0 * pad_x) / st.n;
+    d.cell_dy = (ymax - ymin + 2.0 * pad_y) / st.n;
     d.inv_dx = 1.0 / d.cell_dx;
     d.inv_dy = 1.0 / d.cell_dy;
     rs.dyn[blockIdx.x] = d;
@@ -659,14 +705,21 @@ __global__ void region_bbox_kernel(const __grid_constant__ RegionSet rs) {
 
 __device__ __forceinline__ double margin_of(double cell) { return 0.02 * cell + 1e-11; }
 
+// Row masks: bit i of row r is set when the edge (prev(i) -> i) can matter to a point whose y lies in
+// row r (plus margin).  blockIdx.z = 0 builds the fine rows, 1 the coarse rows.
 __global__ void region_rowmask_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
   const RegionStatic& st = rs.st[blockIdx.y];
   const RegionDyn d = rs.dyn[blockIdx.y];
+  const bool coarse = blockIdx.z == 1;
+  const int nrows = coarse ? st.nc : st.n;
+  const double row_h = coarse ? d.cell_dy * (1 << st.shift) : d.cell_dy;
+  uint32_t* out = coarse ? st.rowmask_coarse : st.rowmask;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= st.ny * st.words) return;
+  if (t >= nrows * st.words) return;
   const int row = t / st.words, word = t - row * st.words;
-  const double mrg = margin_of(d.cell_dy);
-  const double row_lo = d.y0 + row * d.cell_dy - mrg, row_hi = d.y0 + (row + 1) * d.cell_dy + mrg;
+  const double mrg = margin_of(row_h);
+  const double row_lo = d.y0 + row * row_h - mrg, row_hi = d.y0 + (row + 1) * row_h + mrg;
   const int nv = min(total_ring_verts(st), st.nverts);
   uint32_t bits = 0;
   int k = 0;
@@ -680,21 +733,14 @@ __global__ void region_rowmask_kernel(const __grid_constant__ RegionSet rs) {
     const double yi = st.verts[2 * i + 1], yj = st.verts[2 * j + 1];
     if (!(fmax(yi, yj) < row_lo || fmin(yi, yj) > row_hi)) bits |= 1u << b;
   }
-  st.rowmask[t] = bits;
+  out[t] = bits;
 }
 
-__global__ void region_cells_kernel(const __grid_constant__ RegionSet rs) {
-  const RegionStatic& st = rs.st[blockIdx.y];
-  const RegionDyn d = rs.dyn[blockIdx.y];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= st.nx * st.ny) return;
-  const int iy = t / st.nx, ix = t - iy * st.nx;
-  const double mx = margin_of(d.cell_dx), my = margin_of(d.cell_dy);
-  const double x_lo = d.x0 + ix * d.cell_dx - mx, x_hi = d.x0 + (ix + 1) * d.cell_dx + mx;
-  const double y_lo = d.y0 + iy * d.cell_dy - my, y_hi = d.y0 + (iy + 1) * d.cell_dy + my;
-  const double cx = d.x0 + (ix + 0.5) * d.cell_dx, cy = d.y0 + (iy + 0.5) * d.cell_dy;
-  const uint32_t* mask = st.rowmask + static_cast<size_t>(iy) * st.words;
-  uint8_t code = CELL_NONE;
+// Classify one grid cell [x_lo, x_hi] x [y_lo, y_hi] (already inflated by the safety margin) with
+// centre (cx, cy), looking only at the edges in `mask`.
+__device__ __forceinline__ uint8_t classify_cell(const RegionStatic& st, const uint32_t* __restrict__ mask, double x_lo,
+                                                 double x_hi, double y_lo, double y_hi, double cx, double cy,
+                                                 uint32_t& detail) {
   int first_unc = -1, last_unc = -1, hit_ring = -1;
   for (int k = 0; k < st.npoly && hit_ring < 0; ++k) {
     const int s = ring_begin(st.offsets, st.nverts, k), e = ring_begin(st.offsets, st.nverts, k + 1);
@@ -733,15 +779,50 @@ __global__ void region_cells_kernel(const __grid_constant__ RegionSet rs) {
       hit_ring = k;   // certainly inside ring k: later rings can never be the first hit
     }
   }
-  uint32_t detail = 0;
+  detail = 0;
   if (first_unc >= 0) {
-    code = CELL_AMBIG;
     detail = hit_ring >= 0 ? pack_detail(first_unc, hit_ring, hit_ring) : pack_detail(first_unc, last_unc + 1, 255);
-  } else if (hit_ring >= 0) {
-    code = static_cast<uint8_t>(hit_ring);
+    return CELL_AMBIG;
   }
-  st.detail[t] = detail;
-  st.cells[t] = code;
+  return hit_ring >= 0 ? static_cast<uint8_t>(hit_ring) : CELL_NONE;
+}
+
+__global__ void region_coarse_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  const RegionStatic& st = rs.st[blockIdx.y];
+  const RegionDyn d = rs.dyn[blockIdx.y];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= st.nc * st.nc) return;
+  const int iy = t / st.nc, ix = t - iy * st.nc;
+  const double w = d.cell_dx * (1 << st.shift), h = d.cell_dy * (1 << st.shift);
+  const double mx = margin_of(w), my = margin_of(h);
+  uint32_t detail;
+  st.coarse[t] = classify_cell(st, st.rowmask_coarse + static_cast<size_t>(iy) * st.words, d.x0 + ix * w - mx,
+                               d.x0 + (ix + 1) * w + mx, d.y0 + iy * h - my, d.y0 + (iy + 1) * h + my,
+                               d.x0 + (ix + 0.5) * w, d.y0 + (iy + 0.5) * h, detail);
+}
+
+// One block per coarse cell; only MIXED coarse cells get their (1 << shift)^2 fine cells classified.
+__global__ void region_fine_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  const RegionStatic& st = rs.st[blockIdx.y];
+  if (static_cast<int>(blockIdx.x) >= st.nc * st.nc) return;
+  if (st.coarse[blockIdx.x] != CELL_AMBIG) return;
+  const RegionDyn d = rs.dyn[blockIdx.y];
+  const int cy = blockIdx.x / st.nc, cx = blockIdx.x - cy * st.nc;
+  const int S = 1 << st.shift;
+  const double mx = margin_of(d.cell_dx), my = margin_of(d.cell_dy);
+  for (int t = threadIdx.x; t < S * S; t += blockDim.x) {
+    const int iy = (cy << st.shift) + t / S, ix = (cx << st.shift) + (t & (S - 1));
+    uint32_t detail;
+    const uint8_t code = classify_cell(st, st.rowmask + static_cast<size_t>(iy) * st.words, d.x0 + ix * d.cell_dx - mx,
+                                       d.x0 + (ix + 1) * d.cell_dx + mx, d.y0 + iy * d.cell_dy - my,
+                                       d.y0 + (iy + 1) * d.cell_dy + my, d.x0 + (ix + 0.5) * d.cell_dx,
+                                       d.y0 + (iy + 0.5) * d.cell_dy, detail);
+    const size_t cell = static_cast<size_t>(iy) * st.n + ix;
+    st.cells[cell] = code;
+    if (code == CELL_AMBIG) st.detail[cell] = detail;
+  }
 }
 
 template <bool COUNT>
@@ -802,15 +883,17 @@ __global__ void __launch_bounds__(256) pupil_sums_kernel(const float* __restrict
 
 }  // namespace
 
-cudaError_t launch_region_build(const RegionSet& rs, cudaStream_t s) {
+cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s) {
+  region_hash_kernel<<<1, 256, 0, s>>>(rs, rs.hash_state, force ? 1 : 0);
   region_bbox_kernel<<<NUM_REGIONS, 256, 0, s>>>(rs);
-  int max_rw = 0, max_cells = 0;
+  int max_rw = 1, max_coarse = 1;
   for (int r = 0; r < NUM_REGIONS; ++r) {
-    max_rw = max(max_rw, rs.st[r].ny * rs.st[r].words);
-    max_cells = max(max_cells, rs.st[r].nx * rs.st[r].ny);
+    max_rw = max(max_rw, rs.st[r].n * rs.st[r].words);
+    max_coarse = max(max_coarse, rs.st[r].nc * rs.st[r].nc);
   }
-  region_rowmask_kernel<<<dim3((max_rw + 127) / 128, NUM_REGIONS), 128, 0, s>>>(rs);
-  region_cells_kernel<<<dim3((max_cells + 127) / 128, NUM_REGIONS), 128, 0, s>>>(rs);
+  region_rowmask_kernel<<<dim3((max_rw + 127) / 128, NUM_REGIONS, 2), 128, 0, s>>>(rs);
+  region_coarse_kernel<<<dim3((max_coarse + 127) / 128, NUM_REGIONS), 128, 0, s>>>(rs);
+  region_fine_kernel<<<dim3(max_coarse, NUM_REGIONS), 256, 0, s>>>(rs);
   return cudaGetLastError();
 }
 
@@ -818,7 +901,7 @@ cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* 
                              unsigned long long* counters, int num_sms, cudaStream_t s) {
   if (p.num_rays == 0) return cudaSuccess;
   int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
-  pick_tile_kernel<<<1, 32, 0, s>>>(p, tile_size, work_counter);
+  pick_tile_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter);
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   const size_t smem = walk_smem_queue_offset(rows) + (WALK_THREADS / 32) * sizeof(WarpQueue);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;

@@ -4,7 +4,10 @@
 // is_inside_or_on_edge (GRTF:63-71 -> GRTF:52-61 and GRTF:36-50) over every ring in order and
 // every edge of each ring, twice.  That scan is ~92 % of its arithmetic.
 // Here each region set (in-coupler, effective regions 1 and 2, fold-coupler slices, out-coupler
-// slices) gets a uniform cell grid over its bounding box:
+// slices) gets a two-level uniform grid over its bounding box.  The coarse level (64 x 64 bytes,
+// resident in L1) settles every query that falls in a coarse cell no edge comes near; coarse cells
+// marked MIXED defer to the fine level (4096 x 4096 by default, populated only under MIXED coarse
+// cells).  Cell codes, on both levels:
 //
 //   cell code  0..253 : every point that maps to this cell is inside ring <code> and in no
 //                       earlier ring -> the reference's first-hit index, no arithmetic
@@ -30,20 +33,22 @@ namespace wgrt {
 
 // Region descriptor as the walk kernels see it (shared memory copy: static + device-computed part).
 struct alignas(16) Region {
-  double x0, y0, inv_dx, inv_dy;
+  double x0, y0, inv_dx, inv_dy;   // fine-cell coordinates: fx = (x - x0) * inv_dx in [0, n)
+  const uint8_t* coarse;
   const uint8_t* cells;
   const uint32_t* detail;
   const uint32_t* rowmask;
   const double* verts;
   const int64_t* offsets;
-  int nverts, npoly, nx, ny, words;
-  int pad_[3];
+  int nverts, npoly, n, nc, shift, words;
+  int pad_[2];
 };
 
 __device__ __forceinline__ void region_load(Region& r, const RegionStatic& st, const RegionDyn& dy) {
   r.x0 = dy.x0; r.y0 = dy.y0; r.inv_dx = dy.inv_dx; r.inv_dy = dy.inv_dy;
-  r.cells = st.cells; r.detail = st.detail; r.rowmask = st.rowmask; r.verts = st.verts; r.offsets = st.offsets;
-  r.nverts = st.nverts; r.npoly = st.npoly; r.nx = st.nx; r.ny = st.ny; r.words = st.words;
+  r.coarse = st.coarse; r.cells = st.cells; r.detail = st.detail; r.rowmask = st.rowmask; r.verts = st.verts;
+  r.offsets = st.offsets;
+  r.nverts = st.nverts; r.npoly = st.npoly; r.n = st.n; r.nc = st.nc; r.shift = st.shift; r.words = st.words;
 }
 
 __device__ __forceinline__ int ring_begin(const int64_t* off, int nverts, int k) {
@@ -107,13 +112,16 @@ __device__ __forceinline__ int region_locate(const Region& r, double x, double y
   const double fx = (x - r.x0) * r.inv_dx;
   const double fy = (y - r.y0) * r.inv_dy;
   // also rejects NaN coordinates, which the literal test classifies as outside
-  if (!(fx >= 0.0 && fy >= 0.0 && fx < static_cast<double>(r.nx) && fy < static_cast<double>(r.ny))) return -1;
+  const double lim = static_cast<double>(r.n);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return -1;
   const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
-  const int cell = iy * r.nx + ix;
-  const uint8_t code = __ldg(r.cells + cell);
-  if (code == CELL_NONE) return -1;
-  if (code != CELL_AMBIG) return code;
-  return region_locate_exact<COUNT>(r, x, y, cell, iy, cn);
+  uint8_t code = __ldg(r.coarse + (iy >> r.shift) * r.nc + (ix >> r.shift));
+  if (code == CELL_AMBIG) {  // MIXED coarse cell: ask the fine level
+    const int cell = iy * r.n + ix;
+    code = __ldg(r.cells + cell);
+    if (code == CELL_AMBIG) return region_locate_exact<COUNT>(r, x, y, cell, iy, cn);
+  }
+  return code == CELL_NONE ? -1 : code;
 }
 
 }  // namespace wgrt
