@@ -1,0 +1,75 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2 and 3): partition, per-ray RNG seeding, and the
+single bin all-reduce must reproduce the single-process result bit for bit.  The trace callable is
+the CPU oracle here (tests may use it); on GPUs it is the engine's kernel object."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import multi_gpu, synthetic_inputs as si
+    from oracle import oracle
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    scene = si.make_scene(5, 3, 40, seed=21)
+    pts = si.points_in_disc(scene.geom["IC"], 20, 22)
+    EB, rng, span = multi_gpu.run_partitioned(scene, pts, lambda *a: oracle.trace(*a, num_threads=2), num_iter=2)
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), EB=EB, rng=rng, span=np.array(span))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_run_equals_single_process(world, tmp_path, oracle):
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import multi_gpu, synthetic_inputs as si
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    scene = si.make_scene(5, 3, 40, seed=21)
+    pts = si.points_in_disc(scene.geom["IC"], 20, 22)
+    # single process = world size 1 through the same code path
+    EB1, rng1, span1 = multi_gpu.run_partitioned(scene, pts, oracle.trace, num_iter=2, world_size=1, rank=0)
+    assert span1 == (0, 5 * 3 * 3 * 40)
+    rng_all = np.zeros_like(rng1)
+    for r in range(world):
+        d = np.load(tmp_path / f"rank{r}.npz")
+        assert np.array_equal(d["EB"], EB1), "reduced bins differ from the single-process run"
+        a, b = d["span"]
+        rng_all[a:b] = d["rng"]
+    assert np.array_equal(rng_all, rng1)
+    assert EB1.sum() > 0
+
+
+def test_cell_range_partition():
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.multi_gpu import cell_range
+    for n in (0, 1, 7, 22500):
+        for w in (1, 2, 3, 8):
+            spans = [cell_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        cell_range(10, 2, 2)
+
+
+def test_shard_rays_seeds_match_global_layout():
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import multi_gpu, synthetic_inputs as si
+    pts = np.random.default_rng(0).uniform(size=(4, 2))
+    full = si.build_ray_set(pts, 3, 2, 3, 8)
+    for w in (2, 4):
+        for r in range(w):
+            rays, (a, b) = multi_gpu.shard_rays(pts, 3, 2, 3, 8, w, r)
+            for f in si.RAY_FIELDS:
+                assert np.array_equal(getattr(rays, f), getattr(full, f)[a:b]), f
+            assert np.array_equal(rays.rng_states, full.rng_states[a:b])
