@@ -393,6 +393,65 @@ def main():
         e2e_deposits = float(e2e_args[32].sum(dtype=np.float64))
         line["e2e"]["deposits_match_device_run"] = bool(world > 1 or e2e_deposits == deposits_total)
 
+        # ---- the same job through the runner-level entry: the engine
+        #      derives the rays from the start points, so only LUTs / geometry go up and the bins come
+        #      back; ONE call = K launches with continuing RNG streams, as the runner does (RUN:169-177)
+        from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
+        del prob, keep, e2e_args, pinned
+        pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2024 + 1)
+        pin_keep, geom_p, luts_p = [], {}, {}
+        for src, dst in ((scene.geom, geom_p), (scene.luts, luts_p)):
+            for k, a in src.items():
+                tpin, view = pinned_like(a)
+                pin_keep.append(tpin); dst[k] = view
+        tpin, eb_view = pinned_like(scene.new_matrix_EB())
+        pin_keep.append(tpin)
+        seeds_t, seeds = pinned_like(si.initial_rng_states(N, offset=rank * N))
+        h2d_r = sum(a.nbytes for a in list(geom_p.values()) + list(luts_p.values())) + pts.shape[0] * 8 + seeds.nbytes
+        d2h_r = eb_view.nbytes + seeds.nbytes
+        tms_r = []
+        runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1, matrix_EB=eb_view,
+                                bins_start_zero=True, rng_states=seeds)                      # warm-up
+        seeds[...] = si.initial_rng_states(N, offset=rank * N)
+        barrier()
+        t0 = time.perf_counter()
+        runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=args.steps, matrix_EB=eb_view,
+                                bins_start_zero=True, rng_states=seeds, timings=tms_r)
+        wall_r = time.perf_counter() - t0
+        twr = torch.tensor([wall_r], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(twr, op=dist.ReduceOp.MAX)
+        # bounce count of THIS job (K launches from the runner's seeds): replay on the device with counters
+        _capi.reset_counters()
+        ck = kern.configured(counters=True).runner_layout(rpc // 2, N)
+        d_geom = {k: to_dev(v) for k, v in scene.geom.items()}
+        d_luts = {k: to_dev(v) for k, v in scene.luts.items()}
+        d_rng = to_dev(si.initial_rng_states(N, offset=rank * N))
+        d_eb = to_dev(scene.new_matrix_EB())
+        d_px, d_py = to_dev(pts[:, 0].astype(np.float32)), to_dev(pts[:, 1].astype(np.float32))
+        rargs = (d_px, d_py, None, None, None, None, None, None, None, None, None, None, d_rng,
+                 d_geom["IC"], d_geom["FC"], d_geom["FC_offset"], d_geom["OC"], d_geom["OC_offset"], scene.n_g,
+                 d_geom["eff_reg1"], d_geom["eff_reg2"], d_geom["eff_reg_FOV"], d_geom["eff_reg_FOV_range"],
+                 d_luts["lut_ic1"], d_luts["lut_ic2"], d_luts["lut_ic3"], d_luts["lut_fc1"], d_luts["lut_fc2"],
+                 d_luts["lut_oc1"], d_luts["lut_oc2"], d_geom["lut_TIR"], d_geom["lut_gap"], d_eb)
+        for _ in range(args.steps):
+            ck[1, 256, stream](*rargs)
+        cr = _capi.read_counters()
+        same = bool(np.array_equal(d_eb._t.cpu().numpy(), eb_view)) and \
+            bool(np.array_equal(d_rng._t.cpu().numpy().view(np.uint32), seeds))
+        br = torch.tensor([cr["bounces"]], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(br)
+        line["e2e_runner"] = {
+            "value": float(br.item()) / float(twr.item()), "unit": UNIT,
+            "ms_per_step": float(twr.item()) / max(args.steps, 1) * 1e3, "launches_per_call": args.steps,
+            "h2d_bytes_per_call": int(h2d_r), "d2h_bytes_per_call": int(d2h_r),
+            "breakdown_ms_per_call_rank0": {"h2d": tms_r[0], "trace": tms_r[1], "d2h": tms_r[2]},
+            "api": "runner.trace_full_color -> wgrt_trace_fullcolor_host with the runner layout "
+                   "(start points instead of 12 ray arrays); one call = K launches, RUN:169-177",
+            "bit_equal_to_device_launches": same}
+        del d_geom, d_luts, d_rng, d_eb, rargs
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle

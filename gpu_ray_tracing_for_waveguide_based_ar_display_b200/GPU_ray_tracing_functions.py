@@ -124,7 +124,8 @@ def _want(b: _Buf, name: str, dtype, ndim: int):
         raise ValueError(f"{name}: {len(b.shape)}-D array where {ndim}-D is required")
 
 
-def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int = 0
+def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int = 0,
+                 runner_points: int = 0, runner_first_cell: int = 0, num_rays: Optional[int] = None
                  ) -> Tuple[WgrtProblem, list]:
     """Validate the 33 positional kernel arguments and fill a ``wgrt_problem_t``.
 
@@ -132,6 +133,10 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     ``host=False`` requires device buffers (host arrays must have been staged by the caller).
     Raises ``TypeError`` / ``ValueError`` on dtype / rank / shape mismatches -- the analogue of
     Numba's typing error at the first launch.
+
+    Runner layout (``runner_points = P > 0``, see include/wgrt.h): ``x_v`` / ``y_v`` hold the P
+    start points, the arrays m_v .. delta_phase_v may be ``None``, ``num_rays`` gives the launch
+    size (a multiple of 2P) and ``rng_states`` may be ``None`` for the host entry point.
     """
     if len(args) != len(_ARG_NAMES):
         raise TypeError(f"process_rays_kernel_pro_fullColor takes {len(_ARG_NAMES)} positional "
@@ -141,7 +146,7 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
         if nm == "n_g":
             bufs.append(None)
             continue
-        if a is None and i in _DEAD_ARGS:
+        if a is None and (i in _DEAD_ARGS or (runner_points > 0 and (6 <= i <= 11 or (i == 12 and host)))):
             bufs.append(None)
             continue
         b = _describe(a, nm)
@@ -151,19 +156,31 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     B = dict(zip(_ARG_NAMES, bufs))
 
     N = None
-    for i in range(12):
-        nm = _ARG_NAMES[i]
-        b = B[nm]
-        if b is None:
-            continue
-        _want(b, nm, np.float32, 1)
-        if N is None:
-            N = b.shape[0]
-        elif b.shape[0] != N:
-            raise ValueError(f"{nm}: length {b.shape[0]} differs from x_v length {N}")
-    _want(B["rng_states"], "rng_states", np.uint32, 1)
-    if B["rng_states"].shape[0] != N:
-        raise ValueError("rng_states: length differs from the ray arrays")
+    if runner_points > 0:
+        for nm in ("x_v", "y_v"):
+            _want(B[nm], nm, np.float32, 1)
+            if B[nm].shape[0] != runner_points:
+                raise ValueError(f"{nm}: runner layout needs {runner_points} start points")
+        if num_rays is None or num_rays < 0 or num_rays % (2 * runner_points):
+            raise ValueError("runner layout: num_rays must be a multiple of 2 * runner_points")
+        N = int(num_rays)
+        for i in range(6, 12):
+            B[_ARG_NAMES[i]] = None
+    else:
+        for i in range(12):
+            nm = _ARG_NAMES[i]
+            b = B[nm]
+            if b is None:
+                continue
+            _want(b, nm, np.float32, 1)
+            if N is None:
+                N = b.shape[0]
+            elif b.shape[0] != N:
+                raise ValueError(f"{nm}: length {b.shape[0]} differs from x_v length {N}")
+    if B["rng_states"] is not None:
+        _want(B["rng_states"], "rng_states", np.uint32, 1)
+        if B["rng_states"].shape[0] != N:
+            raise ValueError("rng_states: length differs from the ray arrays")
     for nm in ("IC", "FC", "OC", "eff_reg1", "eff_reg2"):
         _want(B[nm], nm, np.float64, 2)
         if B[nm].shape[1] != 2:
@@ -208,6 +225,8 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
         raise ValueError(f"matrix_EB: leading shape {eb[:3]} where (L, Y, X) = {(L, Y, X)} is required")
     if n_FC > 250 or n_OC > 250:
         raise ValueError("at most 250 fold-coupler / out-coupler polygons are supported")
+    if runner_points > 0 and runner_first_cell * 2 * runner_points + N > L * X * Y * 2 * runner_points:
+        raise ValueError("runner layout: cell range exceeds L * X * Y")
 
     p = WgrtProblem()
     for i in range(12):
@@ -215,8 +234,10 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
         field = ("x", "y", "gap_x", "gap_y", "pol", "azi", "m", "n", "lmd_num", "te", "tm",
                  "delta_phase")[i]
         setattr(p, field, B[nm].ptr if B[nm] is not None else None)
-    p.rng_states = B["rng_states"].ptr
+    p.rng_states = B["rng_states"].ptr if B["rng_states"] is not None else None
     p.num_rays = N
+    p.runner_points = runner_points
+    p.runner_first_cell = runner_first_cell
     p.IC, p.IC_n = B["IC"].ptr, B["IC"].shape[0]
     p.FC, p.FC_n, p.FC_offset, p.n_FC = B["FC"].ptr, B["FC"].shape[0], B["FC_offset"].ptr, n_FC
     p.OC, p.OC_n, p.OC_offset, p.n_OC = B["OC"].ptr, B["OC"].shape[0], B["OC_offset"].ptr, n_OC
@@ -260,9 +281,10 @@ class _Launcher:
 class RayWalkKernel:
     """Stand-in for the Numba dispatcher of ``process_rays_kernel_pro_fullColor``."""
 
-    def __init__(self, flags: int = 0, tile_hint: int = 0):
+    def __init__(self, flags: int = 0, tile_hint: int = 0, runner: Optional[Tuple[int, int, int]] = None):
         self.flags = flags
         self.tile_hint = tile_hint
+        self.runner = runner      # (points P, first cell, num_rays) or None
 
     def __getitem__(self, config) -> _Launcher:
         if not isinstance(config, tuple):
@@ -279,7 +301,12 @@ class RayWalkKernel:
             f = (f | _capi.WGRT_FLAG_STRICT) if strict else (f & ~_capi.WGRT_FLAG_STRICT)
         if counters is not None:
             f = (f | _capi.WGRT_FLAG_COUNTERS) if counters else (f & ~_capi.WGRT_FLAG_COUNTERS)
-        return RayWalkKernel(f, self.tile_hint if tile_hint is None else tile_hint)
+        return RayWalkKernel(f, self.tile_hint if tile_hint is None else tile_hint, self.runner)
+
+    def runner_layout(self, points: int, num_rays: int, first_cell: int = 0) -> "RayWalkKernel":
+        """Launch on the runner's implicit ray layout (include/wgrt.h): ``x_v`` / ``y_v`` are the
+        ``points`` start points, m_v .. delta_phase_v may be ``None``."""
+        return RayWalkKernel(self.flags, self.tile_hint, (int(points), int(first_cell), int(num_rays)))
 
     def _launch(self, args, stream):
         lib = _capi.load_library()
@@ -307,7 +334,9 @@ class RayWalkKernel:
                     t = torch.from_numpy(view).cuda()
                 dev_args[i] = _TorchAlias(t, a.shape, a.dtype)
                 staged.append((a, t, nm in ("rng_states", "matrix_EB")))
-        prob, keep = pack_problem(dev_args, host=False, flags=self.flags, tile_hint=self.tile_hint)
+        rp, rc, rn = self.runner if self.runner else (0, 0, None)
+        prob, keep = pack_problem(dev_args, host=False, flags=self.flags, tile_hint=self.tile_hint,
+                                  runner_points=rp, runner_first_cell=rc, num_rays=rn)
         h = _stream_handle(stream)
         if any_host:
             import torch

@@ -168,8 +168,15 @@ int validate(const wgrt_problem_t* p) {
     return fail(WGRT_ERR_INVALID, "negative vertex count");
 #define NEED(f) \
   if (!p->f) return fail(WGRT_ERR_INVALID, "null pointer: " #f)
-  if (p->num_rays > 0) {
-    NEED(x); NEED(y); NEED(m); NEED(n); NEED(lmd_num); NEED(te); NEED(tm); NEED(delta_phase); NEED(rng_states);
+  if (p->runner_points < 0 || p->runner_first_cell < 0) return fail(WGRT_ERR_INVALID, "negative runner layout field");
+  if (p->runner_points > 0) {
+    if (p->num_rays % (2 * p->runner_points) != 0)
+      return fail(WGRT_ERR_INVALID, "runner layout: num_rays must be a multiple of 2 * runner_points");
+    if (p->runner_first_cell + p->num_rays / (2 * p->runner_points) > p->L * p->X * p->Y)
+      return fail(WGRT_ERR_INVALID, "runner layout: cell range exceeds L * X * Y");
+    if (p->num_rays > 0) { NEED(x); NEED(y); }
+  } else if (p->num_rays > 0) {
+    NEED(x); NEED(y); NEED(m); NEED(n); NEED(lmd_num); NEED(te); NEED(tm); NEED(delta_phase);
   }
   NEED(IC); NEED(FC); NEED(FC_offset); NEED(OC); NEED(OC_offset); NEED(eff_reg1); NEED(eff_reg2);
   NEED(eff_reg_FOV); NEED(eff_reg_FOV_range); NEED(lut_ic1); NEED(lut_ic2); NEED(lut_ic3); NEED(lut_fc1);
@@ -180,6 +187,7 @@ int validate(const wgrt_problem_t* p) {
 
 int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
   if (p.num_rays == 0) return WGRT_OK;
+  if (!p.rng_states) return fail(WGRT_ERR_INVALID, "null pointer: rng_states");
   if (p.flags & WGRT_FLAG_STRICT) {
     CUDA_TRY(launch_walk_strict(p, w.counters(), stream));
     return WGRT_OK;
@@ -268,14 +276,26 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* tim
   const size_t N = static_cast<size_t>(hp->num_rays);
   const size_t cells = static_cast<size_t>(hp->L * hp->X * hp->Y), fov = static_cast<size_t>(hp->X * hp->Y);
   const size_t eb_elems = cells * static_cast<size_t>(hp->EBy * hp->EBx);
+  const bool runner = hp->runner_points > 0;
+  const bool seed_rng = runner && hp->rng_states == nullptr;
+  const bool zero_bins = (hp->flags & WGRT_FLAG_BINS_ZERO) != 0;
+  if (!runner && N && !hp->rng_states) return fail(WGRT_ERR_INVALID, "null pointer: rng_states");
   struct Item { const void* src; void** dst; size_t bytes; };
   wgrt_problem_t dp = *hp;
   dp.gap_x = dp.gap_y = dp.pol = dp.azi = nullptr;  // never read by the walk
-  std::vector<Item> in = {
-      {hp->x, (void**)&dp.x, N * 4}, {hp->y, (void**)&dp.y, N * 4}, {hp->m, (void**)&dp.m, N * 4},
-      {hp->n, (void**)&dp.n, N * 4}, {hp->lmd_num, (void**)&dp.lmd_num, N * 4}, {hp->te, (void**)&dp.te, N * 4},
-      {hp->tm, (void**)&dp.tm, N * 4}, {hp->delta_phase, (void**)&dp.delta_phase, N * 4},
-      {hp->rng_states, (void**)&dp.rng_states, N * 4},
+  dp.flags &= ~WGRT_FLAG_BINS_ZERO;
+  const size_t ray_b = N * 4, pts_b = static_cast<size_t>(hp->runner_points) * 4;
+  std::vector<Item> in;
+  if (runner) {
+    dp.m = dp.n = dp.lmd_num = dp.te = dp.tm = dp.delta_phase = nullptr;
+    in = {{hp->x, (void**)&dp.x, pts_b}, {hp->y, (void**)&dp.y, pts_b}};
+  } else {
+    in = {{hp->x, (void**)&dp.x, ray_b}, {hp->y, (void**)&dp.y, ray_b}, {hp->m, (void**)&dp.m, ray_b},
+          {hp->n, (void**)&dp.n, ray_b}, {hp->lmd_num, (void**)&dp.lmd_num, ray_b}, {hp->te, (void**)&dp.te, ray_b},
+          {hp->tm, (void**)&dp.tm, ray_b}, {hp->delta_phase, (void**)&dp.delta_phase, ray_b}};
+  }
+  in.push_back({seed_rng ? nullptr : hp->rng_states, (void**)&dp.rng_states, ray_b});
+  const std::vector<Item> shared_items = {
       {hp->IC, (void**)&dp.IC, (size_t)hp->IC_n * 16}, {hp->FC, (void**)&dp.FC, (size_t)hp->FC_n * 16},
       {hp->FC_offset, (void**)&dp.FC_offset, (size_t)(hp->n_FC + 1) * 8},
       {hp->OC, (void**)&dp.OC, (size_t)hp->OC_n * 16},
@@ -291,8 +311,9 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* tim
       {hp->lut_oc1, (void**)&dp.lut_oc1, cells * hp->n_OC * hp->C_oc * 16},
       {hp->lut_oc2, (void**)&dp.lut_oc2, cells * hp->n_OC * hp->C_oc * 16},
       {hp->lut_TIR, (void**)&dp.lut_TIR, cells * 32}, {hp->lut_gap, (void**)&dp.lut_gap, cells * 64},
-      {hp->matrix_EB, (void**)&dp.matrix_EB, eb_elems * 4},
+      {zero_bins ? nullptr : hp->matrix_EB, (void**)&dp.matrix_EB, eb_elems * 4},
   };
+  in.insert(in.end(), shared_items.begin(), shared_items.end());
   size_t total = 0;
   for (auto& it : in) total += padded(it.bytes);
   CUDA_TRY(w->arena.reserve(total));
@@ -304,15 +325,18 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* tim
   for (auto& it : in) {
     *it.dst = ar.take(it.bytes);
     if (!*it.dst) return fail(WGRT_ERR_CUDA, "arena overflow");
-    if (it.bytes) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, st));
+    if (it.bytes && it.src) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, st));
   }
+  if (zero_bins) CUDA_TRY(cudaMemsetAsync(dp.matrix_EB, 0, eb_elems * 4, st));
+  if (seed_rng)
+    CUDA_TRY(launch_seed_rng(dp.rng_states, hp->num_rays, hp->runner_first_cell * 2 * hp->runner_points, st));
   CUDA_TRY(cudaEventRecord(ev[1], st));
   for (int k = 0; k < num_iter; ++k) {
     rc = trace_device(*w, dp, st);
     if (rc != WGRT_OK) return rc;
   }
   CUDA_TRY(cudaEventRecord(ev[2], st));
-  if (N) CUDA_TRY(cudaMemcpyAsync(hp->rng_states, dp.rng_states, N * 4, cudaMemcpyDeviceToHost, st));
+  if (N && hp->rng_states) CUDA_TRY(cudaMemcpyAsync(hp->rng_states, dp.rng_states, N * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaMemcpyAsync(hp->matrix_EB, dp.matrix_EB, eb_elems * 4, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaEventRecord(ev[3], st));
   CUDA_TRY(cudaStreamSynchronize(st));

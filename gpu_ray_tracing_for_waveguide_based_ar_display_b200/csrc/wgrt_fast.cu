@@ -281,7 +281,7 @@ __device__ __forceinline__ void take_order(const CellConst& cc, const double* __
 // In-coupling (GRTF:842-904) for 32 consecutive rays of the run: one ray per lane, fully coalesced
 // loads, every lane busy.  Rays that enter the waveguide are pushed on the warp's queue; the others
 // (about three quarters with realistic gratings) are finished here.  Returns the new queue fill.
-template <bool COUNT>
+template <bool COUNT, bool IMPLICIT>
 __device__ __forceinline__ int incouple_batch(const wgrt_problem_t& p, WalkShared& sh, const double* __restrict__ tab,
                                               int64_t run_begin, int first, int run_len, WarpQueue& q, int qn,
                                               int lane, unsigned lt_mask, Counts* cn) {
@@ -292,11 +292,25 @@ __device__ __forceinline__ int incouple_batch(const wgrt_problem_t& p, WalkShare
   if (i < run_len) {
     const int64_t idx = run_begin + i;
     r.idx = i;
-    r.x = static_cast<double>(__ldg(p.x + idx));
-    r.y = static_cast<double>(__ldg(p.y + idx));
-    r.a = static_cast<double>(__ldg(p.te + idx));
-    const double tm = static_cast<double>(__ldg(p.tm + idx));
-    const float dlf = __ldg(p.delta_phase + idx);
+    double tm;
+    float dlf;
+    if (IMPLICIT) {
+      // runner layout (RUN:82-115): P TE rays then P TM rays per cell, ray k starts at point k
+      const int64_t k = idx % (2 * p.runner_points);
+      const bool te_half = k < p.runner_points;
+      const int64_t pt = te_half ? k : k - p.runner_points;
+      r.x = static_cast<double>(__ldg(p.x + pt));
+      r.y = static_cast<double>(__ldg(p.y + pt));
+      r.a = te_half ? 1.0 : 0.0;
+      tm = te_half ? 0.0 : 1.0;
+      dlf = 0.0f;
+    } else {
+      r.x = static_cast<double>(__ldg(p.x + idx));
+      r.y = static_cast<double>(__ldg(p.y + idx));
+      r.a = static_cast<double>(__ldg(p.te + idx));
+      tm = static_cast<double>(__ldg(p.tm + idx));
+      dlf = __ldg(p.delta_phase + idx);
+    }
     r.rng = p.rng_states[idx];
     if (dlf == 0.0f) {
       r.w = cplx{tm, 0.0};
@@ -477,7 +491,7 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
   }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool IMPLICIT>
 __global__ void __launch_bounds__(WALK_THREADS, WGRT_WALK_MIN_BLOCKS)
 walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
                  int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
@@ -508,24 +522,36 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
     int64_t run_begin = t_begin;
     while (run_begin < t_end) {
       // ---- find the run of rays sharing the cell of ray run_begin --------------------------
-      const float km = __ldg(p.m + run_begin), kn = __ldg(p.n + run_begin), kl = __ldg(p.lmd_num + run_begin);
-      __syncthreads();  // previous run fully walked; shared tables may be overwritten
-      if (threadIdx.x == 0) sh.run_end = static_cast<int>(t_end - t_begin);
-      __syncthreads();
-      for (int64_t base = run_begin + 1; base < t_end; base += 4 * WALK_THREADS) {
-        int first_bad = INT_MAX;
+      float km, kn, kl;
+      int64_t run_end;
+      if (IMPLICIT) {
+        const int64_t rpc = 2 * p.runner_points;
+        const int64_t cell = p.runner_first_cell + run_begin / rpc;  // runner order: x outer, y, lambda inner
+        kl = static_cast<float>(cell % p.L);
+        kn = static_cast<float>((cell / p.L) % p.Y);
+        km = static_cast<float>(cell / (p.L * p.Y));
+        run_end = min(t_end, (run_begin / rpc + 1) * rpc);
+        __syncthreads();  // previous run fully walked; shared tables may be overwritten
+      } else {
+        km = __ldg(p.m + run_begin); kn = __ldg(p.n + run_begin); kl = __ldg(p.lmd_num + run_begin);
+        __syncthreads();  // previous run fully walked; shared tables may be overwritten
+        if (threadIdx.x == 0) sh.run_end = static_cast<int>(t_end - t_begin);
+        __syncthreads();
+        for (int64_t base = run_begin + 1; base < t_end; base += 4 * WALK_THREADS) {
+          int first_bad = INT_MAX;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int64_t i = base + k * WALK_THREADS + threadIdx.x;
-          if (i < t_end && first_bad == INT_MAX &&
-              (__ldg(p.m + i) != km || __ldg(p.n + i) != kn || __ldg(p.lmd_num + i) != kl))
-            first_bad = static_cast<int>(i - t_begin);
+          for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + k * WALK_THREADS + threadIdx.x;
+            if (i < t_end && first_bad == INT_MAX &&
+                (__ldg(p.m + i) != km || __ldg(p.n + i) != kn || __ldg(p.lmd_num + i) != kl))
+              first_bad = static_cast<int>(i - t_begin);
+          }
+          if (first_bad != INT_MAX) atomicMin(&sh.run_end, first_bad);
+          if (__syncthreads_or(first_bad != INT_MAX)) break;
         }
-        if (first_bad != INT_MAX) atomicMin(&sh.run_end, first_bad);
-        if (__syncthreads_or(first_bad != INT_MAX)) break;
+        __syncthreads();
+        run_end = t_begin + sh.run_end;
       }
-      __syncthreads();
-      const int64_t run_end = t_begin + sh.run_end;
       const int64_t m = static_cast<int64_t>(km), n = static_cast<int64_t>(kn), lm = static_cast<int64_t>(kl);
       const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
       if (valid) {
@@ -551,7 +577,7 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               run_open = false;
               break;
             }
-            qn = incouple_batch<COUNT>(p, sh, tab, run_begin, first, run_len, queue, qn, lane, lt_mask, &cn);
+            qn = incouple_batch<COUNT, IMPLICIT>(p, sh, tab, run_begin, first, run_len, queue, qn, lane, lt_mask, &cn);
           }
           if (nd && qn) {
             const int take = min(nd, qn);
@@ -593,13 +619,18 @@ __global__ void __launch_bounds__(1024) pick_tile_kernel(const __grid_constant__
     if (threadIdx.x == 0) *tile_size = static_cast<int>(p.tile_hint);
     return;
   }
+  if (p.runner_points > 0) {
+    if (threadIdx.x == 0) s_run = static_cast<int>(2 * p.runner_points < (1 << 16) ? 2 * p.runner_points : (1 << 16));
+  }
   __syncthreads();
   const int limit = static_cast<int>(p.num_rays < (1 << 16) ? p.num_rays : (1 << 16));
-  const float km = p.m[0], kn = p.n[0], kl = p.lmd_num[0];
-  for (int i = 1 + threadIdx.x; i < limit; i += blockDim.x) {
-    if (p.m[i] != km || p.n[i] != kn || p.lmd_num[i] != kl) {
-      atomicMin(&s_run, i);
-      break;  // later indices of this thread are larger
+  if (p.runner_points == 0) {
+    const float km = p.m[0], kn = p.n[0], kl = p.lmd_num[0];
+    for (int i = 1 + threadIdx.x; i < limit; i += blockDim.x) {
+      if (p.m[i] != km || p.n[i] != kn || p.lmd_num[i] != kl) {
+        atomicMin(&s_run, i);
+        break;  // later indices of this thread are larger
+      }
     }
   }
   __syncthreads();
@@ -825,6 +856,12 @@ __global__ void region_fine_kernel(const __grid_constant__ RegionSet rs) {
   }
 }
 
+// gpu_ray_tracing_pro_fullColor.py:158: rng_states[i] = 0x9E3779B9 * (i + 1) mod 2^32
+__global__ void seed_rng_kernel(uint32_t* __restrict__ states, int64_t n, int64_t first_index) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) states[i] = 0x9E3779B9u * static_cast<uint32_t>(first_index + i + 1);
+}
+
 template <bool COUNT>
 __global__ void locate_grid_kernel(const __grid_constant__ RegionSet rs, int region, const double* px,
                                    const double* py, int64_t n, int32_t* out, unsigned long long* counters) {
@@ -905,7 +942,9 @@ cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   const size_t smem = walk_smem_queue_offset(rows) + (WALK_THREADS / 32) * sizeof(WarpQueue);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
-  auto kern = count ? walk_fast_kernel<true> : walk_fast_kernel<false>;
+  const bool implicit = p.runner_points > 0;
+  auto kern = count ? (implicit ? walk_fast_kernel<true, true> : walk_fast_kernel<true, false>)
+                    : (implicit ? walk_fast_kernel<false, true> : walk_fast_kernel<false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
   int per_sm = 0;
@@ -916,6 +955,12 @@ cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const int64_t resident = static_cast<int64_t>(num_sms) * per_sm;
   const int grid = static_cast<int>(resident < min_tiles ? resident : (min_tiles > 1 ? min_tiles : 1));
   kern<<<grid, WALK_THREADS, smem, s>>>(p, rs, work_counter, tile_size, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_seed_rng(uint32_t* states, int64_t n, int64_t first_index, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  seed_rng_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(states, n, first_index);
   return cudaGetLastError();
 }
 

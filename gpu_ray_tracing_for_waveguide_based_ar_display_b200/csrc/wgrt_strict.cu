@@ -34,15 +34,28 @@ __device__ __forceinline__ Order jones4(const double* __restrict__ lut, int64_t 
 
 template <bool COUNT>
 __device__ void walk_one_ray(const wgrt_problem_t& p, int64_t idx, Counts* cn) {
-  double x = static_cast<double>(p.x[idx]);
-  double y = static_cast<double>(p.y[idx]);
-  const int64_t m = static_cast<int64_t>(p.m[idx]);
-  const int64_t n = static_cast<int64_t>(p.n[idx]);
-  const int64_t lm = static_cast<int64_t>(p.lmd_num[idx]);
+  double x, y, Ete, Etm, dl;
+  int64_t m, n, lm;
+  if (p.runner_points > 0) {  // runner layout, see include/wgrt.h
+    const int64_t rpc = 2 * p.runner_points, k = idx % rpc, cell = p.runner_first_cell + idx / rpc;
+    const int64_t pt = k < p.runner_points ? k : k - p.runner_points;
+    x = static_cast<double>(p.x[pt]);
+    y = static_cast<double>(p.y[pt]);
+    Ete = k < p.runner_points ? 1.0 : 0.0;
+    Etm = 1.0 - Ete;
+    dl = 0.0;
+    lm = cell % p.L; n = (cell / p.L) % p.Y; m = cell / (p.L * p.Y);
+  } else {
+    x = static_cast<double>(p.x[idx]);
+    y = static_cast<double>(p.y[idx]);
+    m = static_cast<int64_t>(p.m[idx]);
+    n = static_cast<int64_t>(p.n[idx]);
+    lm = static_cast<int64_t>(p.lmd_num[idx]);
+    Ete = static_cast<double>(p.te[idx]);
+    Etm = static_cast<double>(p.tm[idx]);
+    dl = static_cast<double>(p.delta_phase[idx]);
+  }
   if (m < 0 || m >= p.X || n < 0 || n >= p.Y || lm < 0 || lm >= p.L) return;  // outside every table
-  double Ete = static_cast<double>(p.te[idx]);
-  double Etm = static_cast<double>(p.tm[idx]);
-  double dl = static_cast<double>(p.delta_phase[idx]);
   uint32_t rng = p.rng_states[idx];
   double ener = 1.0;
   const double threshold = 0.0;

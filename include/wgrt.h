@@ -31,6 +31,9 @@ extern "C" {
 /* ---- flags ---------------------------------------------------------------------------- */
 #define WGRT_FLAG_STRICT 0x1u   /* literal thread-per-ray walk (parity anchor; slow)       */
 #define WGRT_FLAG_COUNTERS 0x2u /* accumulate the device event counters (see below)       */
+#define WGRT_FLAG_BINS_ZERO 0x4u /* host entry only: matrix_EB starts at zero (as the runner
+                                  * creates it, RUN:37) -> clear it on the device instead of
+                                  * uploading it */
 
 /* ---- event counters (uint64 each) ------------------------------------------------------ */
 enum {
@@ -121,6 +124,22 @@ typedef struct wgrt_problem {
 
   uint32_t flags;
   uint32_t tile_hint; /* 0 = automatic; otherwise rays per work tile of the fast path */
+
+  /*
+   * Runner layout (optional).  The reference runner builds its twelve
+   * ray arrays from P = num_rays_per_FoV/2 start points by a fixed rule
+   * (gpu_ray_tracing_pro_fullColor.py:82-115): cells in the order FoV-x outer, FoV-y, wavelength
+   * inner; per cell P TE rays (te=1, tm=0) then P TM rays (te=0, tm=1), all with delta_phase = 0,
+   * ray k of either half starting at point k.  With runner_points = P > 0 the engine derives every
+   * ray from that rule instead of reading arrays: x and y hold the P start points (float32, as the
+   * runner stores them), m / n / lmd_num / te / tm / delta_phase are ignored (may be NULL), ray i
+   * of this launch belongs to cell runner_first_cell + i / (2P), and num_rays must be a multiple of
+   * 2P.  Results are bit-identical to a launch on the materialised arrays.
+   * In wgrt_trace_fullcolor_host, rng_states may then be NULL: the states are seeded on the device
+   * as the runner does (RUN:158, global ray index = runner_first_cell * 2P + i) and not returned.
+   */
+  int64_t runner_points;
+  int64_t runner_first_cell;
 } wgrt_problem_t;
 
 /* Library / runtime ------------------------------------------------------------------------ */

@@ -198,6 +198,43 @@ def test_host_entry_point(oracle):
     assert all(t >= 0 for t in tms)
 
 
+# ---------------------------------------------------------------------------- runner layout (row f2)
+def test_runner_layout_equals_materialised_arrays(oracle):
+    """Implicit rays (start points + layout rule) must give exactly what the runner's arrays give."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
+    scene = si.make_scene(5, 4, 300, seed=61)
+    pts = si.points_in_disc(scene.geom["IC"], 150, 62)
+    scene.rays = si.build_ray_set(pts, 5, 4, 3, 300)
+    want = run_oracle(oracle, scene, 2)
+    assert_same(run_engine(KERNEL, scene, 2), want, "materialised")
+    # device launch on the implicit layout, fast and strict
+    N = scene.rays.num_rays
+    px = pts[:, 0].astype(np.float32); py = pts[:, 1].astype(np.float32)
+    for kern in (KERNEL, STRICT):
+        EB = scene.new_matrix_EB(); rng = scene.rays.rng_states.copy()
+        a = list(scene.kernel_args(EB, rng))
+        a[0], a[1] = px, py
+        for i in range(2, 12):
+            a[i] = None
+        for _ in range(2):
+            kern.runner_layout(150, N)[1, 256](*a)
+        assert_same((EB, rng), want, "runner layout / device")
+    # host entry: seeds generated on the device, bins cleared on the device
+    EB = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, 300, num_iter=2)
+    assert np.array_equal(EB, want[0])
+    # a cell sub-range with explicit RNG states (multi-GPU sharding)
+    c0, c1 = 7, 31
+    rng = si.initial_rng_states((c1 - c0) * 300, offset=c0 * 300)
+    EBp = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, 300, num_iter=2, first_cell=c0,
+                                  num_cells=c1 - c0, rng_states=rng)
+    assert np.array_equal(rng, want[1][c0 * 300:c1 * 300])
+    full = scene.rays
+    scene.rays = full.take(slice(c0 * 300, c1 * 300))
+    part = run_oracle(oracle, scene, 2)
+    scene.rays = full
+    assert np.array_equal(EBp, part[0])
+
+
 # ---------------------------------------------------------------------------- unit-level parity
 def test_xorshift_unit(oracle):
     g = np.load(os.path.join(GOLDEN, "units.npz"))

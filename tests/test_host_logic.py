@@ -128,6 +128,20 @@ def test_pack_problem_rejects_bad_arguments(small_scene):
         GRTF.pack_problem(a, host=False)                           # host arrays where device buffers are required
 
 
+def test_pack_problem_runner_layout(small_scene):
+    a = _args(small_scene)
+    pts = np.zeros(24, np.float32)
+    b = [pts, pts] + [None] * 10 + [None] + a[13:]
+    prob, _ = GRTF.pack_problem(b, host=True, runner_points=24, num_rays=4 * 3 * 3 * 48)
+    assert prob.runner_points == 24 and prob.num_rays == 1728 and not prob.rng_states
+    with pytest.raises(ValueError):
+        GRTF.pack_problem(b, host=True, runner_points=24, num_rays=1729)
+    with pytest.raises(ValueError):
+        GRTF.pack_problem(b, host=True, runner_points=24, num_rays=1728, runner_first_cell=1)
+    with pytest.raises(ValueError):
+        GRTF.pack_problem([pts[:5], pts] + b[2:], host=True, runner_points=24, num_rays=1728)
+
+
 def test_kernel_object_surface():
     k = GRTF.process_rays_kernel_pro_fullColor
     launcher = k[1024, 256]
