@@ -209,6 +209,25 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
   }
 }
 
+// Ray SoA data is touched once per launch: keep it out of L1 (which the region grids and LUT
+// gathers want) and mark it evict-first in L2.
+__device__ __forceinline__ float ld_stream(const float* ptr) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ void st_stream(uint32_t* ptr, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
 struct Ray {
   double x, y;     // position
   double a;        // |E_te|
@@ -305,13 +324,22 @@ __device__ __forceinline__ int incouple_batch(const wgrt_problem_t& p, WalkShare
       tm = te_half ? 0.0 : 1.0;
       dlf = 0.0f;
     } else {
-      r.x = static_cast<double>(__ldg(p.x + idx));
-      r.y = static_cast<double>(__ldg(p.y + idx));
-      r.a = static_cast<double>(__ldg(p.te + idx));
-      tm = static_cast<double>(__ldg(p.tm + idx));
-      dlf = __ldg(p.delta_phase + idx);
+      r.x = static_cast<double>(ld_stream(p.x + idx));
+      r.y = static_cast<double>(ld_stream(p.y + idx));
+      r.a = static_cast<double>(ld_stream(p.te + idx));
+      tm = static_cast<double>(ld_stream(p.tm + idx));
+      dlf = ld_stream(p.delta_phase + idx);
     }
-    r.rng = p.rng_states[idx];
+    r.rng = ld_stream(p.rng_states + idx);
+    // the batch this warp is likely to claim next (the CTA's other warps take the ones in between)
+    if (i + WALK_THREADS < run_len) {
+      const int64_t nxt = idx + WALK_THREADS;
+      prefetch_l2(p.rng_states + nxt);
+      if (!IMPLICIT) {
+        prefetch_l2(p.x + nxt); prefetch_l2(p.y + nxt); prefetch_l2(p.te + nxt); prefetch_l2(p.tm + nxt);
+        prefetch_l2(p.delta_phase + nxt);
+      }
+    }
     if (dlf == 0.0f) {
       r.w = cplx{tm, 0.0};
     } else {
@@ -352,7 +380,7 @@ __device__ __forceinline__ int incouple_batch(const wgrt_problem_t& p, WalkShare
         survived = in_ic;         // GRTF:899-902
       }
     }
-    if (!survived) p.rng_states[idx] = r.rng;
+    if (!survived) st_stream(p.rng_states + idx, r.rng);
   }
   __syncwarp();
   const unsigned surv = __ballot_sync(FULL_MASK, survived);
@@ -380,28 +408,35 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
   const int sinfo = live ? cc.sinfo[r.state] : 0;
   bool lost = false;  // the ray ends in this step
 
-  // ---- phase 1: the loop's effective-region test (GRTF:905-907) -----------------------------
+  // ---- phase 1: every region query whose point is already known, memory accesses overlapped:
+  //      the loop's effective-region test (GRTF:905-907), the coupler slice under the ray, and for
+  //      state 3 the eff_reg2 test its miss branch needs (GRTF:1103).  Queries are pure functions
+  //      of (x, y), so asking one whose answer ends up unused changes nothing.
+  const int region = sinfo & SI_REGION_MASK;
+  const int miss = (sinfo >> SI_MISS_SHIFT) & 3;
+  int hit = 0;
+  bool in_r2 = true;
   if (live) {
     if (COUNT) cn->c[WGRT_CNT_ITERS]++;
-    if (++r.iter > 100000 || region_locate<COUNT>(sh.reg[REG_R1], r.x, r.y, cn) < 0) lost = true;
+    const Region* const regs[3] = {&sh.reg[REG_R1], &sh.reg[region == SI_REGION_NONE ? REG_R1 : region],
+                                   &sh.reg[REG_R2]};
+    const bool want[3] = {true, region != SI_REGION_NONE, miss == 1};
+    int res[3];
+    region_locate_multi<COUNT, 3>(regs, want, r.x, r.y, res, cn);
+    if (++r.iter > 100000 || res[0] < 0) lost = true;
+    if (region != SI_REGION_NONE) hit = res[1];
+    in_r2 = res[2] >= 0;
   }
-  __syncwarp();
-
-  // ---- phase 2: which coupler slice is under the ray ------------------------------------------
-  int hit = 0;
-  const int region = sinfo & SI_REGION_MASK;
-  if (live && !lost && region != SI_REGION_NONE) hit = region_locate<COUNT>(sh.reg[region], r.x, r.y, cn);
   __syncwarp();
 
   // ---- phase 3: no grating: free TIR bounce (GRTF:1049-1052, 1102-1108, 1175-1178, 1244-1246) ---
   int query = -1;  // region set to consult in phase 5
   const bool event = live && !lost && hit >= 0;
   if (live && !lost && hit < 0) {
-    const int miss = (sinfo >> SI_MISS_SHIFT) & 3;
     if (miss == 2) {
       lost = true;
-    } else if (miss == 1) {
-      query = REG_R2;  // state 3 leaves the fold zone only when outside eff_reg2
+    } else if (miss == 1 && !in_r2) {
+      r.state = 4;  // GRTF:1103-1104: state 3 left the fold zone; no move in this iteration
     } else {
       const int g = (sinfo >> SI_GAP_SHIFT) & 3;
       r.x += cc.gap[2 * g];
@@ -465,28 +500,15 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
   }
   __syncwarp();
 
-  // ---- phase 5: follow-up region queries --------------------------------------------------------
+  // ---- phase 5: did the in-coupler event leave the ray inside the in-coupler? ---------------------
   if (query >= 0) {
-    const bool in = region_locate<COUNT>(sh.reg[query], r.x, r.y, cn) >= 0;
-    if (query == REG_R2) {
-      if (!in) {
-        r.state = 4;  // GRTF:1103-1104: no move in this iteration
-      } else {
-        const int g = (sinfo >> SI_GAP_SHIFT) & 3;
-        r.x += cc.gap[2 * g];
-        r.y += cc.gap[2 * g + 1];
-        r.w = cmul(r.w, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
-        if (COUNT) cn->c[WGRT_CNT_BOUNCES]++;
-      }
-    } else if (post == POST_IC_FWD) {
-      r.state = in ? 0 : 2;  // GRTF:932-935
-    } else if (!in) {
-      lost = true;  // GRTF:948-951
-    }
+    const bool in = region_locate<COUNT>(sh.reg[REG_IC], r.x, r.y, cn) >= 0;
+    if (post == POST_IC_FWD) r.state = in ? 0 : 2;  // GRTF:932-935
+    else if (!in) lost = true;                       // GRTF:948-951
   }
   __syncwarp();
   if (lost) {
-    p.rng_states[run_begin + r.idx] = r.rng;
+    st_stream(p.rng_states + run_begin + r.idx, r.rng);
     r.state = ST_DEAD;
   }
 }
@@ -537,18 +559,15 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         __syncthreads();  // previous run fully walked; shared tables may be overwritten
         if (threadIdx.x == 0) sh.run_end = static_cast<int>(t_end - t_begin);
         __syncthreads();
-        for (int64_t base = run_begin + 1; base < t_end; base += 4 * WALK_THREADS) {
-          int first_bad = INT_MAX;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int64_t i = base + k * WALK_THREADS + threadIdx.x;
-            if (i < t_end && first_bad == INT_MAX &&
-                (__ldg(p.m + i) != km || __ldg(p.n + i) != kn || __ldg(p.lmd_num + i) != kl))
-              first_bad = static_cast<int>(i - t_begin);
-          }
-          if (first_bad != INT_MAX) atomicMin(&sh.run_end, first_bad);
-          if (__syncthreads_or(first_bad != INT_MAX)) break;
+        // one pass over the rest of the tile with every load in flight at once (no early exit, no
+        // barrier per chunk: that serialised DRAM latency and was 10 % of the kernel)
+        int first_bad = INT_MAX;
+#pragma unroll 4
+        for (int64_t i = run_begin + 1 + threadIdx.x; i < t_end; i += WALK_THREADS) {
+          const bool bad = ld_stream(p.m + i) != km || ld_stream(p.n + i) != kn || ld_stream(p.lmd_num + i) != kl;
+          first_bad = min(first_bad, bad ? static_cast<int>(i - t_begin) : INT_MAX);
         }
+        if (first_bad != INT_MAX) atomicMin(&sh.run_end, first_bad);
         __syncthreads();
         run_end = t_begin + sh.run_end;
       }
@@ -636,13 +655,18 @@ __global__ void __launch_bounds__(1024) pick_tile_kernel(const __grid_constant__
   __syncthreads();
   if (threadIdx.x == 0) {
     const int64_t run = s_run == INT_MAX ? limit : s_run;
-    const int64_t target = 2560;  // rays per tile: ~20 per lane keeps the end-of-run tail small
+    // a tile should be a whole run (or whole runs): long runs are cut into equal pieces of at
+    // most 5120 rays, short ones are grouped up to at least 2560 (~20-40 rays per lane keeps the
+    // end-of-run tail small)
+    const int64_t t_min = 2560, t_max = 5120;
     int64_t t;
-    if (run >= target) {
-      const int64_t pieces = (run + target - 1) / target;
+    if (run > t_max) {
+      const int64_t pieces = (run + t_max - 1) / t_max;
       t = (run + pieces - 1) / pieces;
+    } else if (run >= t_min) {
+      t = run;
     } else {
-      t = run * ((target + run - 1) / run);
+      t = run * ((t_min + run - 1) / run);
     }
     *tile_size = static_cast<int>(t > 32 ? t : 32);
   }

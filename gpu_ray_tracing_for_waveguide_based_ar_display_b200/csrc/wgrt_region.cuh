@@ -124,4 +124,35 @@ __device__ __forceinline__ int region_locate(const Region& r, double x, double y
   return code == CELL_NONE ? -1 : code;
 }
 
+// Several region queries for the same point, with the memory accesses of all of them in flight
+// together: first every coarse byte, then every needed fine byte, then (rarely) the exact scans.
+// `want[k]` switches query k off (result -1).  Same answers as N calls of region_locate.
+template <bool COUNT, int N>
+__device__ __forceinline__ void region_locate_multi(const Region* const (&regs)[N], const bool (&want)[N], double x,
+                                                    double y, int (&hit)[N], Counts* cn) {
+  int cell[N], row[N];
+  uint8_t code[N];
+  bool ok[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const Region& r = *regs[k];
+    const double fx = (x - r.x0) * r.inv_dx, fy = (y - r.y0) * r.inv_dy, lim = static_cast<double>(r.n);
+    ok[k] = want[k] && fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim;
+    const int ix = ok[k] ? static_cast<int>(fx) : 0, iy = ok[k] ? static_cast<int>(fy) : 0;
+    row[k] = iy;
+    cell[k] = iy * r.n + ix;
+    code[k] = CELL_NONE;
+    if (ok[k]) code[k] = __ldg(r.coarse + (iy >> r.shift) * r.nc + (ix >> r.shift));
+    if (COUNT && want[k]) cn->c[WGRT_CNT_POLY_TESTS]++;
+  }
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (code[k] == CELL_AMBIG) code[k] = __ldg(regs[k]->cells + cell[k]);  // MIXED coarse cell: fine level
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    if (code[k] == CELL_AMBIG) hit[k] = region_locate_exact<COUNT>(*regs[k], x, y, cell[k], row[k], cn);
+    else hit[k] = code[k] == CELL_NONE ? -1 : code[k];
+  }
+}
+
 }  // namespace wgrt
