@@ -14,9 +14,11 @@ Printed JSON line (rank 0):
   value    ray-bounces / s, all ranks, inputs resident in HBM, CUDA events on the launch stream
            (a bounce = one position advance x += gap; counted exactly for the
            timed launches by replaying them with device counters from the saved RNG states)
-  e2e      the same metric through the C ABI host entry wgrt_trace_fullcolor_host: pinned HOST
-           buffers, H2D of rays / LUTs / geometry / bins and D2H of bins + RNG states inside the
-           timed region, every step
+  e2e      the same metric through the C ABI host entry wgrt_trace_fullcolor_host with pinned HOST
+           buffers, copies inside the timed region, every step.  The headline uses the runner
+           layout (the engine derives the rays from the start points: uploads LUTs + geometry +
+           points, downloads the bins); e2e_dropin is the literal 33-array call (uploads the 12
+           materialised ray arrays too) and e2e_job does the runner's K launches in one call
   roofline dominant kernel (walk_fast_kernel) against the FP64 FMA peak measured live on this GPU
            (the path is FP64-issue bound, not HBM bound: SURVEY.md section 8d); roofline_hbm gives
            the algorithmic-bytes view against MEASURED_PEAKS.json
@@ -349,11 +351,103 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers -----------------------------------
     if not args.no_e2e:
-        rng_saved_host = None
+        from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
         del dev_args, count_args
         torch.cuda.empty_cache()
-        pinned = []
-        e2e_args = []
+
+        def wall_max(seconds):
+            tw = torch.tensor([seconds], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            return float(tw.item())
+
+        def all_sum(v):
+            tv = torch.tensor([float(v)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tv)
+            return float(tv.item())
+
+        # (1) e2e -- the runner-level entry: what the reference runner does
+        # between having its inputs and having its bins (RUN:59-185), with the ray set derived on the
+        # device from the start points.  Every step is one complete job of ONE launch: upload LUTs,
+        # geometry and start points from pinned host memory, seed the RNG as RUN:158, walk, download the
+        # bins.  (Steps are independent jobs, so each uploads and downloads everything it needs.)
+        pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2024 + 1)
+        pin_keep, geom_p, luts_p = [], {}, {}
+        for src, dst in ((scene.geom, geom_p), (scene.luts, luts_p)):
+            for k, a in src.items():
+                tpin, view = pinned_like(a)
+                pin_keep.append(tpin); dst[k] = view
+        tpin, eb_view = pinned_like(scene.new_matrix_EB())
+        pin_keep.append(tpin)
+        first_cell = 0
+        h2d_r = sum(a.nbytes for a in list(geom_p.values()) + list(luts_p.values())) + pts.shape[0] * 8
+        d2h_r = eb_view.nbytes
+        for _ in range(2):
+            runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1, matrix_EB=eb_view,
+                                    bins_start_zero=True)
+        barrier()
+        parts = np.zeros(3)
+        tms_r = []
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1, matrix_EB=eb_view,
+                                    bins_start_zero=True, timings=tms_r)
+            parts += np.array(tms_r)
+        wall_r = wall_max(time.perf_counter() - t0)
+        # bounces of that job: replay launch #1 from the runner's seeds on the device with counters
+        _capi.reset_counters()
+        ck = kern.configured(counters=True).runner_layout(rpc // 2, N)
+        d_geom = {k: to_dev(v) for k, v in scene.geom.items()}
+        d_luts = {k: to_dev(v) for k, v in scene.luts.items()}
+        d_rng = to_dev(si.initial_rng_states(N))
+        d_eb = to_dev(scene.new_matrix_EB())
+        d_px, d_py = to_dev(pts[:, 0].astype(np.float32)), to_dev(pts[:, 1].astype(np.float32))
+        rargs = [d_px, d_py, None, None, None, None, None, None, None, None, None, None, d_rng,
+                 d_geom["IC"], d_geom["FC"], d_geom["FC_offset"], d_geom["OC"], d_geom["OC_offset"], scene.n_g,
+                 d_geom["eff_reg1"], d_geom["eff_reg2"], d_geom["eff_reg_FOV"], d_geom["eff_reg_FOV_range"],
+                 d_luts["lut_ic1"], d_luts["lut_ic2"], d_luts["lut_ic3"], d_luts["lut_fc1"], d_luts["lut_fc2"],
+                 d_luts["lut_oc1"], d_luts["lut_oc2"], d_geom["lut_TIR"], d_geom["lut_gap"], d_eb]
+        ck[1, 256, stream](*rargs)
+        c1 = _capi.read_counters()
+        same1 = bool(np.array_equal(d_eb._t.cpu().numpy(), eb_view))
+        line["e2e"] = {
+            "value": all_sum(c1["bounces"]) * args.steps / wall_r, "unit": UNIT,
+            "h2d_bytes_per_step": int(h2d_r), "d2h_bytes_per_step": int(d2h_r),
+            "ms_per_step": wall_r / max(args.steps, 1) * 1e3,
+            "breakdown_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
+                                            "d2h": parts[2] / args.steps},
+            "api": "runner.trace_full_color -> wgrt_trace_fullcolor_host, runner layout (start points instead of "
+                   "the 12 materialised ray arrays), one launch per call, pinned host buffers",
+            "bins_bit_equal_to_device_launch": same1}
+
+        # (2) e2e_job -- the same entry doing the runner's whole job in one call: K launches with
+        # continuing RNG streams (RUN:169-177), RNG states returned to the host as well
+        seeds_t, seeds = pinned_like(si.initial_rng_states(N))
+        pin_keep.append(seeds_t)
+        tms_j = []
+        barrier()
+        t0 = time.perf_counter()
+        runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=args.steps, matrix_EB=eb_view,
+                                bins_start_zero=True, rng_states=seeds, timings=tms_j)
+        wall_j = wall_max(time.perf_counter() - t0)
+        for _ in range(args.steps - 1):
+            ck[1, 256, stream](*rargs)
+        cj = _capi.read_counters()
+        samej = bool(np.array_equal(d_eb._t.cpu().numpy(), eb_view)) and \
+            bool(np.array_equal(d_rng._t.cpu().numpy().view(np.uint32), seeds))
+        line["e2e_job"] = {
+            "value": all_sum(cj["bounces"]) / wall_j, "unit": UNIT, "ms_per_step": wall_j / max(args.steps, 1) * 1e3,
+            "launches_per_call": args.steps, "h2d_bytes_per_call": int(h2d_r + seeds.nbytes),
+            "d2h_bytes_per_call": int(d2h_r + seeds.nbytes),
+            "breakdown_ms_per_call_rank0": {"h2d": tms_j[0], "trace": tms_j[1], "d2h": tms_j[2]},
+            "bins_and_rng_bit_equal_to_device_launches": samej}
+        del d_geom, d_luts, d_rng, d_eb, rargs, pin_keep, geom_p, luts_p, eb_view, seeds
+        torch.cuda.empty_cache()
+
+        # (3) e2e_dropin -- the literal 33-argument call on the runner's materialised arrays: H2D of all
+        # ray arrays, LUTs, geometry and bins plus D2H of bins and RNG states, every step
+        pinned, e2e_args = [], []
         for i, a in enumerate(host_args):
             if isinstance(a, np.ndarray) and i not in (2, 3, 4, 5):
                 tpin, view = pinned_like(a)
@@ -372,85 +466,22 @@ def main():
             _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 1, tms), lib)
         e2e_args[12][...] = rng_host0
         e2e_args[32][...] = 0
-        _capi.reset_counters()
-        prob.flags = 0
         barrier()
         t0 = time.perf_counter()
         parts = np.zeros(3)
         for _ in range(args.steps):
             _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 1, tms), lib)
             parts += np.array(list(tms))
-        wall = time.perf_counter() - t0
-        tw = torch.tensor([wall], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        wall = wall_max(time.perf_counter() - t0)
         # same RNG streams as the timed device-resident launches -> same bounce count
-        line["e2e"] = {"value": bounces_all / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h), "ms_per_step": float(tw.item()) / max(args.steps, 1) * 1e3,
-                       "breakdown_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
-                                                       "d2h": parts[2] / args.steps},
-                       "api": "wgrt_trace_fullcolor_host (pinned host buffers, 1 launch per call)"}
+        line["e2e_dropin"] = {"value": bounces_all / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                              "d2h_bytes_per_step": int(d2h), "ms_per_step": wall / max(args.steps, 1) * 1e3,
+                              "breakdown_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
+                                                              "d2h": parts[2] / args.steps},
+                              "api": "wgrt_trace_fullcolor_host on the 12 materialised ray arrays (pinned), 1 launch per call"}
         e2e_deposits = float(e2e_args[32].sum(dtype=np.float64))
-        line["e2e"]["deposits_match_device_run"] = bool(world > 1 or e2e_deposits == deposits_total)
-
-        # ---- the same job through the runner-level entry: the engine
-        #      derives the rays from the start points, so only LUTs / geometry go up and the bins come
-        #      back; ONE call = K launches with continuing RNG streams, as the runner does (RUN:169-177)
-        from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
+        line["e2e_dropin"]["deposits_match_device_run"] = bool(world > 1 or e2e_deposits == deposits_total)
         del prob, keep, e2e_args, pinned
-        pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2024 + 1)
-        pin_keep, geom_p, luts_p = [], {}, {}
-        for src, dst in ((scene.geom, geom_p), (scene.luts, luts_p)):
-            for k, a in src.items():
-                tpin, view = pinned_like(a)
-                pin_keep.append(tpin); dst[k] = view
-        tpin, eb_view = pinned_like(scene.new_matrix_EB())
-        pin_keep.append(tpin)
-        seeds_t, seeds = pinned_like(si.initial_rng_states(N, offset=rank * N))
-        h2d_r = sum(a.nbytes for a in list(geom_p.values()) + list(luts_p.values())) + pts.shape[0] * 8 + seeds.nbytes
-        d2h_r = eb_view.nbytes + seeds.nbytes
-        tms_r = []
-        runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1, matrix_EB=eb_view,
-                                bins_start_zero=True, rng_states=seeds)                      # warm-up
-        seeds[...] = si.initial_rng_states(N, offset=rank * N)
-        barrier()
-        t0 = time.perf_counter()
-        runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=args.steps, matrix_EB=eb_view,
-                                bins_start_zero=True, rng_states=seeds, timings=tms_r)
-        wall_r = time.perf_counter() - t0
-        twr = torch.tensor([wall_r], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(twr, op=dist.ReduceOp.MAX)
-        # bounce count of THIS job (K launches from the runner's seeds): replay on the device with counters
-        _capi.reset_counters()
-        ck = kern.configured(counters=True).runner_layout(rpc // 2, N)
-        d_geom = {k: to_dev(v) for k, v in scene.geom.items()}
-        d_luts = {k: to_dev(v) for k, v in scene.luts.items()}
-        d_rng = to_dev(si.initial_rng_states(N, offset=rank * N))
-        d_eb = to_dev(scene.new_matrix_EB())
-        d_px, d_py = to_dev(pts[:, 0].astype(np.float32)), to_dev(pts[:, 1].astype(np.float32))
-        rargs = (d_px, d_py, None, None, None, None, None, None, None, None, None, None, d_rng,
-                 d_geom["IC"], d_geom["FC"], d_geom["FC_offset"], d_geom["OC"], d_geom["OC_offset"], scene.n_g,
-                 d_geom["eff_reg1"], d_geom["eff_reg2"], d_geom["eff_reg_FOV"], d_geom["eff_reg_FOV_range"],
-                 d_luts["lut_ic1"], d_luts["lut_ic2"], d_luts["lut_ic3"], d_luts["lut_fc1"], d_luts["lut_fc2"],
-                 d_luts["lut_oc1"], d_luts["lut_oc2"], d_geom["lut_TIR"], d_geom["lut_gap"], d_eb)
-        for _ in range(args.steps):
-            ck[1, 256, stream](*rargs)
-        cr = _capi.read_counters()
-        same = bool(np.array_equal(d_eb._t.cpu().numpy(), eb_view)) and \
-            bool(np.array_equal(d_rng._t.cpu().numpy().view(np.uint32), seeds))
-        br = torch.tensor([cr["bounces"]], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(br)
-        line["e2e_runner"] = {
-            "value": float(br.item()) / float(twr.item()), "unit": UNIT,
-            "ms_per_step": float(twr.item()) / max(args.steps, 1) * 1e3, "launches_per_call": args.steps,
-            "h2d_bytes_per_call": int(h2d_r), "d2h_bytes_per_call": int(d2h_r),
-            "breakdown_ms_per_call_rank0": {"h2d": tms_r[0], "trace": tms_r[1], "d2h": tms_r[2]},
-            "api": "runner.trace_full_color -> wgrt_trace_fullcolor_host with the runner layout "
-                   "(start points instead of 12 ray arrays); one call = K launches, RUN:169-177",
-            "bit_equal_to_device_launches": same}
-        del d_geom, d_luts, d_rng, d_eb, rargs
 
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

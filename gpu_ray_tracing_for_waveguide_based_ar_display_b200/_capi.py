@@ -19,7 +19,7 @@ WGRT_FLAG_COUNTERS = 0x2
 WGRT_FLAG_BINS_ZERO = 0x4
 WGRT_NUM_COUNTERS = 16
 COUNTER_NAMES = ("rays", "bounces", "draws", "draw2", "draw3", "efield", "iters", "deposits",
-                 "poly_tests", "edge_visits", "straddle", "cross", "exact_fallback")
+                 "poly_tests", "edge_visits", "straddle", "cross", "exact_fallback", "warp_steps", "warp_batches")
 
 _f32p = C.c_void_p
 _f64p = C.c_void_p

@@ -597,6 +597,7 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               break;
             }
             qn = incouple_batch<COUNT, IMPLICIT>(p, sh, tab, run_begin, first, run_len, queue, qn, lane, lt_mask, &cn);
+            if (COUNT && lane == 0) cn.c[WGRT_CNT_WARP_BATCHES]++;
           }
           if (nd && qn) {
             const int take = min(nd, qn);
@@ -615,6 +616,7 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             if (!run_open) break;  // queue is empty too: every queued ray found a free lane above
             continue;
           }
+          if (COUNT && lane == 0) cn.c[WGRT_CNT_WARP_STEPS]++;
           walk_step<COUNT>(p, sh, tab, run_begin, lm, m, n, r, &cn);
         }
       }

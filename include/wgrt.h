@@ -50,6 +50,8 @@ enum {
   WGRT_CNT_STRADDLE,     /* edges with (yi>y)!=(yj>y): intersection arithmetic needed       */
   WGRT_CNT_CROSS,        /* on-segment cross products evaluated                             */
   WGRT_CNT_EXACT_FALLBACK, /* region queries that left the cell grid for the exact edge scan */
+  WGRT_CNT_WARP_STEPS,   /* fast walk: loop iterations executed per WARP (iters / this = live lanes) */
+  WGRT_CNT_WARP_BATCHES, /* fast walk: 32-ray in-coupling batches */
   WGRT_NUM_COUNTERS = 16
 };
 
