@@ -30,7 +30,7 @@ import numpy as np
 from . import _capi
 from ._capi import WgrtProblem
 
-__all__ = ["generate_points_in_polygon", "process_rays_kernel_pro_fullColor", "pack_problem",
+__all__ = ["generate_points_in_polygon", "process_rays_kernel_pro_fullColor", "process_rays_kernel_pro", "pack_problem",
            "RayWalkKernel"]
 
 
@@ -125,8 +125,8 @@ def _want(b: _Buf, name: str, dtype, ndim: int):
 
 
 def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int = 0,
-                 runner_points: int = 0, runner_first_cell: int = 0, num_rays: Optional[int] = None
-                 ) -> Tuple[WgrtProblem, list]:
+                 runner_points: int = 0, runner_first_cell: int = 0, num_rays: Optional[int] = None,
+                 single_lambda: bool = False, threshold: float = 0.0) -> Tuple[WgrtProblem, list]:
     """Validate the 33 positional kernel arguments and fill a ``wgrt_problem_t``.
 
     ``host=True`` requires NumPy arrays (used for the host entry point and by the test oracle);
@@ -137,6 +137,11 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     Runner layout (``runner_points = P > 0``, see include/wgrt.h): ``x_v`` / ``y_v`` hold the P
     start points, the arrays m_v .. delta_phase_v may be ``None``, ``num_rays`` gives the launch
     size (a multiple of 2P) and ``rng_states`` may be ``None`` for the host entry point.
+
+    ``single_lambda=True`` is the layout of ``process_rays_kernel_pro`` (GRTF:419-831): ``lmd_num`` is
+    ``None`` and the tables / bins lack the wavelength axis (LUTs [X,Y,C] or [n,X,Y,C], lut_TIR
+    [X,Y,4], lut_gap [X,Y,8], matrix_EB [Y,X,EBy,EBx]); they are the L = 1 case of the same memory
+    layout.  ``threshold`` is the energy gate of the fold / out-coupler branches.
     """
     if len(args) != len(_ARG_NAMES):
         raise TypeError(f"process_rays_kernel_pro_fullColor takes {len(_ARG_NAMES)} positional "
@@ -146,7 +151,8 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
         if nm == "n_g":
             bufs.append(None)
             continue
-        if a is None and (i in _DEAD_ARGS or (runner_points > 0 and (6 <= i <= 11 or (i == 12 and host)))):
+        if a is None and (i in _DEAD_ARGS or (single_lambda and i == 8) or
+                          (runner_points > 0 and (6 <= i <= 11 or (i == 12 and host)))):
             bufs.append(None)
             continue
         b = _describe(a, nm)
@@ -197,6 +203,17 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
             if off[0] != 0 or np.any(np.diff(off) < 0) or off[-1] > tot:
                 raise ValueError(f"{nm}: must start at 0, be non-decreasing and end within the vertex array")
 
+    if single_lambda:
+        # present the L-less arrays as L = 1 (same bytes)
+        for nm, nd in (("lut_TIR", 3), ("lut_gap", 3), ("lut_ic1", 3), ("lut_ic2", 3), ("lut_ic3", 3),
+                       ("lut_fc1", 4), ("lut_fc2", 4), ("lut_oc1", 4), ("lut_oc2", 4), ("matrix_EB", 4)):
+            b = B[nm]
+            if len(b.shape) != nd:
+                raise ValueError(f"{nm}: {len(b.shape)}-D array where {nd}-D is required (single-wavelength layout)")
+            lead = 1 if nm in ("lut_fc1", "lut_fc2", "lut_oc1", "lut_oc2") else 0
+            b.shape = b.shape[:lead] + (1,) + b.shape[lead:]
+        if B["lmd_num"] is not None:
+            raise TypeError("lmd_num is not an argument of the single-wavelength kernel")
     _want(B["lut_TIR"], "lut_TIR", np.float64, 4)
     _want(B["lut_gap"], "lut_gap", np.float64, 4)
     L, X, Y, k = B["lut_TIR"].shape
@@ -253,6 +270,7 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     p.matrix_EB, p.EBy, p.EBx = B["matrix_EB"].ptr, eb[3], eb[4]
     p.flags = flags
     p.tile_hint = tile_hint
+    p.threshold = float(threshold)
     return p, [b.owner for b in bufs if b is not None]
 
 
@@ -281,10 +299,13 @@ class _Launcher:
 class RayWalkKernel:
     """Stand-in for the Numba dispatcher of ``process_rays_kernel_pro_fullColor``."""
 
-    def __init__(self, flags: int = 0, tile_hint: int = 0, runner: Optional[Tuple[int, int, int]] = None):
+    def __init__(self, flags: int = 0, tile_hint: int = 0, runner: Optional[Tuple[int, int, int]] = None,
+                 single_lambda: bool = False, threshold: float = 0.0):
         self.flags = flags
         self.tile_hint = tile_hint
         self.runner = runner      # (points P, first cell, num_rays) or None
+        self.single_lambda = single_lambda
+        self.threshold = threshold
 
     def __getitem__(self, config) -> _Launcher:
         if not isinstance(config, tuple):
@@ -301,15 +322,22 @@ class RayWalkKernel:
             f = (f | _capi.WGRT_FLAG_STRICT) if strict else (f & ~_capi.WGRT_FLAG_STRICT)
         if counters is not None:
             f = (f | _capi.WGRT_FLAG_COUNTERS) if counters else (f & ~_capi.WGRT_FLAG_COUNTERS)
-        return RayWalkKernel(f, self.tile_hint if tile_hint is None else tile_hint, self.runner)
+        return RayWalkKernel(f, self.tile_hint if tile_hint is None else tile_hint, self.runner,
+                             self.single_lambda, self.threshold)
 
     def runner_layout(self, points: int, num_rays: int, first_cell: int = 0) -> "RayWalkKernel":
         """Launch on the runner's implicit ray layout (include/wgrt.h): ``x_v`` / ``y_v`` are the
         ``points`` start points, m_v .. delta_phase_v may be ``None``."""
-        return RayWalkKernel(self.flags, self.tile_hint, (int(points), int(first_cell), int(num_rays)))
+        return RayWalkKernel(self.flags, self.tile_hint, (int(points), int(first_cell), int(num_rays)),
+                             self.single_lambda, self.threshold)
 
     def _launch(self, args, stream):
         lib = _capi.load_library()
+        if self.single_lambda:
+            if len(args) != len(_ARG_NAMES) - 1:
+                raise TypeError(f"process_rays_kernel_pro takes {len(_ARG_NAMES) - 1} positional "
+                                f"arguments ({len(args)} given)")
+            args = tuple(args[:8]) + (None,) + tuple(args[8:])      # no lmd_num argument (GRTF:420-427)
         if len(args) != len(_ARG_NAMES):
             raise TypeError(f"process_rays_kernel_pro_fullColor takes {len(_ARG_NAMES)} positional "
                             f"arguments ({len(args)} given)")
@@ -336,7 +364,8 @@ class RayWalkKernel:
                 staged.append((a, t, nm in ("rng_states", "matrix_EB")))
         rp, rc, rn = self.runner if self.runner else (0, 0, None)
         prob, keep = pack_problem(dev_args, host=False, flags=self.flags, tile_hint=self.tile_hint,
-                                  runner_points=rp, runner_first_cell=rc, num_rays=rn)
+                                  runner_points=rp, runner_first_cell=rc, num_rays=rn,
+                                  single_lambda=self.single_lambda, threshold=self.threshold)
         h = _stream_handle(stream)
         if any_host:
             import torch
@@ -363,3 +392,5 @@ class _TorchAlias:
 
 
 process_rays_kernel_pro_fullColor = RayWalkKernel()
+# single-wavelength twin (GRTF:419-831): 32 arguments (no lmd_num), L-less tables, threshold 1e-15
+process_rays_kernel_pro = RayWalkKernel(single_lambda=True, threshold=1e-15)

@@ -158,6 +158,7 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
 int validate(const wgrt_problem_t* p) {
   if (!p) return fail(WGRT_ERR_INVALID, "null problem");
   if (p->num_rays < 0) return fail(WGRT_ERR_INVALID, "num_rays < 0");
+  if (!(p->threshold >= 0.0)) return fail(WGRT_ERR_INVALID, "threshold must be >= 0");
   if (p->L <= 0 || p->X <= 0 || p->Y <= 0 || p->EBx <= 0 || p->EBy <= 0)
     return fail(WGRT_ERR_INVALID, "L, X, Y, EBy, EBx must be positive");
   if (p->n_FC < 0 || p->n_OC < 0 || p->n_FC > 250 || p->n_OC > 250)
@@ -176,7 +177,8 @@ int validate(const wgrt_problem_t* p) {
       return fail(WGRT_ERR_INVALID, "runner layout: cell range exceeds L * X * Y");
     if (p->num_rays > 0) { NEED(x); NEED(y); }
   } else if (p->num_rays > 0) {
-    NEED(x); NEED(y); NEED(m); NEED(n); NEED(lmd_num); NEED(te); NEED(tm); NEED(delta_phase);
+    NEED(x); NEED(y); NEED(m); NEED(n); NEED(te); NEED(tm); NEED(delta_phase);
+    if (!p->lmd_num && p->L != 1) return fail(WGRT_ERR_INVALID, "lmd_num may be NULL only when L == 1");
   }
   NEED(IC); NEED(FC); NEED(FC_offset); NEED(OC); NEED(OC_offset); NEED(eff_reg1); NEED(eff_reg2);
   NEED(eff_reg_FOV); NEED(eff_reg_FOV_range); NEED(lut_ic1); NEED(lut_ic2); NEED(lut_ic3); NEED(lut_fc1);
@@ -291,7 +293,7 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* tim
     in = {{hp->x, (void**)&dp.x, pts_b}, {hp->y, (void**)&dp.y, pts_b}};
   } else {
     in = {{hp->x, (void**)&dp.x, ray_b}, {hp->y, (void**)&dp.y, ray_b}, {hp->m, (void**)&dp.m, ray_b},
-          {hp->n, (void**)&dp.n, ray_b}, {hp->lmd_num, (void**)&dp.lmd_num, ray_b}, {hp->te, (void**)&dp.te, ray_b},
+          {hp->n, (void**)&dp.n, ray_b}, {hp->lmd_num, (void**)&dp.lmd_num, hp->lmd_num ? ray_b : 0}, {hp->te, (void**)&dp.te, ray_b},
           {hp->tm, (void**)&dp.tm, ray_b}, {hp->delta_phase, (void**)&dp.delta_phase, ray_b}};
   }
   in.push_back({seed_rng ? nullptr : hp->rng_states, (void**)&dp.rng_states, ray_b});
@@ -323,8 +325,8 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* tim
   for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
   CUDA_TRY(cudaEventRecord(ev[0], st));
   for (auto& it : in) {
-    *it.dst = ar.take(it.bytes);
-    if (!*it.dst) return fail(WGRT_ERR_CUDA, "arena overflow");
+    *it.dst = (it.bytes || it.src) ? ar.take(it.bytes) : nullptr;
+    if (!*it.dst && (it.bytes || it.src)) return fail(WGRT_ERR_CUDA, "arena overflow");
     if (it.bytes && it.src) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, st));
   }
   if (zero_bins) CUDA_TRY(cudaMemsetAsync(dp.matrix_EB, 0, eb_elems * 4, st));

@@ -465,18 +465,19 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
     jones_apply(row, r.a, r.w, ote, otm);
     double esel = power_of(ote, otm) * row[8] * r.inv_cos;
     double esum = esel;
-    bool taken = u <= esum && (!gated || r.ener * esel > 0.0);
+    const double threshold = p.threshold;
+    bool taken = u <= esum && (!gated || r.ener * esel > threshold);
     if (!taken) {
       row = e + ENTRY_DOUBLES;
       jones_apply(row, r.a, r.w, ote, otm);
       esel = power_of(ote, otm) * row[8] * r.inv_cos;
       esum += esel;
-      taken = u <= esum && (!gated || r.ener * esel > 0.0);
+      taken = u <= esum && (!gated || r.ener * esel > threshold);
       if (!taken && three) {
         row = e + 2 * ENTRY_DOUBLES;
         jones_apply(row, r.a, r.w, ote, otm);
         esel = power_of(ote, otm) * row[8] * r.inv_cos;
-        taken = u <= esum + esel && r.ener * esel > 0.0;
+        taken = u <= esum + esel && r.ener * esel > threshold;
       }
     }
     if (!taken) {
@@ -555,7 +556,8 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         run_end = min(t_end, (run_begin / rpc + 1) * rpc);
         __syncthreads();  // previous run fully walked; shared tables may be overwritten
       } else {
-        km = __ldg(p.m + run_begin); kn = __ldg(p.n + run_begin); kl = __ldg(p.lmd_num + run_begin);
+        const bool has_l = p.lmd_num != nullptr;
+        km = __ldg(p.m + run_begin); kn = __ldg(p.n + run_begin); kl = has_l ? __ldg(p.lmd_num + run_begin) : 0.0f;
         __syncthreads();  // previous run fully walked; shared tables may be overwritten
         if (threadIdx.x == 0) sh.run_end = static_cast<int>(t_end - t_begin);
         __syncthreads();
@@ -564,7 +566,7 @@ walk_fast_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         int first_bad = INT_MAX;
 #pragma unroll 4
         for (int64_t i = run_begin + 1 + threadIdx.x; i < t_end; i += WALK_THREADS) {
-          const bool bad = ld_stream(p.m + i) != km || ld_stream(p.n + i) != kn || ld_stream(p.lmd_num + i) != kl;
+          const bool bad = ld_stream(p.m + i) != km || ld_stream(p.n + i) != kn || (has_l && ld_stream(p.lmd_num + i) != kl);
           first_bad = min(first_bad, bad ? static_cast<int>(i - t_begin) : INT_MAX);
         }
         if (first_bad != INT_MAX) atomicMin(&sh.run_end, first_bad);
@@ -646,9 +648,10 @@ __global__ void __launch_bounds__(1024) pick_tile_kernel(const __grid_constant__
   __syncthreads();
   const int limit = static_cast<int>(p.num_rays < (1 << 16) ? p.num_rays : (1 << 16));
   if (p.runner_points == 0) {
-    const float km = p.m[0], kn = p.n[0], kl = p.lmd_num[0];
+    const bool has_l = p.lmd_num != nullptr;
+    const float km = p.m[0], kn = p.n[0], kl = has_l ? p.lmd_num[0] : 0.0f;
     for (int i = 1 + threadIdx.x; i < limit; i += blockDim.x) {
-      if (p.m[i] != km || p.n[i] != kn || p.lmd_num[i] != kl) {
+      if (p.m[i] != km || p.n[i] != kn || (has_l && p.lmd_num[i] != kl)) {
         atomicMin(&s_run, i);
         break;  // later indices of this thread are larger
       }

@@ -50,7 +50,7 @@ __device__ void walk_one_ray(const wgrt_problem_t& p, int64_t idx, Counts* cn) {
     y = static_cast<double>(p.y[idx]);
     m = static_cast<int64_t>(p.m[idx]);
     n = static_cast<int64_t>(p.n[idx]);
-    lm = static_cast<int64_t>(p.lmd_num[idx]);
+    lm = p.lmd_num ? static_cast<int64_t>(p.lmd_num[idx]) : 0;
     Ete = static_cast<double>(p.te[idx]);
     Etm = static_cast<double>(p.tm[idx]);
     dl = static_cast<double>(p.delta_phase[idx]);
@@ -58,7 +58,7 @@ __device__ void walk_one_ray(const wgrt_problem_t& p, int64_t idx, Counts* cn) {
   if (m < 0 || m >= p.X || n < 0 || n >= p.Y || lm < 0 || lm >= p.L) return;  // outside every table
   uint32_t rng = p.rng_states[idx];
   double ener = 1.0;
-  const double threshold = 0.0;
+  const double threshold = p.threshold;  // GRTF:859 (0) or GRTF:444 (1e-15)
   double gap_x = 0.0, gap_y = 0.0, cos_theta = 0.0, norm;
   int state;
   if (COUNT) cn->c[WGRT_CNT_RAYS]++;

@@ -75,7 +75,7 @@ typedef struct wgrt_problem {
   const float* azi;
   const float* m;       /* FoV-x index, integer valued */
   const float* n;       /* FoV-y index, integer valued */
-  const float* lmd_num; /* wavelength index, integer valued */
+  const float* lmd_num; /* wavelength index, integer valued; NULL = 0 for every ray (needs L == 1) */
   const float* te;
   const float* tm;
   const float* delta_phase;
@@ -142,6 +142,15 @@ typedef struct wgrt_problem {
    */
   int64_t runner_points;
   int64_t runner_first_cell;
+
+  /*
+   * Energy gate of the fold / out-coupler branches, `ener_k > threshold`
+   * (GPU_ray_tracing_functions.py:1020 ff.).  0 for process_rays_kernel_pro_fullColor (GRTF:859);
+   * 1e-15 for its single-wavelength twin process_rays_kernel_pro (GRTF:444), which is otherwise
+   * the same walk with L = 1: pass lmd_num = NULL (every ray has wavelength index 0), LUTs
+   * [X, Y, C] as [1, X, Y, C] and bins [Y, X, EBy, EBx] as [1, Y, X, EBy, EBx].
+   */
+  double threshold;
 } wgrt_problem_t;
 
 /* Library / runtime ------------------------------------------------------------------------ */

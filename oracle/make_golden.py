@@ -194,12 +194,112 @@ def make_units(procs: int):
     print(f"units -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
 
 
+def single_lambda_args(scene, lam, EB, rng):
+    """The 32 arguments of process_rays_kernel_pro for wavelength index `lam` of a full-colour scene."""
+    a = list(scene.kernel_args(None, rng))
+    sel = scene.rays.lmd_num == lam
+    rays = [np.ascontiguousarray(x[sel]) for x in a[:12]]
+    out = rays[:8] + rays[9:12] + [rng]
+    out += a[13:23]
+    out += [np.ascontiguousarray(a[k][lam]) for k in (23, 24, 25)]              # lut_ic*: [X,Y,C]
+    out += [np.ascontiguousarray(a[k][:, lam]) for k in (26, 27, 28, 29)]       # lut_fc*, lut_oc*: [n,X,Y,C]
+    out += [np.ascontiguousarray(a[30][lam]), np.ascontiguousarray(a[31][lam]), EB]
+    return out, sel
+
+
+def _run_single_lambda_chunk(job):
+    recipe, lam, lo, hi = job
+    GRTF = import_reference()
+    scene = scene_from_recipe(recipe)
+    sel = scene.rays.lmd_num == lam
+    rng_all = scene.rays.rng_states[sel].copy()
+    EB = np.zeros(scene.eb_shape[1:], dtype=np.float32)
+    args, _ = single_lambda_args(scene, lam, EB, rng_all)
+    for k in list(range(8)) + [8, 9, 10, 11]:
+        args[k] = np.ascontiguousarray(args[k][lo:hi])
+    GRTF.process_rays_kernel_pro[(hi - lo + 31) // 32, 32](*args)
+    nz = np.flatnonzero(EB)
+    return lo, hi, args[11], nz, EB.ravel()[nz]
+
+
+def make_single_lambda(procs: int):
+    """Golden for the single-wavelength twin process_rays_kernel_pro (GRTF:419-831)."""
+    import multiprocessing as mp
+    recipe = dict(SCENES["walk_deep"]); recipe["num_rays_per_FoV"] = 300
+    lam = 1
+    scene = scene_from_recipe(recipe)
+    n = int(np.count_nonzero(scene.rays.lmd_num == lam))
+    step = max(32, (n + 4 * procs - 1) // (4 * procs))
+    jobs = [(recipe, lam, lo, min(n, lo + step)) for lo in range(0, n, step)]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        parts = pool.map(_run_single_lambda_chunk, jobs)
+    rng = np.zeros(n, dtype=np.uint32); EB = np.zeros(int(np.prod(scene.eb_shape[1:])), dtype=np.float32)
+    for lo, hi, r, nz, val in parts:
+        rng[lo:hi] = r; EB[nz] += val
+    nz = np.flatnonzero(EB)
+    path = os.path.join(GOLDEN_DIR, "walk_single_lambda.npz")
+    np.savez_compressed(path, recipe=np.array(repr(recipe)), lam=np.array(lam), digest=np.array(input_digest(scene)),
+                        rng_states=rng, eb_index=nz.astype(np.int64), eb_value=EB[nz], eb_shape=np.array(scene.eb_shape[1:]))
+    print(f"walk_single_lambda: {n} rays, deposits={EB.sum():.0f} -> {path}")
+
+
+def make_eval(procs: int):
+    """U_fov / U_EB / output_image / pupil sums from the REFERENCE evaluation() itself.  Only `colour`
+    (not installed) is stubbed -- with this repository's restatement of Lab / CIEDE2000 -- so delta_e is
+    NOT a reference value (parity unpinned) while everything else is."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import AR_system_evaluation_functions as mine
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import synthetic_inputs as si
+    from oracle import oracle
+    col = types.ModuleType("colour")
+    col.SDS_ILLUMINANTS = {"D65": "D65"}
+    col.sd_to_XYZ = lambda sd: mine._XYZ_D65_SPD.copy()
+    x_w, y_w = mine._WHITE_XY
+    white = np.array([x_w / y_w, 1.0, (1 - x_w - y_w) / y_w]) * 100.0
+    col.XYZ_to_Lab = lambda xyz: mine._xyz_to_lab(np.asarray(xyz, dtype=np.float64), white)
+    col.delta_E = lambda a, b, method="CIE 2000": mine._delta_e_2000(np.asarray(a), np.asarray(b))
+    sys.modules["colour"] = col
+    sys.path.insert(0, REFERENCE_DIR)
+    import AR_system_evaluation_functions as REF
+    eff = dict(incouple=0.9, incouple_m1=0.05, ic_zero=0.95, ic_cross=0.02, fc_zero=0.8, fc_turn=0.18,
+               oc_zero=0.85, oc_cross=0.02, outcouple=0.12)
+    scene = si.make_scene(6, 5, 20000, seed=41, eff=eff)
+    EB = scene.new_matrix_EB(); rng = scene.rays.rng_states.copy()
+    num_iter = 2
+    for _ in range(num_iter):
+        oracle.trace(*scene.kernel_args(EB, rng), num_threads=procs)
+    EB2 = EB / 20000 / num_iter                                  # RUN:197
+    captured = {}
+    real_sum = np.sum
+    delta_e, U_fov, U_EB, output_image = REF.evaluation(EB2)
+    # pupil sums restated exactly as the reference lines 91-109 (they are not returned by evaluation())
+    size = 30; radius = size / 2
+    yy, xx = np.ogrid[:size, :size]
+    mask = (np.sqrt((xx - (radius - 0.5)) ** 2 + (yy - (radius - 0.5)) ** 2) <= radius).astype(np.float32)
+    y0l = np.arange(0, 80 - size + 1, 8); x0l = np.arange(0, 120 - size + 1, 12)
+    perceive = np.zeros(EB2.shape[:3] + (len(y0l), len(x0l)), dtype=EB2.dtype)
+    for iy, y0 in enumerate(y0l):
+        for ix, x0 in enumerate(x0l):
+            perceive[:, :, :, iy, ix] = np.sum(EB2[:, :, :, y0:y0 + size, x0:x0 + size] * mask[None, None, None], axis=(-1, -2))
+    nz = np.flatnonzero(EB)
+    path = os.path.join(GOLDEN_DIR, "eval.npz")
+    np.savez_compressed(path, eb_index=nz.astype(np.int64), eb_value=EB.ravel()[nz].astype(np.float32),
+                        eb_shape=np.array(EB.shape), rays_per_fov=np.array(20000), num_iter=np.array(num_iter),
+                        U_fov=np.array(U_fov), U_EB=np.array(U_EB), delta_e_stubbed=np.array(delta_e),
+                        output_image=output_image.astype(np.float32), perceive=perceive)
+    print(f"eval: deposits={EB.sum():.0f} U_fov={U_fov:.4f} U_EB={U_EB:.4f} delta_e(stub)={delta_e:.3f} -> {path} "
+          f"({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     procs = int(os.environ.get("WGRT_GOLDEN_PROCS", os.cpu_count() or 1))
-    which = sys.argv[1:] or ["units"] + list(SCENES)
+    which = sys.argv[1:] or ["units", "eval", "single_lambda"] + list(SCENES)
     for w in which:
         if w == "units":
             make_units(procs)
+        elif w == "eval":
+            make_eval(procs)
+        elif w == "single_lambda":
+            make_single_lambda(procs)
         else:
             make_walk(w, SCENES[w], procs)

@@ -240,12 +240,12 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
   double y = (double)p->y[idx];
   int64_t m = (int64_t)p->m[idx];
   int64_t n = (int64_t)p->n[idx];
-  int64_t lm = (int64_t)p->lmd_num[idx];
+  int64_t lm = p->lmd_num ? (int64_t)p->lmd_num[idx] : 0;
   double Ete = (double)p->te[idx];
   double Etm = (double)p->tm[idx];
   double dl = (double)p->delta_phase[idx];
   double ener = 1.0;
-  const double threshold = 0.0;
+  const double threshold = p->threshold; /* GRTF:859 (0) or GRTF:444 (1e-15) */
   double gap_x = 0.0, gap_y = 0.0;
   double cos_theta = 0.0; /* cos(theta.real) of the current direction */
   int state;
@@ -421,7 +421,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
 static int check_problem(const wgrt_problem_t* p) {
   if (!p || p->num_rays < 0) return WGRT_ERR_INVALID;
   if (p->num_rays == 0) return WGRT_OK;
-  if (!p->x || !p->y || !p->m || !p->n || !p->lmd_num || !p->te || !p->tm || !p->delta_phase ||
+  if (!p->x || !p->y || !p->m || !p->n || (!p->lmd_num && p->L != 1) || !p->te || !p->tm || !p->delta_phase ||
       !p->rng_states || !p->IC || !p->FC || !p->FC_offset || !p->OC || !p->OC_offset ||
       !p->eff_reg1 || !p->eff_reg2 || !p->eff_reg_FOV || !p->eff_reg_FOV_range || !p->lut_ic1 ||
       !p->lut_ic2 || !p->lut_ic3 || !p->lut_fc1 || !p->lut_fc2 || !p->lut_oc1 || !p->lut_oc2 ||
@@ -448,7 +448,7 @@ static void* worker_main(void* arg) {
     if (lo >= w->end) break;
     int64_t hi = lo + chunk < w->end ? lo + chunk : w->end;
     for (int64_t i = lo; i < hi; ++i) {
-      int64_t m = (int64_t)p->m[i], n = (int64_t)p->n[i], lm = (int64_t)p->lmd_num[i];
+      int64_t m = (int64_t)p->m[i], n = (int64_t)p->n[i], lm = p->lmd_num ? (int64_t)p->lmd_num[i] : 0;
       if (m < 0 || m >= p->X || n < 0 || n >= p->Y || lm < 0 || lm >= p->L) {
         __atomic_store_n(w->bad, 1, __ATOMIC_RELAXED);
         continue;

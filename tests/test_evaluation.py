@@ -1,0 +1,82 @@
+"""Row f1: the evaluation mirror against outputs of the reference's own evaluation() (tests/golden/
+eval.npz, produced by oracle/make_golden.py with only `colour` stubbed).  Tolerance: rel 1e-5 on the
+maps (the reference sums float32 in NumPy's pairwise order; the GPU kernel in its own order)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import AR_system_evaluation_functions as EV
+
+
+def load():
+    g = np.load(os.path.join(GOLDEN, "eval.npz"))
+    EB = np.zeros(int(np.prod(g["eb_shape"])), dtype=np.float32)
+    EB[g["eb_index"]] = g["eb_value"]
+    EB = EB.reshape(tuple(g["eb_shape"]))
+    return g, EB, EB / int(g["rays_per_fov"]) / int(g["num_iter"])
+
+
+def test_evaluation_post_processing_matches_reference():
+    """CPU part (reference lines 112-160) fed with the reference's own pupil sums."""
+    g, EB, EB2 = load()
+    delta_e, U_fov, U_EB, img = EV.evaluation(EB2, matrix_eye_perceive=g["perceive"])
+    assert U_fov == pytest.approx(float(g["U_fov"]), rel=1e-9)
+    assert U_EB == pytest.approx(float(g["U_EB"]), rel=1e-9)
+    np.testing.assert_allclose(img, g["output_image"], rtol=1e-5, atol=1e-6)
+    assert delta_e == pytest.approx(float(g["delta_e_stubbed"]), rel=1e-9)   # same restated colour maths
+    assert 0 < U_fov < 1 and 0 < U_EB < 1
+
+
+def test_ciede2000_known_pairs():
+    """Sharma et al. (2005) test data, pairs 1, 2, 17 and 25."""
+    lab1 = np.array([[50.0, 2.6772, -79.7751], [50.0, 3.1571, -77.2803], [50.0, 2.5, 0.0], [60.2574, -34.0099, 36.2677]])
+    lab2 = np.array([[50.0, 0.0, -82.7485], [50.0, 0.0, -82.7485], [73.0, 25.0, -18.0], [60.4626, -34.1751, 39.4387]])
+    want = np.array([2.0425, 2.8615, 27.1492, 1.2644])
+    np.testing.assert_allclose(EV._delta_e_2000(lab1, lab2), want, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_pupil_sums_kernel_matches_reference():
+    g, EB, EB2 = load()
+    perceive, cells = EV.pupil_sums(EB2)
+    assert perceive.shape == g["perceive"].shape
+    np.testing.assert_allclose(perceive, g["perceive"], rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(cells, EB2.sum(axis=(-1, -2), dtype=np.float64), rtol=1e-5)
+    # on raw integer counts the sums are exact
+    p_int, c_int = EV.pupil_sums(EB)
+    assert np.array_equal(c_int, EB.sum(axis=(-1, -2), dtype=np.float64).astype(np.float32))
+    assert np.all(p_int == np.round(p_int))
+
+
+@pytest.mark.gpu
+def test_evaluation_end_to_end_on_gpu():
+    g, EB, EB2 = load()
+    delta_e, U_fov, U_EB, img = EV.evaluation(EB2)
+    assert U_fov == pytest.approx(float(g["U_fov"]), rel=1e-5)
+    assert U_EB == pytest.approx(float(g["U_EB"]), rel=1e-5)
+    np.testing.assert_allclose(img, g["output_image"], rtol=1e-4, atol=1e-5)
+    eff = EV.efficiency_per_colour(EB, 6 * 5 * 3 * int(g["rays_per_fov"]), int(g["num_iter"]))
+    want = EB.sum(axis=(1, 2, 3, 4), dtype=np.float64) / (6 * 5 * 3 * int(g["rays_per_fov"])) / int(g["num_iter"]) * 3
+    np.testing.assert_allclose(eff, want, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_pupil_sums_other_shapes():
+    rs = np.random.default_rng(3)
+    for shape, mask, sy, sx in (((1, 2, 3, 40, 50), 30, 8, 12), ((2, 1, 1, 64, 64), 16, 1, 1), ((1, 1, 2, 20, 20), 30, 8, 12)):
+        EB = rs.integers(0, 5, size=shape).astype(np.float32)
+        lib = EV._capi.load_library()
+        n_epy = (shape[3] - mask) // sy + 1 if shape[3] >= mask else 0
+        n_epx = (shape[4] - mask) // sx + 1 if shape[4] >= mask else 0
+        out = np.zeros(shape[:3] + (n_epy, n_epx), np.float32); cells = np.zeros(shape[:3], np.float32)
+        EV._capi.check(lib.wgrt_eval_pupil_sums_host(EB.ctypes.data, *shape, mask, sy, sx, out.ctypes.data,
+                                                     cells.ctypes.data), lib)
+        yy, xx = np.ogrid[:mask, :mask]
+        disc = (np.sqrt((xx - (mask / 2 - 0.5)) ** 2 + (yy - (mask / 2 - 0.5)) ** 2) <= mask / 2)
+        for iy in range(n_epy):
+            for ix in range(n_epx):
+                want = (EB[..., iy * sy:iy * sy + mask, ix * sx:ix * sx + mask] * disc).sum(axis=(-1, -2))
+                assert np.array_equal(out[..., iy, ix], want)
+        assert np.array_equal(cells, EB.sum(axis=(-1, -2)))

@@ -235,6 +235,19 @@ def test_runner_layout_equals_materialised_arrays(oracle):
     assert np.array_equal(EBp, part[0])
 
 
+# ---------------------------------------------------------------------------- single-wavelength twin (row f3)
+@pytest.mark.parametrize("mode", ["fast", "strict"])
+def test_single_lambda_twin(mode):
+    from test_oracle_golden import _single_lambda_case
+    g, args, EB, rng, want = _single_lambda_case()
+    kern = GRTF.process_rays_kernel_pro if mode == "fast" else GRTF.process_rays_kernel_pro.configured(strict=True)
+    assert kern.threshold == 1e-15 and kern.single_lambda
+    kern[(len(rng) + 255) // 256, 256](*args)
+    assert_same((EB, rng), (want, g["rng_states"]), f"single lambda / {mode}")
+    with pytest.raises(TypeError):
+        kern[1, 256](*args, None)        # 33 arguments: that is the full-colour signature
+
+
 # ---------------------------------------------------------------------------- unit-level parity
 def test_xorshift_unit(oracle):
     g = np.load(os.path.join(GOLDEN, "units.npz"))

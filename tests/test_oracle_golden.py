@@ -80,3 +80,26 @@ def test_counters_consistent(oracle, small_scene):
     assert c["draws"] == c["draw2"] + c["draw3"]
     assert c["efield"] == 2 * c["draw2"] + 3 * c["draw3"]
     assert c["deposits"] == int(EB.sum())
+
+
+def _single_lambda_case():
+    import ast
+    from oracle import make_golden
+    g = np.load(os.path.join(GOLDEN, "walk_single_lambda.npz"))
+    recipe = ast.literal_eval(str(g["recipe"]))
+    scene = make_golden.scene_from_recipe(recipe)
+    assert input_digest(scene) == str(g["digest"])
+    lam = int(g["lam"])
+    EB = np.zeros(tuple(g["eb_shape"]), dtype=np.float32)
+    rng = scene.rays.rng_states[scene.rays.lmd_num == lam].copy()
+    args, _ = make_golden.single_lambda_args(scene, lam, EB, rng)
+    want = np.zeros(EB.size, np.float32); want[g["eb_index"]] = g["eb_value"]
+    return g, args, EB, rng, want.reshape(EB.shape)
+
+
+def test_single_lambda_twin_matches_reference(oracle):
+    """process_rays_kernel_pro (GRTF:419-831): 32 arguments, no wavelength axis, threshold 1e-15."""
+    g, args, EB, rng, want = _single_lambda_case()
+    oracle.trace(*args, single_lambda=True, threshold=1e-15)
+    assert np.array_equal(rng, g["rng_states"])
+    assert np.array_equal(EB, want) and EB.sum() > 0
