@@ -63,6 +63,7 @@ def parse_args():
                     choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded baseline sample")
     return ap.parse_args()
 
@@ -273,6 +274,7 @@ def main():
             dist.all_reduce(eb_t)
         ev[args.steps + 1].record(stream)
         barrier()
+    rng_final = rng_t.clone()
     total_ms = ev[0].elapsed_time(ev[args.steps + 1])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -348,6 +350,12 @@ def main():
                                 "frac": gbs / peaks["hbm_gbs"], "peak_source": src,
                                 "algorithmic_bytes_per_launch": alg_bytes}
         rng_t.copy_(rng_saved)
+
+    # ---- the reference's own Numba-CUDA kernel on this GPU (rank 0, N = 1 only) -----------------
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        line["reference_numba_cuda"] = reference_gpu_leg(args, dev_args, host_args, rng_saved, rng_final, eb_t,
+                                                         N, stream, value, bounces_all)
+    del rng_final
 
     # ---- end to end through the C ABI with pinned host buffers -----------------------------------
     if not args.no_e2e:
@@ -499,6 +507,53 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_gpu_leg(args, dev_args, host_args, rng_saved, rng_final, eb_engine, N, stream, value, bounces_all):
+    """BASELINE.json's second baseline: the reference's own kernel (GPU_ray_tracing_functions.py:833-1246,
+    compiled by Numba to PTX in the build container, oracle/build_ref_ptx.py; JITed here by the driver as
+    at a Numba launch) on the SAME device-resident inputs and RNG states as the timed launches, with the
+    runner's launch shape (256 threads, RUN:160-177).  Also the full-size parity check: its bins and final
+    RNG states must be bit-equal to the engine's."""
+    import torch
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
+    from oracle import ref_numba_cuda as ref
+    if not ref.available():
+        return {"unavailable": "oracle/_ref PTX not built (needs /root/reference at build time)"}
+    name = "process_rays_kernel_pro_fullColor"
+    dead = torch.zeros(N, dtype=torch.float32, device="cuda")       # gap_x, gap_y, pol, azi: overwritten before use
+    r_rng = rng_saved.clone()
+    r_eb = torch.zeros_like(eb_engine)
+    r_args = list(dev_args)
+    for i in (2, 3, 4, 5):
+        r_args[i] = GRTF._TorchAlias(dead, (N,), np.float32)
+    r_args[12] = GRTF._TorchAlias(r_rng, (N,), np.uint32)
+    r_args[32] = GRTF._TorchAlias(r_eb, host_args[32].shape, np.float32)
+    t0 = time.perf_counter()
+    attrs = ref.function_attributes(name)                           # module load = driver JIT of the PTX
+    jit_s = time.perf_counter() - t0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        ref.launch(name, r_args, stream=stream.cuda_stream)
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_s = ev[0].elapsed_time(ev[args.steps]) * 1e-3
+    ref_value = bounces_all / total_s
+    out = {"kernel": "GPU_ray_tracing_functions.process_rays_kernel_pro_fullColor (Numba 0.65 -> PTX sm_90, driver JIT)",
+           "launch_shape": [(N + 255) // 256, 256], "ms_per_launch": ms, "value": ref_value, "unit": UNIT,
+           "rays_per_s": N * args.steps / total_s, "driver_jit_s": jit_s, "registers": attrs["registers"],
+           "local_bytes": attrs["local_bytes"],
+           "bins_bit_equal_to_engine": bool(torch.equal(r_eb, eb_engine)),
+           "rng_states_bit_equal_to_engine": bool(torch.equal(r_rng, rng_final)),
+           "engine_over_reference_device_resident": value / ref_value,
+           "note": "same inputs, same RNG states, same number of launches as the timed engine launches; warm "
+                   "(the reference as shipped also pays Numba's Python->PTX compile, ~10 s, in its first launch)"}
+    del dead, r_rng, r_eb
+    torch.cuda.empty_cache()
+    return out
 
 
 def load_traffic():
