@@ -423,8 +423,9 @@ def main():
             "value": all_sum(c1["bounces"]) * args.steps / wall_r, "unit": UNIT,
             "h2d_bytes_per_step": int(h2d_r), "d2h_bytes_per_step": int(d2h_r),
             "ms_per_step": wall_r / max(args.steps, 1) * 1e3,
-            "breakdown_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
-                                            "d2h": parts[2] / args.steps},
+            "stream_spans_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
+                                               "d2h": parts[2] / args.steps,
+                                               "note": "the three streams run as a pipeline over FoV-x column chunks: spans overlap"},
             "api": "runner.trace_full_color -> wgrt_trace_fullcolor_host, runner layout (start points instead of "
                    "the 12 materialised ray arrays), one launch per call, pinned host buffers",
             "bins_bit_equal_to_device_launch": same1}
@@ -448,7 +449,7 @@ def main():
             "value": all_sum(cj["bounces"]) / wall_j, "unit": UNIT, "ms_per_step": wall_j / max(args.steps, 1) * 1e3,
             "launches_per_call": args.steps, "h2d_bytes_per_call": int(h2d_r + seeds.nbytes),
             "d2h_bytes_per_call": int(d2h_r + seeds.nbytes),
-            "breakdown_ms_per_call_rank0": {"h2d": tms_j[0], "trace": tms_j[1], "d2h": tms_j[2]},
+            "stream_spans_ms_per_call_rank0": {"h2d": tms_j[0], "trace": tms_j[1], "d2h": tms_j[2]},
             "bins_and_rng_bit_equal_to_device_launches": samej}
         del d_geom, d_luts, d_rng, d_eb, rargs, pin_keep, geom_p, luts_p, eb_view, seeds
         torch.cuda.empty_cache()
@@ -484,8 +485,8 @@ def main():
         # same RNG streams as the timed device-resident launches -> same bounce count
         line["e2e_dropin"] = {"value": bounces_all / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                               "d2h_bytes_per_step": int(d2h), "ms_per_step": wall / max(args.steps, 1) * 1e3,
-                              "breakdown_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
-                                                              "d2h": parts[2] / args.steps},
+                              "stream_spans_ms_per_step_rank0": {"h2d": parts[0] / args.steps, "trace": parts[1] / args.steps,
+                                                                 "d2h": parts[2] / args.steps},
                               "api": "wgrt_trace_fullcolor_host on the 12 materialised ray arrays (pinned), 1 launch per call"}
         e2e_deposits = float(e2e_args[32].sum(dtype=np.float64))
         line["e2e_dropin"]["deposits_match_device_run"] = bool(world > 1 or e2e_deposits == deposits_total)

@@ -1,4 +1,5 @@
 // wgrt_api.cu -- the C ABI of include/wgrt.h: validation, per-device workspace, launches.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -61,8 +62,12 @@ struct Workspace {
   DeviceBuf small;   // RegionDyn[NUM_REGIONS] | work counter + tile size | hash state | counters
   bool index_stale = true;  // the index buffers were (re)allocated or used by a debug call
   DeviceBuf arena;   // staging for the host entry points
+  bool pipe_ready = false;                         // streams of the host entry's H2D / walk / D2H pipeline
+  cudaStream_t s_in = nullptr, s_run[2] = {nullptr, nullptr}, s_out = nullptr;
   RegionDyn* dyn() { return static_cast<RegionDyn*>(small.ptr); }
-  int* work() { return reinterpret_cast<int*>(static_cast<char*>(small.ptr) + 512); }
+  // {tile counter, tile size} pairs, one per concurrent launch slot: slot 0 = wgrt_trace_fullcolor,
+  // slots 1 and 2 = the two walk streams of the host entry's pipeline
+  int* work(int slot) { return reinterpret_cast<int*>(static_cast<char*>(small.ptr) + 512 + 16 * slot); }
   unsigned long long* hash_state() {
     return reinterpret_cast<unsigned long long*>(static_cast<char*>(small.ptr) + 768);
   }
@@ -75,6 +80,10 @@ struct Workspace {
     }
     small.release();
     arena.release();
+    if (pipe_ready) {
+      cudaStreamDestroy(s_in); cudaStreamDestroy(s_run[0]); cudaStreamDestroy(s_run[1]); cudaStreamDestroy(s_out);
+      pipe_ready = false;
+    }
   }
 };
 
@@ -187,7 +196,27 @@ int validate(const wgrt_problem_t* p) {
   return WGRT_OK;
 }
 
-int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
+int region_set_of(Workspace& w, const wgrt_problem_t& p, RegionSet& rs) {
+  const double* verts[NUM_REGIONS] = {p.IC, p.eff_reg1, p.eff_reg2, p.FC, p.OC};
+  const int64_t* offs[NUM_REGIONS] = {nullptr, nullptr, nullptr, p.FC_offset, p.OC_offset};
+  const int64_t nv[NUM_REGIONS] = {p.IC_n, p.eff_reg1_n, p.eff_reg2_n, p.FC_n, p.OC_n};
+  const int64_t np[NUM_REGIONS] = {1, 1, 1, p.n_FC, p.n_OC};
+  return setup_regions(w, rs, verts, offs, nv, np);
+}
+
+// (Re)build the region index for p's polygons on `stream` if their content changed.
+int build_region_index(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
+  RegionSet rs;
+  int rc = region_set_of(w, p, rs);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
+  w.index_stale = false;
+  return WGRT_OK;
+}
+
+// One launch of the walk.  `slot` selects the tile-counter pair (launches that may run concurrently
+// need different slots); `build_index = false` when the caller built the region index already.
+int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream, int slot = 0, bool build_index = true) {
   if (p.num_rays == 0) return WGRT_OK;
   if (!p.rng_states) return fail(WGRT_ERR_INVALID, "null pointer: rng_states");
   if (p.flags & WGRT_FLAG_STRICT) {
@@ -195,15 +224,13 @@ int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
     return WGRT_OK;
   }
   RegionSet rs;
-  const double* verts[NUM_REGIONS] = {p.IC, p.eff_reg1, p.eff_reg2, p.FC, p.OC};
-  const int64_t* offs[NUM_REGIONS] = {nullptr, nullptr, nullptr, p.FC_offset, p.OC_offset};
-  const int64_t nv[NUM_REGIONS] = {p.IC_n, p.eff_reg1_n, p.eff_reg2_n, p.FC_n, p.OC_n};
-  const int64_t np[NUM_REGIONS] = {1, 1, 1, p.n_FC, p.n_OC};
-  int rc = setup_regions(w, rs, verts, offs, nv, np);
+  int rc = region_set_of(w, p, rs);
   if (rc != WGRT_OK) return rc;
-  CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
-  w.index_stale = false;
-  CUDA_TRY(launch_walk_fast(p, rs, w.work(), w.counters(), w.num_sms, stream));
+  if (build_index) {
+    CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
+    w.index_stale = false;
+  }
+  CUDA_TRY(launch_walk_fast(p, rs, w.work(slot), w.counters(), w.num_sms, stream));
   return WGRT_OK;
 }
 
@@ -259,7 +286,53 @@ int wgrt_trace_fullcolor(const wgrt_problem_t* p, void* stream) {
   return trace_device(*w, *p, static_cast<cudaStream_t>(stream));
 }
 
-int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* timings_ms) {
+}  // extern "C" (the host entry below needs helpers from an unnamed namespace)
+
+// The host entry is a three-stage pipeline over CHUNKS of the job (H2D stream -> walk stream -> D2H
+// stream, chained by events), so that the PCIe transfers of one chunk run under the walk of its
+// neighbours.  Rays are independent and carry their own RNG stream (GRTF:25-34, RUN:158), so walking
+// the job chunk by chunk -- and a chunk num_iter times before the next one starts -- is bit-identical
+// to num_iter launches over the whole ray set.
+//   runner layout : a chunk is a range of FoV-x columns (the runner's outermost loop, RUN:82-84).  The
+//                   LUT / TIR / gap / eyebox tables of those columns go up as strided 2-D copies into
+//                   the full-shape device arrays, the chunk's rays are walked, and the columns' slice
+//                   matrix_EB[:, :, m0:m1] comes down while the next chunk is walked.
+//   ray arrays    : a chunk is a range of rays; the shared tables go up first, the bins come down last.
+namespace {
+
+struct Copy2D {
+  void* dst; const void* src; size_t dpitch, spitch, width, height;
+};
+
+cudaError_t copy2d(const Copy2D& c, cudaMemcpyKind kind, cudaStream_t st) {
+  if (!c.width || !c.height) return cudaSuccess;
+  if (c.height == 1 || (c.width == c.dpitch && c.width == c.spitch))
+    return cudaMemcpyAsync(c.dst, c.src, c.width * c.height, kind, st);
+  return cudaMemcpy2DAsync(c.dst, c.dpitch, c.src, c.spitch, c.width, c.height, kind, st);
+}
+
+int host_chunk_target(int64_t num_rays, int num_iter) {
+  const char* e = getenv("WGRT_HOST_CHUNKS");   // read at every call: tests force odd chunkings
+  const int forced = e ? atoi(e) : 0;
+  if (forced > 0) return forced;
+  // enough chunks to hide the transfers of the first and last one, few enough that a chunk is
+  // still several waves of tiles (about 4 M rays per wave of resident CTAs at runner-sized cells);
+  // measured on C2 (B200): 1 chunk 33.5 ms, 4: 20.8, 8: 19.4, 16: 18.6, 25: 18.4 (num_iter = 1)
+  (void)num_iter;
+  const int64_t by_size = num_rays / 7000000;
+  return static_cast<int>(by_size < 1 ? 1 : (by_size > 16 ? 16 : by_size));
+}
+
+struct HostChunk {
+  int64_t ray0 = 0, rays = 0;        // launch-relative ray range walked by this chunk
+  int64_t cell0 = 0;                 // runner layout: first cell of the chunk (global cell index)
+  int64_t in_m0 = 0, in_m1 = 0;      // runner layout: FoV-x columns whose tables this chunk uploads
+  int64_t out_m0 = 0, out_m1 = 0;    // runner layout: FoV-x columns of matrix_EB this chunk moves
+};
+
+}  // namespace
+
+extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* timings_ms) {
   std::lock_guard<std::mutex> lk(g_mu);
   int rc = validate(hp);
   if (rc != WGRT_OK) return rc;
@@ -276,77 +349,236 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* tim
   if (rc != WGRT_OK) return rc;
 
   const size_t N = static_cast<size_t>(hp->num_rays);
-  const size_t cells = static_cast<size_t>(hp->L * hp->X * hp->Y), fov = static_cast<size_t>(hp->X * hp->Y);
-  const size_t eb_elems = cells * static_cast<size_t>(hp->EBy * hp->EBx);
+  const size_t L = hp->L, X = hp->X, Y = hp->Y;
+  const size_t cells = L * X * Y, fov = X * Y;
+  const size_t tile_b = static_cast<size_t>(hp->EBy * hp->EBx) * 4;   // one FoV cell's bins
+  const size_t eb_b = cells * tile_b;
   const bool runner = hp->runner_points > 0;
   const bool seed_rng = runner && hp->rng_states == nullptr;
   const bool zero_bins = (hp->flags & WGRT_FLAG_BINS_ZERO) != 0;
   if (!runner && N && !hp->rng_states) return fail(WGRT_ERR_INVALID, "null pointer: rng_states");
-  struct Item { const void* src; void** dst; size_t bytes; };
+
+  // ---- device staging: full-shape copies of every array (arena, grow-only) --------------------
+  struct Item { const void* src; void** dst; size_t bytes; bool upfront; };
   wgrt_problem_t dp = *hp;
   dp.gap_x = dp.gap_y = dp.pol = dp.azi = nullptr;  // never read by the walk
   dp.flags &= ~WGRT_FLAG_BINS_ZERO;
   const size_t ray_b = N * 4, pts_b = static_cast<size_t>(hp->runner_points) * 4;
-  std::vector<Item> in;
+  const size_t ic_b = fov * hp->C_ic * 16, fc_b = fov * hp->C_fc * 16, oc_b = fov * hp->C_oc * 16;  // per wavelength (and slice)
+  std::vector<Item> items;
   if (runner) {
     dp.m = dp.n = dp.lmd_num = dp.te = dp.tm = dp.delta_phase = nullptr;
-    in = {{hp->x, (void**)&dp.x, pts_b}, {hp->y, (void**)&dp.y, pts_b}};
+    items = {{hp->x, (void**)&dp.x, pts_b, true}, {hp->y, (void**)&dp.y, pts_b, true}};
   } else {
-    in = {{hp->x, (void**)&dp.x, ray_b}, {hp->y, (void**)&dp.y, ray_b}, {hp->m, (void**)&dp.m, ray_b},
-          {hp->n, (void**)&dp.n, ray_b}, {hp->lmd_num, (void**)&dp.lmd_num, hp->lmd_num ? ray_b : 0}, {hp->te, (void**)&dp.te, ray_b},
-          {hp->tm, (void**)&dp.tm, ray_b}, {hp->delta_phase, (void**)&dp.delta_phase, ray_b}};
+    items = {{hp->x, (void**)&dp.x, ray_b, false}, {hp->y, (void**)&dp.y, ray_b, false},
+             {hp->m, (void**)&dp.m, ray_b, false}, {hp->n, (void**)&dp.n, ray_b, false},
+             {hp->lmd_num, (void**)&dp.lmd_num, hp->lmd_num ? ray_b : 0, false},
+             {hp->te, (void**)&dp.te, ray_b, false}, {hp->tm, (void**)&dp.tm, ray_b, false},
+             {hp->delta_phase, (void**)&dp.delta_phase, ray_b, false}};
   }
-  in.push_back({seed_rng ? nullptr : hp->rng_states, (void**)&dp.rng_states, ray_b});
+  const size_t n_ray_items = items.size();
+  items.push_back({nullptr, (void**)&dp.rng_states, ray_b, false});
+  const bool tables_upfront = !runner;   // runner layout: the per-cell tables go up column range by column range
   const std::vector<Item> shared_items = {
-      {hp->IC, (void**)&dp.IC, (size_t)hp->IC_n * 16}, {hp->FC, (void**)&dp.FC, (size_t)hp->FC_n * 16},
-      {hp->FC_offset, (void**)&dp.FC_offset, (size_t)(hp->n_FC + 1) * 8},
-      {hp->OC, (void**)&dp.OC, (size_t)hp->OC_n * 16},
-      {hp->OC_offset, (void**)&dp.OC_offset, (size_t)(hp->n_OC + 1) * 8},
-      {hp->eff_reg1, (void**)&dp.eff_reg1, (size_t)hp->eff_reg1_n * 16},
-      {hp->eff_reg2, (void**)&dp.eff_reg2, (size_t)hp->eff_reg2_n * 16},
-      {hp->eff_reg_FOV, (void**)&dp.eff_reg_FOV, fov * 64},
-      {hp->eff_reg_FOV_range, (void**)&dp.eff_reg_FOV_range, fov * 32},
-      {hp->lut_ic1, (void**)&dp.lut_ic1, cells * hp->C_ic * 16}, {hp->lut_ic2, (void**)&dp.lut_ic2, cells * hp->C_ic * 16},
-      {hp->lut_ic3, (void**)&dp.lut_ic3, cells * hp->C_ic * 16},
-      {hp->lut_fc1, (void**)&dp.lut_fc1, cells * hp->n_FC * hp->C_fc * 16},
-      {hp->lut_fc2, (void**)&dp.lut_fc2, cells * hp->n_FC * hp->C_fc * 16},
-      {hp->lut_oc1, (void**)&dp.lut_oc1, cells * hp->n_OC * hp->C_oc * 16},
-      {hp->lut_oc2, (void**)&dp.lut_oc2, cells * hp->n_OC * hp->C_oc * 16},
-      {hp->lut_TIR, (void**)&dp.lut_TIR, cells * 32}, {hp->lut_gap, (void**)&dp.lut_gap, cells * 64},
-      {zero_bins ? nullptr : hp->matrix_EB, (void**)&dp.matrix_EB, eb_elems * 4},
+      {hp->IC, (void**)&dp.IC, (size_t)hp->IC_n * 16, true}, {hp->FC, (void**)&dp.FC, (size_t)hp->FC_n * 16, true},
+      {hp->FC_offset, (void**)&dp.FC_offset, (size_t)(hp->n_FC + 1) * 8, true},
+      {hp->OC, (void**)&dp.OC, (size_t)hp->OC_n * 16, true},
+      {hp->OC_offset, (void**)&dp.OC_offset, (size_t)(hp->n_OC + 1) * 8, true},
+      {hp->eff_reg1, (void**)&dp.eff_reg1, (size_t)hp->eff_reg1_n * 16, true},
+      {hp->eff_reg2, (void**)&dp.eff_reg2, (size_t)hp->eff_reg2_n * 16, true},
+      {hp->eff_reg_FOV, (void**)&dp.eff_reg_FOV, fov * 64, tables_upfront},
+      {hp->eff_reg_FOV_range, (void**)&dp.eff_reg_FOV_range, fov * 32, tables_upfront},
+      {hp->lut_ic1, (void**)&dp.lut_ic1, L * ic_b, tables_upfront}, {hp->lut_ic2, (void**)&dp.lut_ic2, L * ic_b, tables_upfront},
+      {hp->lut_ic3, (void**)&dp.lut_ic3, L * ic_b, tables_upfront},
+      {hp->lut_fc1, (void**)&dp.lut_fc1, L * hp->n_FC * fc_b, tables_upfront},
+      {hp->lut_fc2, (void**)&dp.lut_fc2, L * hp->n_FC * fc_b, tables_upfront},
+      {hp->lut_oc1, (void**)&dp.lut_oc1, L * hp->n_OC * oc_b, tables_upfront},
+      {hp->lut_oc2, (void**)&dp.lut_oc2, L * hp->n_OC * oc_b, tables_upfront},
+      {hp->lut_TIR, (void**)&dp.lut_TIR, cells * 32, tables_upfront}, {hp->lut_gap, (void**)&dp.lut_gap, cells * 64, tables_upfront},
+      {hp->matrix_EB, (void**)&dp.matrix_EB, eb_b, !zero_bins && !runner},
   };
-  in.insert(in.end(), shared_items.begin(), shared_items.end());
+  items.insert(items.end(), shared_items.begin(), shared_items.end());
   size_t total = 0;
-  for (auto& it : in) total += padded(it.bytes);
+  for (auto& it : items) total += padded(it.bytes);
   CUDA_TRY(w->arena.reserve(total));
   Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
-  cudaStream_t st = nullptr;
-  cudaEvent_t ev[4];
-  for (auto& e : ev) CUDA_TRY(cudaEventCreate(&e));
-  CUDA_TRY(cudaEventRecord(ev[0], st));
-  for (auto& it : in) {
+  for (auto& it : items) {
     *it.dst = (it.bytes || it.src) ? ar.take(it.bytes) : nullptr;
     if (!*it.dst && (it.bytes || it.src)) return fail(WGRT_ERR_CUDA, "arena overflow");
-    if (it.bytes && it.src) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, cudaMemcpyHostToDevice, st));
   }
-  if (zero_bins) CUDA_TRY(cudaMemsetAsync(dp.matrix_EB, 0, eb_elems * 4, st));
-  if (seed_rng)
-    CUDA_TRY(launch_seed_rng(dp.rng_states, hp->num_rays, hp->runner_first_cell * 2 * hp->runner_points, st));
-  CUDA_TRY(cudaEventRecord(ev[1], st));
-  for (int k = 0; k < num_iter; ++k) {
-    rc = trace_device(*w, dp, st);
+
+  // ---- chunk plan ------------------------------------------------------------------------------
+  std::vector<HostChunk> chunks;
+  const int want = host_chunk_target(hp->num_rays, num_iter);
+  if (runner) {
+    const int64_t rpc = 2 * hp->runner_points, cpc = static_cast<int64_t>(Y * L);   // cells per FoV-x column
+    const int64_t c0 = hp->runner_first_cell, c1 = c0 + hp->num_rays / rpc;
+    const int64_t m_lo = N ? c0 / cpc : 0, m_hi = N ? (c1 - 1) / cpc + 1 : 0;
+    const int64_t K = N ? std::max<int64_t>(1, std::min<int64_t>(want, m_hi - m_lo)) : 1;
+    for (int64_t k = 0; k < K; ++k) {
+      HostChunk c;
+      c.in_m0 = m_lo + (m_hi - m_lo) * k / K;
+      c.in_m1 = m_lo + (m_hi - m_lo) * (k + 1) / K;
+      const int64_t a = std::max(c0, c.in_m0 * cpc), b = std::min(c1, c.in_m1 * cpc);
+      c.cell0 = a;
+      c.ray0 = (a - c0) * rpc;
+      c.rays = b > a ? (b - a) * rpc : 0;
+      // matrix_EB columns outside the cell range travel with the first / last chunk: the whole
+      // tensor is uploaded (unless declared zero) and downloaded, as by a single full copy
+      c.out_m0 = k == 0 ? 0 : c.in_m0;
+      c.out_m1 = k == K - 1 ? static_cast<int64_t>(X) : c.in_m1;
+      chunks.push_back(c);
+    }
+  } else {
+    const char* forced = getenv("WGRT_HOST_CHUNKS");
+    const int64_t grain = (forced && atoi(forced) > 0) ? 64 : 1048576;   // rays per chunk, at least
+    const int64_t K = std::max<int64_t>(1, std::min<int64_t>(want, (hp->num_rays + grain - 1) / grain));
+    for (int64_t k = 0; k < K; ++k) {
+      HostChunk c;
+      c.ray0 = hp->num_rays * k / K;
+      c.rays = hp->num_rays * (k + 1) / K - c.ray0;
+      chunks.push_back(c);
+    }
+  }
+  const size_t K = chunks.size();
+
+  // ---- streams and events ----------------------------------------------------------------------
+  if (!w->pipe_ready) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&w->s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&w->s_run[0], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&w->s_run[1], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&w->s_out, cudaStreamNonBlocking));
+    w->pipe_ready = true;
+  }
+  // two walk streams, chunks alternate: the next chunk's CTAs fill the SMs the previous chunk's
+  // persistent CTAs leave as they run out of tiles (no idle tail at chunk boundaries)
+  cudaStream_t s_in = w->s_in, s_run2[2] = {w->s_run[0], w->s_run[1]}, s_out = w->s_out;
+  std::vector<cudaEvent_t> ev_in(K), ev_run(K);
+  cudaEvent_t span[8];   // begin / end of the work on each of the three stages; [6], [7]: shared tables up, index built
+  struct EventGuard {
+    std::vector<cudaEvent_t>*a, *b; cudaEvent_t* c;
+    ~EventGuard() {
+      for (auto e : *a) if (e) cudaEventDestroy(e);
+      for (auto e : *b) if (e) cudaEventDestroy(e);
+      for (int i = 0; i < 8; ++i) if (c[i]) cudaEventDestroy(c[i]);
+    }
+  } guard{&ev_in, &ev_run, span};
+  for (auto& e : span) e = nullptr;
+  for (auto& e : ev_in) e = nullptr;
+  for (auto& e : ev_run) e = nullptr;
+  for (auto& e : span) CUDA_TRY(cudaEventCreate(&e));
+  for (auto& e : ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : ev_run) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  // a failure below must not leave copies running into buffers the caller is about to free
+  struct SyncGuard {
+    cudaStream_t a, b, c, d;
+    ~SyncGuard() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); cudaStreamSynchronize(c); cudaStreamSynchronize(d); }
+  } sync_guard{s_in, s_run2[0], s_run2[1], s_out};
+
+  const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  CUDA_TRY(cudaEventRecord(span[0], s_in));
+  for (auto& it : items)
+    if (it.upfront && it.bytes && it.src) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, H2D, s_in));
+  if (zero_bins) CUDA_TRY(cudaMemsetAsync(dp.matrix_EB, 0, eb_b, s_in));
+  // the region index is built once, on walk stream 0, as soon as the polygons are up
+  CUDA_TRY(cudaEventRecord(span[6], s_in));
+  CUDA_TRY(cudaStreamWaitEvent(s_run2[0], span[6], 0));
+  CUDA_TRY(cudaEventRecord(span[2], s_run2[0]));
+  if (N && !(dp.flags & WGRT_FLAG_STRICT)) {
+    rc = build_region_index(*w, dp, s_run2[0]);
     if (rc != WGRT_OK) return rc;
   }
-  CUDA_TRY(cudaEventRecord(ev[2], st));
-  if (N && hp->rng_states) CUDA_TRY(cudaMemcpyAsync(hp->rng_states, dp.rng_states, N * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(hp->matrix_EB, dp.matrix_EB, eb_elems * 4, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaEventRecord(ev[3], st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaEventRecord(span[7], s_run2[0]));
+  CUDA_TRY(cudaStreamWaitEvent(s_run2[1], span[7], 0));
+
+  for (size_t k = 0; k < K; ++k) {
+    const HostChunk& c = chunks[k];
+    cudaStream_t s_run = s_run2[k & 1];
+    // ---- stage 1: this chunk's inputs ----------------------------------------------------------
+    if (runner) {
+      const size_t cols = static_cast<size_t>(c.in_m1 - c.in_m0), m0 = static_cast<size_t>(c.in_m0);
+      auto table = [&](const double* dst, const double* src, size_t row_b, size_t planes) {
+        // [planes, X, row] arrays: columns m0 .. m0+cols of every plane
+        return copy2d({(char*)dst + m0 * row_b, (const char*)src + m0 * row_b, X * row_b, X * row_b, cols * row_b, planes},
+                      H2D, s_in);
+      };
+      CUDA_TRY(table(dp.lut_ic1, hp->lut_ic1, Y * hp->C_ic * 16, L));
+      CUDA_TRY(table(dp.lut_ic2, hp->lut_ic2, Y * hp->C_ic * 16, L));
+      CUDA_TRY(table(dp.lut_ic3, hp->lut_ic3, Y * hp->C_ic * 16, L));
+      CUDA_TRY(table(dp.lut_fc1, hp->lut_fc1, Y * hp->C_fc * 16, L * hp->n_FC));
+      CUDA_TRY(table(dp.lut_fc2, hp->lut_fc2, Y * hp->C_fc * 16, L * hp->n_FC));
+      CUDA_TRY(table(dp.lut_oc1, hp->lut_oc1, Y * hp->C_oc * 16, L * hp->n_OC));
+      CUDA_TRY(table(dp.lut_oc2, hp->lut_oc2, Y * hp->C_oc * 16, L * hp->n_OC));
+      CUDA_TRY(table(dp.lut_TIR, hp->lut_TIR, Y * 32, L));
+      CUDA_TRY(table(dp.lut_gap, hp->lut_gap, Y * 64, L));
+      CUDA_TRY(table(dp.eff_reg_FOV, hp->eff_reg_FOV, Y * 64, 1));
+      CUDA_TRY(table(dp.eff_reg_FOV_range, hp->eff_reg_FOV_range, Y * 32, 1));
+      if (!zero_bins) {
+        const size_t o0 = static_cast<size_t>(c.out_m0), ocols = static_cast<size_t>(c.out_m1 - c.out_m0);
+        CUDA_TRY(copy2d({(char*)dp.matrix_EB + o0 * tile_b, (const char*)hp->matrix_EB + o0 * tile_b, X * tile_b,
+                         X * tile_b, ocols * tile_b, L * Y}, H2D, s_in));
+      }
+    } else {
+      for (size_t i = 0; i < n_ray_items; ++i)
+        if (items[i].bytes && items[i].src)
+          CUDA_TRY(cudaMemcpyAsync((char*)*items[i].dst + c.ray0 * 4, (const char*)items[i].src + c.ray0 * 4,
+                                   static_cast<size_t>(c.rays) * 4, H2D, s_in));
+    }
+    if (!seed_rng && c.rays)
+      CUDA_TRY(cudaMemcpyAsync(dp.rng_states + c.ray0, hp->rng_states + c.ray0, static_cast<size_t>(c.rays) * 4, H2D, s_in));
+    if (k == K - 1) CUDA_TRY(cudaEventRecord(span[1], s_in));
+    CUDA_TRY(cudaEventRecord(ev_in[k], s_in));
+
+    // ---- stage 2: walk the chunk num_iter times --------------------------------------------------
+    CUDA_TRY(cudaStreamWaitEvent(s_run, ev_in[k], 0));
+    if (c.rays) {
+      wgrt_problem_t cp = dp;
+      cp.num_rays = c.rays;
+      cp.rng_states = dp.rng_states + c.ray0;
+      if (const char* e = getenv("WGRT_HOST_TILE")) if (!cp.tile_hint && atoi(e) > 0) cp.tile_hint = atoi(e);
+      if (runner) {
+        cp.runner_first_cell = c.cell0;
+      } else {
+        cp.x += c.ray0; cp.y += c.ray0; cp.m += c.ray0; cp.n += c.ray0; cp.te += c.ray0; cp.tm += c.ray0;
+        cp.delta_phase += c.ray0;
+        if (cp.lmd_num) cp.lmd_num += c.ray0;
+      }
+      if (seed_rng) CUDA_TRY(launch_seed_rng(cp.rng_states, c.rays, c.cell0 * 2 * hp->runner_points, s_run));
+      for (int it = 0; it < num_iter; ++it) {
+        rc = trace_device(*w, cp, s_run, 1 + static_cast<int>(k & 1), false);
+        if (rc != WGRT_OK) return rc;
+      }
+    }
+    CUDA_TRY(cudaEventRecord(ev_run[k], s_run));
+
+    // ---- stage 3: results of the chunk -----------------------------------------------------------
+    CUDA_TRY(cudaStreamWaitEvent(s_out, ev_run[k], 0));
+    if (k == 0) CUDA_TRY(cudaEventRecord(span[4], s_out));
+    if (c.rays && hp->rng_states)
+      CUDA_TRY(cudaMemcpyAsync(hp->rng_states + c.ray0, dp.rng_states + c.ray0, static_cast<size_t>(c.rays) * 4, D2H, s_out));
+    if (runner) {
+      const size_t o0 = static_cast<size_t>(c.out_m0), ocols = static_cast<size_t>(c.out_m1 - c.out_m0);
+      CUDA_TRY(copy2d({(char*)hp->matrix_EB + o0 * tile_b, (const char*)dp.matrix_EB + o0 * tile_b, X * tile_b, X * tile_b,
+                       ocols * tile_b, L * Y}, D2H, s_out));
+    } else if (k == K - 1) {
+      CUDA_TRY(cudaMemcpyAsync(hp->matrix_EB, dp.matrix_EB, eb_b, D2H, s_out));
+    }
+  }
+  CUDA_TRY(cudaEventRecord(span[5], s_out));
+  // end of the walk stage: the later of the two walk streams (the D2H stream waited for both)
+  CUDA_TRY(cudaStreamWaitEvent(s_run2[0], ev_run[K - 1], 0));
+  if (K > 1) CUDA_TRY(cudaStreamWaitEvent(s_run2[0], ev_run[K - 2], 0));
+  CUDA_TRY(cudaEventRecord(span[3], s_run2[0]));
+  CUDA_TRY(cudaStreamSynchronize(s_in));
+  CUDA_TRY(cudaStreamSynchronize(s_run2[0]));
+  CUDA_TRY(cudaStreamSynchronize(s_run2[1]));
+  CUDA_TRY(cudaStreamSynchronize(s_out));
   if (timings_ms)
-    for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventElapsedTime(&timings_ms[k], ev[k], ev[k + 1]));
-  for (auto& e : ev) cudaEventDestroy(e);
+    for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventElapsedTime(&timings_ms[k], span[2 * k], span[2 * k + 1]));
   return WGRT_OK;
 }
+
+extern "C" {
 
 int wgrt_counters_read(uint64_t* out, int n) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -175,8 +175,18 @@ int wgrt_trace_fullcolor(const wgrt_problem_t* dev_problem, void* stream);
 /*
  * Replaces the runner's region gpu_ray_tracing_pro_fullColor.py:145-185 for HOST buffers:
  * H2D of rays/geometry/LUTs/bins, `num_iter` launches (RUN:169-177), synchronize, D2H of
- * matrix_EB and rng_states.  Synchronous.  `timings_ms`, if not NULL, receives
- * {h2d, trace, d2h} device-event times in milliseconds.
+ * matrix_EB and rng_states.  Synchronous.
+ *
+ * The three steps run as a pipeline over chunks of the job on three internal streams, so the PCIe
+ * transfers hide under the walk: with the runner layout a chunk is a range of FoV-x columns (their
+ * LUT / table slices go up, their rays are walked num_iter times, their matrix_EB slice comes down
+ * while the next columns are walked); with explicit ray arrays a chunk is a range of rays and the
+ * bins come down after the last one.  Rays are independent and own their RNG stream, so the result
+ * is bit-identical to num_iter launches over the whole ray set.  WGRT_HOST_CHUNKS=<n> in the
+ * environment forces the number of chunks (default: by job size, at most 16).
+ * `timings_ms`, if not NULL, receives the device-event SPANS {first H2D start -> last H2D end,
+ * first launch start -> last launch end, first D2H start -> last D2H end} in milliseconds; the
+ * spans overlap, their sum exceeds the wall time.
  */
 int wgrt_trace_fullcolor_host(const wgrt_problem_t* host_problem, int num_iter, float* timings_ms);
 

@@ -235,6 +235,48 @@ def test_runner_layout_equals_materialised_arrays(oracle):
     assert np.array_equal(EBp, part[0])
 
 
+@pytest.mark.parametrize("chunks", [1, 3, 7, 64])
+def test_host_pipeline_chunking_is_invisible(chunks, oracle, monkeypatch):
+    """The host entry pipelines H2D / walk / D2H over chunks (FoV-x column ranges with the runner
+    layout, ray ranges with explicit arrays): any chunking, bins that do not start at zero, cell
+    sub-ranges that cut through columns, and returned RNG states must all match the plain launches."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
+    monkeypatch.setenv("WGRT_HOST_CHUNKS", str(chunks))
+    rpc = 120
+    scene = si.make_scene(9, 4, rpc, seed=41)
+    pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 41 + 1)
+    scene.rays = si.build_ray_set(pts, 9, 4, 3, rpc)
+    want = run_oracle(oracle, scene, 2)
+    # (a) runner layout, whole job, device-seeded RNG, bins cleared on the device
+    EB = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2)
+    assert np.array_equal(EB, want[0])
+    # (b) runner layout, bins accumulate onto what the caller passes in, RNG states round trip
+    base = np.random.default_rng(5).integers(0, 3, size=scene.eb_shape).astype(np.float32)
+    EB = base.copy(); rng = si.initial_rng_states(scene.rays.num_rays)
+    runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, matrix_EB=EB, rng_states=rng)
+    assert np.array_equal(EB, base + want[0]) and np.array_equal(rng, want[1])
+    # (c) a cell range that starts and ends inside FoV-x columns (multi-GPU shard); the rest of the
+    #     caller's bins must come back untouched
+    c0, c1 = 17, 83
+    full = scene.rays
+    scene.rays = full.take(slice(c0 * rpc, c1 * rpc))
+    part = run_oracle(oracle, scene, 2)
+    scene.rays = full
+    EB = base.copy(); rng = si.initial_rng_states((c1 - c0) * rpc, offset=c0 * rpc)
+    runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, first_cell=c0, num_cells=c1 - c0,
+                            matrix_EB=EB, rng_states=rng)
+    assert np.array_equal(EB, base + part[0]) and np.array_equal(rng, part[1])
+    EB = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, first_cell=c0,
+                                 num_cells=c1 - c0)
+    assert np.array_equal(EB, part[0])
+    # (d) explicit ray arrays through the C ABI host entry
+    EB = base.copy(); rng = scene.rays.rng_states.copy()
+    prob, keep = GRTF.pack_problem(scene.kernel_args(EB, rng), host=True)
+    lib = _capi.load_library()
+    _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 2, None), lib)
+    assert np.array_equal(EB, base + want[0]) and np.array_equal(rng, want[1])
+
+
 # ---------------------------------------------------------------------------- single-wavelength twin (row f3)
 @pytest.mark.parametrize("mode", ["fast", "strict"])
 def test_single_lambda_twin(mode):
