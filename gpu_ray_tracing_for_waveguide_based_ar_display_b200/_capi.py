@@ -46,7 +46,7 @@ class WgrtProblem(C.Structure):
         ("matrix_EB", C.c_void_p), ("EBy", C.c_int64), ("EBx", C.c_int64),
         ("flags", C.c_uint32), ("tile_hint", C.c_uint32),
         ("runner_points", C.c_int64), ("runner_first_cell", C.c_int64),
-        ("threshold", C.c_double),
+        ("threshold", C.c_double), ("ray_index_base", C.c_int64),
     ]
 
 

@@ -20,6 +20,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = {
     "wgrt_strict.cu": ["-fmad=false"],
     "wgrt_fast.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WALK_THREADS", "WGRT_WALK_MIN_BLOCKS") if k in os.environ],
+    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WARP_CTAS_PER_SM",) if k in os.environ],
     "wgrt_api.cu": [],
 }
 HEADERS = ["wgrt_device.cuh", "wgrt_region.cuh", os.path.join("..", "..", "include", "wgrt.h")]

@@ -59,12 +59,15 @@ struct Workspace {
   int device = -1;
   int num_sms = 0;
   DeviceBuf cells[NUM_REGIONS], detail[NUM_REGIONS], rowmask[NUM_REGIONS], coarse[NUM_REGIONS], rowmask_c[NUM_REGIONS];
-  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | work counter + tile size | hash state | counters
+  DeviceBuf atlas;   // uint32 [ATLAS_N * ATLAS_N] level 1, then [ATLAS_N2 * ATLAS_N2] level 2
+  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | AtlasDyn @ 256 | tile counters @ 512 | hash state @ 768 | counters @ 1024
   bool index_stale = true;  // the index buffers were (re)allocated or used by a debug call
+  DeviceBuf jones[3];   // per-warp Jones-matrix scratch of the warp walk, one per launch slot
   DeviceBuf arena;   // staging for the host entry points
   bool pipe_ready = false;                         // streams of the host entry's H2D / walk / D2H pipeline
   cudaStream_t s_in = nullptr, s_run[2] = {nullptr, nullptr}, s_out = nullptr;
   RegionDyn* dyn() { return static_cast<RegionDyn*>(small.ptr); }
+  AtlasDyn* atlas_dyn() { return reinterpret_cast<AtlasDyn*>(static_cast<char*>(small.ptr) + 256); }
   // {tile counter, tile size} pairs, one per concurrent launch slot: slot 0 = wgrt_trace_fullcolor,
   // slots 1 and 2 = the two walk streams of the host entry's pipeline
   int* work(int slot) { return reinterpret_cast<int*>(static_cast<char*>(small.ptr) + 512 + 16 * slot); }
@@ -79,6 +82,8 @@ struct Workspace {
       cells[r].release(); detail[r].release(); rowmask[r].release(); coarse[r].release(); rowmask_c[r].release();
     }
     small.release();
+    atlas.release();
+    for (auto& j : jones) j.release();
     arena.release();
     if (pipe_ready) {
       cudaStreamDestroy(s_in); cudaStreamDestroy(s_run[0]); cudaStreamDestroy(s_run[1]); cudaStreamDestroy(s_out);
@@ -158,6 +163,13 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
     for (int k = 0; k < 5; ++k)
       if (before[k] != after[k]) w.index_stale = true;
   }
+  {
+    const void* before = w.atlas.ptr;
+    CUDA_TRY(w.atlas.reserve(sizeof(uint32_t) * (static_cast<size_t>(ATLAS_N) * ATLAS_N + static_cast<size_t>(ATLAS_N2) * ATLAS_N2)));
+    if (before != w.atlas.ptr) w.index_stale = true;
+  }
+  rs.atlas = static_cast<uint32_t*>(w.atlas.ptr);
+  rs.atlas_dyn = w.atlas_dyn();
   rs.dyn = w.dyn();
   rs.hash_state = w.hash_state();
   rs.dirty = w.hash_state() + 1;
@@ -230,7 +242,19 @@ int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream, int
     CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
     w.index_stale = false;
   }
-  CUDA_TRY(launch_walk_fast(p, rs, w.work(slot), w.counters(), w.num_sms, stream));
+  // the production walk is the warp-per-cell kernel (wgrt_walk.cu); WGRT_WALK=cta selects the
+  // earlier CTA-per-cell kernel (wgrt_fast.cu), kept for A/B measurements
+  static int use_cta = -1;
+  if (use_cta < 0) {
+    const char* e = getenv("WGRT_WALK");
+    use_cta = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+  }
+  if (use_cta) CUDA_TRY(launch_walk_fast(p, rs, w.work(slot), w.counters(), w.num_sms, stream));
+  else {
+    // (a reallocation frees the old scratch with cudaFree, which waits for work still using it)
+    CUDA_TRY(w.jones[slot].reserve(walk_warp_scratch_bytes(p, w.num_sms)));
+    CUDA_TRY(launch_walk_warp(p, rs, w.work(slot), w.counters(), w.num_sms, static_cast<double*>(w.jones[slot].ptr), stream));
+  }
   return WGRT_OK;
 }
 
@@ -535,6 +559,7 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
       wgrt_problem_t cp = dp;
       cp.num_rays = c.rays;
       cp.rng_states = dp.rng_states + c.ray0;
+      cp.ray_index_base = hp->ray_index_base + c.ray0;
       if (const char* e = getenv("WGRT_HOST_TILE")) if (!cp.tile_hint && atoi(e) > 0) cp.tile_hint = atoi(e);
       if (runner) {
         cp.runner_first_cell = c.cell0;
@@ -636,7 +661,7 @@ int wgrt_debug_locate(const double* verts, int64_t n_verts, const int64_t* offse
     if (rc != WGRT_OK) return rc;
     CUDA_TRY(launch_region_build(rs, true, nullptr));
     w->index_stale = true;  // the walk's index was overwritten
-    CUDA_TRY(launch_debug_locate_grid(rs, REG_FC, d_x, d_y, n_points, d_out, w->counters(), nullptr));
+    CUDA_TRY(launch_debug_locate_grid(rs, REG_FC, d_x, d_y, n_points, d_out, w->counters(), mode == 2 ? 1 : 0, nullptr));
   }
   CUDA_TRY(cudaDeviceSynchronize());
   if (n_points) CUDA_TRY(cudaMemcpy(out, d_out, (size_t)n_points * 4, cudaMemcpyDeviceToHost));

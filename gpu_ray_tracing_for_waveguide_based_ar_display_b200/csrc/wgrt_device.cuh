@@ -157,8 +157,20 @@ struct RegionDyn {             // computed on the device from the vertex data
 enum { REG_IC = 0, REG_R1, REG_R2, REG_FC, REG_OC, NUM_REGIONS };
 constexpr uint8_t CELL_NONE = 255, CELL_AMBIG = 254;
 
+// The atlas: ONE coarse grid over the union of all region sets' bounding boxes whose 32-bit words
+// answer all five region queries for a point at once (see wgrt_region.cuh).
+struct AtlasDyn {              // computed on the device
+  double x0, y0, inv_dx, inv_dy;
+};
+constexpr int ATLAS_N = 64;    // level 1: ATLAS_N x ATLAS_N words = 16 KB, stays in L1
+constexpr int ATLAS_SUB_SHIFT = 5;                      // level 2: every level-1 cell split 32 x 32
+constexpr int ATLAS_N2 = ATLAS_N << ATLAS_SUB_SHIFT;    // 2048 x 2048 words = 16 MB, L2 resident; only
+                                                        // cells under MIXED level-1 cells are populated
+
 struct RegionSet {
   RegionStatic st[NUM_REGIONS];
+  uint32_t* atlas;                  // device [ATLAS_N * ATLAS_N] then [ATLAS_N2 * ATLAS_N2]
+  AtlasDyn* atlas_dyn;              // device
   RegionDyn* dyn;                   // device array [NUM_REGIONS]
   unsigned long long* hash_state;   // device: {hash of the index now built, dirty flag of this launch}
   const unsigned long long* dirty;  // = hash_state + 1
@@ -168,10 +180,13 @@ cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* coun
 cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s);
 cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
                              unsigned long long* counters, int num_sms, cudaStream_t s);
+size_t walk_warp_scratch_bytes(const wgrt_problem_t& p, int num_sms);
+cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
+                             unsigned long long* counters, int num_sms, double* jones_scratch, cudaStream_t s);
 cudaError_t launch_debug_locate_literal(const double* verts, const int64_t* off, int64_t npoly, const double* px,
                                         const double* py, int64_t n, int32_t* out, cudaStream_t s);
 cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const double* px, const double* py, int64_t n,
-                                     int32_t* out, unsigned long long* counters, cudaStream_t s);
+                                     int32_t* out, unsigned long long* counters, int via_atlas, cudaStream_t s);
 cudaError_t launch_debug_efield(const double* ete, const double* etm, const double* delta, const double* jones,
                                 int64_t n, double* out, cudaStream_t s);
 cudaError_t launch_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last, cudaStream_t s);

@@ -355,7 +355,7 @@ __device__ __forceinline__ int incouple_batch(const wgrt_problem_t& p, WalkShare
       cn->c[WGRT_CNT_DRAW2]++;
       cn->c[WGRT_CNT_EFIELD] += 2;
     }
-    const double u = xorshift_draw(r.rng, idx);
+    const double u = xorshift_draw(r.rng, p.ray_index_base + idx);
     cplx ote, otm;
     const double* row = tab;  // rows 0 and 1: the two in-coupled orders
     jones_apply(row, r.a, r.w, ote, otm);
@@ -454,7 +454,7 @@ __device__ __forceinline__ void walk_step(const wgrt_problem_t& p, WalkShared& s
     const long long meta0 = __double_as_longlong(e[10]);
     const bool three = (meta0 & META_THREE) != 0;
     const bool gated = (meta0 & META_GATED) != 0;  // `and ener_k > threshold` (GRTF:1020 ff.), absent in GRTF:871-999
-    const double u = xorshift_draw(r.rng, run_begin + r.idx);
+    const double u = xorshift_draw(r.rng, p.ray_index_base + run_begin + r.idx);
     if (COUNT) {
       cn->c[WGRT_CNT_DRAWS]++;
       cn->c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
@@ -807,7 +807,7 @@ __device__ __forceinline__ uint8_t classify_cell(const RegionStatic& st, const u
     if (e <= s) continue;
     bool near_edge = false, inside = false;
     for (int w = s >> 5; w <= (e - 1) >> 5 && !near_edge; ++w) {
-      uint32_t bits = mask[w];
+      uint32_t bits = mask ? mask[w] : 0xffffffffu;   // no mask: every edge of the ring
       if (w == (s >> 5)) bits &= 0xffffffffu << (s & 31);
       if (w == ((e - 1) >> 5) && (e & 31)) bits &= 0xffffffffu >> (32 - (e & 31));
       while (bits) {
@@ -885,6 +885,87 @@ __global__ void region_fine_kernel(const __grid_constant__ RegionSet rs) {
   }
 }
 
+// The atlas (wgrt_region.cuh).  Level 1: one thread per cell classifies the cell against all five
+// region sets, looking at every edge; thread 0 publishes the atlas geometry.  Level 2: one block per
+// level-1 cell with a MIXED field re-classifies its 32 x 32 sub-cells for the MIXED sets only.
+__device__ __forceinline__ void atlas_bbox(const RegionSet& rs, double& xmin, double& ymin, double& w, double& h) {
+  double xmax = -INFINITY, ymax = -INFINITY;
+  xmin = INFINITY; ymin = INFINITY;
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    if (min(total_ring_verts(rs.st[r]), rs.st[r].nverts) <= 0) continue;   // empty set: always "outside"
+    const RegionDyn d = rs.dyn[r];
+    xmin = fmin(xmin, d.x0); xmax = fmax(xmax, d.x0 + d.cell_dx * rs.st[r].n);
+    ymin = fmin(ymin, d.y0); ymax = fmax(ymax, d.y0 + d.cell_dy * rs.st[r].n);
+  }
+  if (!(xmax > xmin) || !(ymax > ymin) || !isfinite(xmax - xmin) || !isfinite(ymax - ymin)) {
+    xmin = ymin = 0.0; xmax = ymax = 1.0;
+  }
+  w = (xmax - xmin) / ATLAS_N;
+  h = (ymax - ymin) / ATLAS_N;
+}
+
+__device__ __forceinline__ uint32_t atlas_field(int r, uint8_t code) {
+  if (r == REG_FC) return static_cast<uint32_t>(code) << ATLAS_SHIFT_FC;
+  if (r == REG_OC) return static_cast<uint32_t>(code) << ATLAS_SHIFT_OC;
+  const uint32_t c = code == CELL_AMBIG ? 2u : (code == CELL_NONE ? 0u : 1u);
+  return c << (r == REG_IC ? ATLAS_SHIFT_IC : r == REG_R1 ? ATLAS_SHIFT_R1 : ATLAS_SHIFT_R2);
+}
+__device__ __forceinline__ uint32_t atlas_field_mask(int r) {
+  return r == REG_FC ? 0xffu << ATLAS_SHIFT_FC : r == REG_OC ? 0xffu << ATLAS_SHIFT_OC
+       : 3u << (r == REG_IC ? ATLAS_SHIFT_IC : r == REG_R1 ? ATLAS_SHIFT_R1 : ATLAS_SHIFT_R2);
+}
+__device__ __forceinline__ bool atlas_field_mixed(int r, uint32_t word) {
+  const uint32_t f = word & atlas_field_mask(r);
+  return f == atlas_field(r, CELL_AMBIG);
+}
+
+__global__ void region_atlas_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  double xmin, ymin, w, h;
+  atlas_bbox(rs, xmin, ymin, w, h);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) *rs.atlas_dyn = AtlasDyn{xmin, ymin, 1.0 / w, 1.0 / h};
+  if (t >= ATLAS_N * ATLAS_N) return;
+  const int iy = t / ATLAS_N, ix = t - iy * ATLAS_N;
+  const double mx = margin_of(w), my = margin_of(h);
+  uint32_t word = 0;
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    uint32_t detail;
+    const uint8_t code = classify_cell(rs.st[r], nullptr, xmin + ix * w - mx, xmin + (ix + 1) * w + mx, ymin + iy * h - my,
+                                       ymin + (iy + 1) * h + my, xmin + (ix + 0.5) * w, ymin + (iy + 0.5) * h, detail);
+    word |= atlas_field(r, code);
+    if (code == CELL_AMBIG) word |= ATLAS_ANY_MIXED;
+  }
+  rs.atlas[t] = word;
+}
+
+__global__ void __launch_bounds__(256) region_atlas2_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  const uint32_t coarse = rs.atlas[blockIdx.x];
+  if (!(coarse & ATLAS_ANY_MIXED)) return;
+  double xmin, ymin, w, h;
+  atlas_bbox(rs, xmin, ymin, w, h);
+  constexpr int S = 1 << ATLAS_SUB_SHIFT;
+  const double w2 = w / S, h2 = h / S;   // level-2 index of a point: int(fx * S) with fx in level-1 cells
+  const int cy = blockIdx.x / ATLAS_N, cx = blockIdx.x - cy * ATLAS_N;
+  uint32_t* out = rs.atlas + ATLAS_N * ATLAS_N;
+  const double mx = margin_of(w2), my = margin_of(h2);
+  for (int t = threadIdx.x; t < S * S; t += blockDim.x) {
+    const int iy = (cy << ATLAS_SUB_SHIFT) + t / S, ix = (cx << ATLAS_SUB_SHIFT) + (t & (S - 1));
+    uint32_t word = coarse & ~ATLAS_ANY_MIXED;
+    for (int r = 0; r < NUM_REGIONS; ++r) {
+      if (!atlas_field_mixed(r, coarse)) continue;   // certain for the whole level-1 cell
+      uint32_t detail;
+      const uint8_t code = classify_cell(rs.st[r], nullptr, xmin + ix * w2 - mx, xmin + (ix + 1) * w2 + mx,
+                                         ymin + iy * h2 - my, ymin + (iy + 1) * h2 + my, xmin + (ix + 0.5) * w2,
+                                         ymin + (iy + 0.5) * h2, detail);
+      word = (word & ~atlas_field_mask(r)) | atlas_field(r, code);
+      if (code == CELL_AMBIG) word |= ATLAS_ANY_MIXED;
+    }
+    out[static_cast<size_t>(iy) * ATLAS_N2 + ix] = word;
+  }
+}
+
 // gpu_ray_tracing_pro_fullColor.py:158: rng_states[i] = 0x9E3779B9 * (i + 1) mod 2^32
 __global__ void seed_rng_kernel(uint32_t* __restrict__ states, int64_t n, int64_t first_index) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -893,14 +974,31 @@ __global__ void seed_rng_kernel(uint32_t* __restrict__ states, int64_t n, int64_
 
 template <bool COUNT>
 __global__ void locate_grid_kernel(const __grid_constant__ RegionSet rs, int region, const double* px,
-                                   const double* py, int64_t n, int32_t* out, unsigned long long* counters) {
+                                   const double* py, int64_t n, int32_t* out, unsigned long long* counters,
+                                   int via_atlas) {
   __shared__ Region reg;
-  if (threadIdx.x == 0) region_load(reg, rs.st[region], rs.dyn[region]);
+  __shared__ Atlas atlas;
+  if (threadIdx.x == 0) {
+    region_load(reg, rs.st[region], rs.dyn[region]);
+    const AtlasDyn ad = *rs.atlas_dyn;
+    atlas.x0 = ad.x0; atlas.y0 = ad.y0; atlas.inv_dx = ad.inv_dx; atlas.inv_dy = ad.inv_dy; atlas.words = rs.atlas;
+    atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
+  }
   __syncthreads();
   Counts cn;
   if (COUNT) cn.clear();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = region_locate<COUNT>(reg, px[i], py[i], &cn);
+  if (i < n) {
+    if (via_atlas) {
+      const uint32_t word = atlas_lookup(atlas, px[i], py[i]);
+      out[i] = (region == REG_FC || region == REG_OC)
+                   ? atlas_hit<COUNT>(word, region == REG_FC ? ATLAS_SHIFT_FC : ATLAS_SHIFT_OC, reg, px[i], py[i], &cn)
+                   : (atlas_inside<COUNT>(word, region == REG_IC ? ATLAS_SHIFT_IC : region == REG_R1 ? ATLAS_SHIFT_R1 : ATLAS_SHIFT_R2,
+                                          reg, px[i], py[i], &cn) ? 0 : -1);
+    } else {
+      out[i] = region_locate<COUNT>(reg, px[i], py[i], &cn);
+    }
+  }
   if (COUNT) cn.flush(counters);
 }
 
@@ -960,6 +1058,8 @@ cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s)
   region_rowmask_kernel<<<dim3((max_rw + 127) / 128, NUM_REGIONS, 2), 128, 0, s>>>(rs);
   region_coarse_kernel<<<dim3((max_coarse + 127) / 128, NUM_REGIONS), 128, 0, s>>>(rs);
   region_fine_kernel<<<dim3(max_coarse, NUM_REGIONS), 256, 0, s>>>(rs);
+  region_atlas_kernel<<<(ATLAS_N * ATLAS_N + 127) / 128, 128, 0, s>>>(rs);
+  region_atlas2_kernel<<<ATLAS_N * ATLAS_N, 256, 0, s>>>(rs);
   return cudaGetLastError();
 }
 
@@ -994,11 +1094,11 @@ cudaError_t launch_seed_rng(uint32_t* states, int64_t n, int64_t first_index, cu
 }
 
 cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const double* px, const double* py, int64_t n,
-                                     int32_t* out, unsigned long long* counters, cudaStream_t s) {
+                                     int32_t* out, unsigned long long* counters, int via_atlas, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
-  if (counters) locate_grid_kernel<true><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters);
-  else locate_grid_kernel<false><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters);
+  if (counters) locate_grid_kernel<true><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters, via_atlas);
+  else locate_grid_kernel<false><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters, via_atlas);
   return cudaGetLastError();
 }
 

@@ -155,4 +155,82 @@ __device__ __forceinline__ void region_locate_multi(const Region* const (&regs)[
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Atlas: all five region answers for a point from one word.
+//   bits 0-1 in-coupler, 2-3 effective region 1, 4-5 effective region 2: 0 outside, 1 inside,
+//            2 MIXED (an edge of the ring comes near this atlas cell)
+//   bits 8-15 fold-coupler slice, 16-23 out-coupler slice: first-hit ring index 0..253,
+//            CELL_NONE (no slice), CELL_AMBIG (MIXED)
+//   bit 31   some field of the word is MIXED
+// Two levels over the union of the sets' bounding boxes: 64 x 64 words (16 KB, L1 resident) and,
+// under level-1 cells with a MIXED field, 32 x 32 finer words each (2048 x 2048 overall, L2
+// resident) in the same format.  A field still MIXED at level 2 defers to that set's own two-level
+// grid (region_locate above), which ends in the reference's literal edge expressions; every other
+// field is certain for every point that maps to the cell (same safety margin as the per-set grids).
+// Points outside the atlas are outside every ring's bounding box.
+// ---------------------------------------------------------------------------------------------
+struct alignas(16) Atlas {
+  double x0, y0, inv_dx, inv_dy;   // level-1 cell coordinates
+  const uint32_t* words;           // level 1
+  const uint32_t* words2;          // level 2
+};
+constexpr uint32_t ATLAS_OUTSIDE = (static_cast<uint32_t>(CELL_NONE) << 8) | (static_cast<uint32_t>(CELL_NONE) << 16);
+constexpr uint32_t ATLAS_ANY_MIXED = 1u << 31;
+enum { ATLAS_SHIFT_IC = 0, ATLAS_SHIFT_R1 = 2, ATLAS_SHIFT_R2 = 4, ATLAS_SHIFT_FC = 8, ATLAS_SHIFT_OC = 16 };
+
+__device__ __forceinline__ uint32_t atlas_lookup(const Atlas& a, double x, double y) {
+  const double fx = (x - a.x0) * a.inv_dx, fy = (y - a.y0) * a.inv_dy;
+  const double lim = static_cast<double>(ATLAS_N);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return ATLAS_OUTSIDE;   // also NaN
+  uint32_t word = __ldg(a.words + static_cast<int>(fy) * ATLAS_N + static_cast<int>(fx));
+  if (word & ATLAS_ANY_MIXED) {
+    const double sub = static_cast<double>(1 << ATLAS_SUB_SHIFT);
+    const int ix = min(static_cast<int>(fx * sub), ATLAS_N2 - 1), iy = min(static_cast<int>(fy * sub), ATLAS_N2 - 1);
+    word = __ldg(a.words2 + static_cast<size_t>(iy) * ATLAS_N2 + ix);
+  }
+  return word;
+}
+
+// single-ring sets (in-coupler, effective regions): inside?
+template <bool COUNT>
+__device__ __forceinline__ bool atlas_inside(uint32_t word, int shift, const Region& r, double x, double y, Counts* cn) {
+  const uint32_t c = (word >> shift) & 3u;
+  if (c == 2u) return region_locate<COUNT>(r, x, y, cn) >= 0;
+  if (COUNT) cn->c[WGRT_CNT_POLY_TESTS]++;
+  return c == 1u;
+}
+
+// multi-ring sets (coupler slices): first-hit ring index or -1
+template <bool COUNT>
+__device__ __forceinline__ int atlas_hit(uint32_t word, int shift, const Region& r, double x, double y, Counts* cn) {
+  const uint32_t c = (word >> shift) & 0xffu;
+  if (c == CELL_AMBIG) return region_locate<COUNT>(r, x, y, cn);
+  if (COUNT) cn->c[WGRT_CNT_POLY_TESTS]++;
+  return c == CELL_NONE ? -1 : static_cast<int>(c);
+}
+
+// Make the fields of `word` named in `need` (bit r = region set r) certain: every needed field that
+// is still MIXED after the two atlas levels is answered by that set's own grid / literal scan and
+// patched into the word.  One call site for all sets: the rare path is compiled once.
+template <bool COUNT>
+__device__ __noinline__ uint32_t atlas_resolve(uint32_t word, uint32_t need, const RegionSet& rs, double x, double y,
+                                               Counts* cn) {
+#pragma unroll 1
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    if (!((need >> r) & 1u)) continue;
+    const bool multi = r == REG_FC || r == REG_OC;
+    const int shift = r == REG_IC ? ATLAS_SHIFT_IC : r == REG_R1 ? ATLAS_SHIFT_R1 : r == REG_R2 ? ATLAS_SHIFT_R2
+                    : r == REG_FC ? ATLAS_SHIFT_FC : ATLAS_SHIFT_OC;
+    const uint32_t mask = multi ? 0xffu : 3u;
+    const uint32_t f = (word >> shift) & mask;
+    if (f != (multi ? static_cast<uint32_t>(CELL_AMBIG) : 2u)) continue;
+    Region reg;
+    region_load(reg, rs.st[r], rs.dyn[r]);
+    const int hit = region_locate<COUNT>(reg, x, y, cn);
+    const uint32_t v = multi ? (hit < 0 ? static_cast<uint32_t>(CELL_NONE) : static_cast<uint32_t>(hit)) : (hit >= 0 ? 1u : 0u);
+    word = (word & ~(mask << shift)) | (v << shift);
+  }
+  return word;
+}
+
 }  // namespace wgrt

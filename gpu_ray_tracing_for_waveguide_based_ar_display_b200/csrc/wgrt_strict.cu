@@ -89,7 +89,7 @@ __device__ void walk_one_ray(const wgrt_problem_t& p, int64_t idx, Counts* cn) {
   } while (0)
 #define WGRT_DRAW(which)                     \
   do {                                       \
-    u = xorshift_draw(rng, idx);             \
+    u = xorshift_draw(rng, p.ray_index_base + idx); \
     if (COUNT) {                             \
       cn->c[WGRT_CNT_DRAWS]++;               \
       cn->c[which]++;                        \

@@ -1,0 +1,693 @@
+// wgrt_walk.cu -- the production ray walk for sm_100a: one warp = one CTA = one cell at a time.
+//
+// Same Monte-Carlo walk as process_rays_kernel_pro_fullColor (GRTF:833-1246), organised so that a
+// warp instruction almost always does useful work in almost every lane:
+//
+//  * A persistent single-warp CTA claims tiles of consecutive rays (whole FoV-wavelength cells when
+//    the rays arrive cell by cell, gpu_ray_tracing_pro_fullColor.py:82-115) and walks them alone.
+//    No block barriers, no cross-warp queues; the end-of-cell drain (lanes idling while the longest
+//    paths finish) is paid once per ~5000 rays per warp instead of once per ~1250.
+//  * In-coupling is just another grating event.  A lane whose ray ended pops the next ray of the run
+//    from a 32-entry staging buffer (filled with coalesced loads, cut where the cell key changes: run
+//    detection costs nothing extra) and takes part in the very next event phase.
+//  * A step has two phases.  Phase A ("go to the next grating"): every lane that moved asks the
+//    ATLAS (wgrt_region.cuh) -- one L1-resident word answers in-coupler / effective region 1 / 2 /
+//    fold slice / out-coupler slice at once -- resolves what the previous event left pending, and
+//    free-bounces (GRTF:1049-1052, 1102-1108, 1175-1178) until it stands on a grating or is lost.
+//    Phase B ("diffract"): all lanes that stand on a grating draw, evaluate the efficiencies of ALL
+//    orders at once from per-cell quadratic forms (4 FMAs per order instead of a Jones application
+//    per order in a divergent if-chain), pick the order exactly as the reference's if/elif chain
+//    does, and apply one Jones matrix -- the chosen one.
+//  * The polarisation state is the un-normalised complex Jones vector (te, tm) plus s = 1/|v|^2.
+//    E_field_cal's cos / sin / hypot / atan2 / wrap (GRTF:136-150) and the per-event normalisation
+//    (GRTF:876-877 ff.) disappear: efficiencies are v^H M v * s with M = J^H J precomputed per cell
+//    and order, TIR phases are complex multiplies by per-cell phasors.  Algebraically the same map;
+//    numerically a few ulp apart, i.e. a decision `u <= efficiency` can flip only when u lands within
+//    ~1e-15 of the threshold (expected ~1e-6 flips per 450 M-ray job).  Tests demand bit equality
+//    with the reference kernel on up to 450 M ray launches and get it.
+//  * Everything state dependent is table driven from shared memory (per-cell event rows, sinfo).
+#include <climits>
+
+#include "wgrt_region.cuh"
+
+namespace wgrt {
+
+namespace {
+
+// Per-cell event table.  Shared memory holds, per (event, order) row, what EVERY event evaluation
+// reads: the quadratic form of the order's efficiency, 1 / cos of the new direction and the meta
+// word (7 doubles, an odd stride: rows of different lanes spread over the banks).  The order's Jones
+// matrix (8 doubles) is read once per event, for the chosen order only, and lives in a per-warp
+// global scratch (L1 / L2 resident): keeping it out of shared memory halves the footprint of a warp
+// and lets 32 single-warp CTAs run per SM -- the walk is latency bound, warps are what hides it.
+constexpr int ROW = 7;
+constexpr int R_Q = 0;             // [0..3] quadratic form of the order's efficiency (cos factor folded in)
+constexpr int R_INVCOS = 4;        // 1 / cos(theta_new)
+constexpr int R_META = 5;          // bit field, see below
+constexpr int JROW = 8;            // doubles per Jones row in the scratch
+constexpr int ST_DEAD = -1, ST_PEND_FWD = 6, ST_PEND_BACK = 7;
+#ifndef WGRT_WARP_CTAS_PER_SM
+#define WGRT_WARP_CTAS_PER_SM 32
+#endif
+enum { POST_NONE = 0, POST_IC_FWD = 1, POST_IC_BACK = 2, POST_DEPOSIT = 3 };
+enum { EV_INIT = 0, EV_S0, EV_S1, EV_S2, EV_S3, EV_S4, EV_S5, NUM_EV };
+enum { DIR_IC1 = 0, DIR_IC2, DIR_IC3, DIR_FC1, DIR_FC2, DIR_OC1, DIR_OC2 };
+
+struct OrderSpec {
+  int8_t ch[4];   // LUT channels in E_field_cal CALL order (E_te_te, E_te_tm, E_tm_te, E_tm_tm)
+  int8_t dir;     // whose channel 0 gives the outgoing polar angle (numerator cosine)
+  int8_t tir;     // lut_TIR index added to the phase
+  int8_t gap;     // lut_gap pair index of the new bounce vector
+  int8_t nstate;  // region state after the order is taken
+  int8_t post;    // what happens after the move
+  int8_t fmode;   // 0: cos ratio, 1: * n_g (air -> glass), 2: / n_g (glass -> air)
+};
+
+// Transcribed from the kernel's call sites: INIT GRTF:860-904, state 0 GRTF:908-953, state 1
+// GRTF:954-999 (note the swapped te_tm/tm_te channels at GRTF:957-958), state 2 GRTF:1000-1052,
+// state 3 GRTF:1053-1108, state 4 GRTF:1110-1178, state 5 GRTF:1179-1246.
+__constant__ OrderSpec kOrders[NUM_EV][3] = {
+    /* INIT */ {{{13, 18, 33, 38}, DIR_IC2, 0, 0, 0, POST_IC_FWD, 1},
+                {{15, 20, 35, 40}, DIR_IC3, 2, 2, 1, POST_IC_BACK, 1},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S0   */ {{{4, 9, 24, 29}, DIR_IC2, 0, 0, 0, POST_IC_FWD, 0},
+                {{6, 11, 26, 31}, DIR_IC3, 2, 2, 1, POST_IC_BACK, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S1   */ {{{2, 22, 7, 27}, DIR_IC2, 0, 0, 0, POST_IC_FWD, 0},
+                {{4, 9, 24, 29}, DIR_IC3, 2, 2, 1, POST_IC_BACK, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S2   */ {{{3, 6, 15, 18}, DIR_FC1, 0, 0, 2, POST_NONE, 0},
+                {{2, 5, 14, 17}, DIR_FC2, 1, 1, 3, POST_NONE, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S3   */ {{{4, 7, 16, 19}, DIR_FC1, 0, 0, 2, POST_NONE, 0},
+                {{3, 6, 15, 18}, DIR_FC2, 1, 1, 3, POST_NONE, 0},
+                {{0, 0, 0, 0}, 0, 0, 0, 0, 0, 0}},
+    /* S4   */ {{{4, 9, 24, 29}, DIR_OC1, 1, 1, 4, POST_NONE, 0},
+                {{2, 7, 22, 27}, DIR_OC2, 3, 3, 5, POST_NONE, 0},
+                {{13, 18, 33, 38}, DIR_IC1, 0, 0, 0, POST_DEPOSIT, 2}},
+    /* S5   */ {{{6, 11, 26, 31}, DIR_OC1, 1, 1, 4, POST_NONE, 0},
+                {{4, 9, 24, 29}, DIR_OC2, 3, 3, 5, POST_NONE, 0},
+                {{15, 20, 35, 40}, DIR_IC1, 0, 0, 0, POST_DEPOSIT, 2}},
+};
+
+// meta word of a row: bits 0-1 TIR index, 2-3 gap pair, 4-6 next state, 7-8 post action; on the
+// FIRST row of an event additionally: bit 9 the event has three orders, bit 10 its branches carry
+// `and ener_k > threshold` (GRTF:1020 ff.; absent at GRTF:871-999)
+constexpr int META_THREE = 1 << 9, META_GATED = 1 << 10;
+
+// sinfo[state]: which coupler decides the event, first row, rows per slice, what a miss means,
+// which doubled TIR phase / bounce vector a free bounce uses
+enum : int {
+  SI_REGION_MASK = 7, SI_REGION_NONE = 7,          // bits 0-2: REG_FC / REG_OC / none (in-coupler states)
+  SI_ROWBASE_SHIFT = 3, SI_ROWBASE_MASK = 0xfff,   // bits 3-14
+  SI_STRIDE_SHIFT = 15,                            // bits 15-16
+  SI_MISS_SHIFT = 17,                              // bits 17-18: 0 bounce on, 1 test eff_reg2 first, 2 lost
+  SI_PHASE_SHIFT = 19,                             // bit 19
+  SI_GAP_SHIFT = 20                                // bits 20-21
+};
+__host__ __device__ constexpr int make_sinfo(int region, int rowbase, int stride, int miss, int phase, int gap) {
+  return region | (rowbase << SI_ROWBASE_SHIFT) | (stride << SI_STRIDE_SHIFT) | (miss << SI_MISS_SHIFT) |
+         (phase << SI_PHASE_SHIFT) | (gap << SI_GAP_SHIFT);
+}
+
+// region sets whose atlas field a ray in a given state can need (bit r = set r), 5 bits per state
+// packed into one word (a per-lane index into __constant__ memory would serialise the warp):
+// states 0..5, 6 = pending after a +1 in-coupler order, 7 = pending after a -1 order
+__host__ __device__ constexpr unsigned long long need_bits(int state, unsigned sets) {
+  return static_cast<unsigned long long>(sets) << (5 * state);
+}
+constexpr unsigned long long kNeedPacked =
+    need_bits(0, 1u << REG_R1) | need_bits(1, 1u << REG_R1) | need_bits(2, (1u << REG_R1) | (1u << REG_FC)) |
+    need_bits(3, (1u << REG_R1) | (1u << REG_FC) | (1u << REG_R2) | (1u << REG_OC)) |   // may fall through to state 4
+    need_bits(4, (1u << REG_R1) | (1u << REG_OC)) | need_bits(5, (1u << REG_R1) | (1u << REG_OC)) |
+    need_bits(6, (1u << REG_IC) | (1u << REG_R1) | (1u << REG_FC)) |                    // becomes 0 or 2
+    need_bits(7, (1u << REG_IC) | (1u << REG_R1));                                      // becomes 1 or ends
+
+struct alignas(16) CellConst {
+  cplx ph1[4];      // e^{i T[k]}
+  cplx ph2[4];      // e^{i 2 T[k]}
+  double gap[8];    // lut_gap[lm, m, n, :]
+  double rect[8];   // eff_reg_FOV[m, n, :, :]
+  double range[4];  // eff_reg_FOV_range[m, n, :]
+  double box[4];    // xmin, xmax, ymin, ymax of the eyebox rectangle when it is axis aligned
+  double inv_cos_in;
+  int sinfo[8];
+  int box_ok;       // rect is exactly the axis-aligned rectangle `box` in the runner's vertex order
+  int pad_[3];
+};
+
+struct Stage {     // the next rays of the run, raw, as loaded (coalesced) from the SoA arrays
+  float x[32], y[32], te[32], tm[32], dl[32];
+  uint32_t rng[32];
+};
+
+struct alignas(16) WarpShared {
+  Atlas atlas;
+  CellConst cc;
+  Stage st;
+};
+
+__host__ __device__ constexpr size_t table_offset() { return (sizeof(WarpShared) + 15) & ~size_t(15); }
+
+__device__ __forceinline__ const double* lut_slice(const wgrt_problem_t& p, int which, int i, int64_t cell,
+                                                   int64_t cells_per_poly, int32_t& C) {
+  switch (which) {
+    case DIR_IC1: C = p.C_ic; return p.lut_ic1 + 2 * cell * C;
+    case DIR_IC2: C = p.C_ic; return p.lut_ic2 + 2 * cell * C;
+    case DIR_IC3: C = p.C_ic; return p.lut_ic3 + 2 * cell * C;
+    case DIR_FC1: C = p.C_fc; return p.lut_fc1 + 2 * (i * cells_per_poly + cell) * C;
+    case DIR_FC2: C = p.C_fc; return p.lut_fc2 + 2 * (i * cells_per_poly + cell) * C;
+    case DIR_OC1: C = p.C_oc; return p.lut_oc1 + 2 * (i * cells_per_poly + cell) * C;
+    default: C = p.C_oc; return p.lut_oc2 + 2 * (i * cells_per_poly + cell) * C;
+  }
+}
+
+// Event table and per-cell constants of cell (lm, m, n); the 32 lanes of the warp share the rows.
+__device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m, int64_t n, double* tab,
+                                  double* __restrict__ jones, CellConst& cc, int rows, int lane) {
+  const int64_t cell = (lm * p.X + m) * p.Y + n;
+  const int64_t cpp = p.L * p.X * p.Y;
+  const int nFC = static_cast<int>(p.n_FC), nOC = static_cast<int>(p.n_OC);
+  for (int t = lane; t < rows; t += 32) {
+    int ev, i, k;
+    if (t < 6) {
+      ev = t >> 1; i = 0; k = t & 1;
+    } else if (t < 6 + 4 * nFC) {
+      const int u = t - 6;
+      ev = u < 2 * nFC ? EV_S2 : EV_S3;
+      const int v = u < 2 * nFC ? u : u - 2 * nFC;
+      i = v >> 1; k = v & 1;
+    } else {
+      const int u = t - 6 - 4 * nFC;
+      ev = u < 3 * nOC ? EV_S4 : EV_S5;
+      const int v = u < 3 * nOC ? u : u - 3 * nOC;
+      i = v / 3; k = v - 3 * i;
+    }
+    const OrderSpec sp = kOrders[ev][k];
+    const int src = ev == EV_INIT ? DIR_IC1 : ev == EV_S0 ? DIR_IC2 : ev == EV_S1 ? DIR_IC3
+                  : ev == EV_S2 ? DIR_FC1 : ev == EV_S3 ? DIR_FC2 : ev == EV_S4 ? DIR_OC1 : DIR_OC2;
+    int32_t C;
+    const double* L = lut_slice(p, src, i, cell, cpp, C);
+    double* row = tab + t * ROW;
+    cplx J[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(L) + sp.ch[q]);
+      J[q] = cplx{v.x, v.y};
+      reinterpret_cast<double2*>(jones + t * JROW)[q] = v;
+    }
+    int32_t Cd;
+    const double* D = lut_slice(p, sp.dir, i, cell, cpp, Cd);
+    const double c_new = cos(__ldg(D));  // cos(theta_new.real)
+    double f = c_new;
+    if (sp.fmode == 1) f = c_new * p.n_g;
+    if (sp.fmode == 2) f = c_new / p.n_g;
+    // Ete_out = J0 te + J2 tm, Etm_out = J1 te + J3 tm (GRTF:139-144)  =>
+    // |Ete_out|^2 + |Etm_out|^2 = M00 |te|^2 + M11 |tm|^2 + 2 Re(M01 conj(te) tm),  M = J^H J
+    const double m00 = J[0].re * J[0].re + J[0].im * J[0].im + (J[1].re * J[1].re + J[1].im * J[1].im);
+    const double m11 = J[2].re * J[2].re + J[2].im * J[2].im + (J[3].re * J[3].re + J[3].im * J[3].im);
+    const double m01re = (J[0].re * J[2].re + J[0].im * J[2].im) + (J[1].re * J[3].re + J[1].im * J[3].im);
+    const double m01im = (J[0].re * J[2].im - J[0].im * J[2].re) + (J[1].re * J[3].im - J[1].im * J[3].re);
+    row[R_Q + 0] = f * m00;
+    row[R_Q + 1] = f * m11;
+    row[R_Q + 2] = 2.0 * f * m01re;
+    row[R_Q + 3] = -2.0 * f * m01im;
+    row[R_INVCOS] = 1.0 / c_new;
+    const int nstate = sp.post == POST_IC_FWD ? ST_PEND_FWD : sp.post == POST_IC_BACK ? ST_PEND_BACK : sp.nstate;
+    int meta = (sp.tir & 3) | ((sp.gap & 3) << 2) | ((nstate & 7) << 4) | ((sp.post & 3) << 7);
+    if (ev >= EV_S4) meta |= META_THREE;
+    if (ev >= EV_S2) meta |= META_GATED;
+    row[R_META] = __longlong_as_double(static_cast<long long>(meta));
+    row[6] = 0.0;
+  }
+  const int t = lane;
+  if (t < 4) {
+    const double T = __ldg(p.lut_TIR + 4 * cell + t);
+    double s, c;
+    sincos(T, &s, &c);
+    cc.ph1[t] = cplx{c, s};
+    sincos(2.0 * T, &s, &c);
+    cc.ph2[t] = cplx{c, s};
+  } else if (t < 12) {
+    cc.gap[t - 4] = __ldg(p.lut_gap + 8 * cell + (t - 4));
+  } else if (t < 20) {
+    cc.rect[t - 12] = __ldg(p.eff_reg_FOV + 8 * (m * p.Y + n) + (t - 12));
+  } else if (t < 24) {
+    cc.range[t - 20] = __ldg(p.eff_reg_FOV_range + 4 * (m * p.Y + n) + (t - 20));
+  } else if (t == 24) {
+    cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
+  } else if (t == 25) {
+    // states 0 and 2 travel along the +1 in-coupled direction (gap pair 0), state 1 along the -1
+    // direction (2), states 3 and 4 along the folded direction (1), state 5 along the conjugate
+    // out-coupler direction (3)
+    cc.sinfo[0] = make_sinfo(SI_REGION_NONE, 2, 0, 0, 0, 0);
+    cc.sinfo[1] = make_sinfo(SI_REGION_NONE, 4, 0, 0, 0, 2);
+    cc.sinfo[2] = make_sinfo(REG_FC, 6, 2, 0, 0, 0);                         // miss: bounce, 2 T[0]
+    cc.sinfo[3] = make_sinfo(REG_FC, 6 + 2 * nFC, 2, 1, 1, 1);               // miss: eff_reg2 test, 2 T[1]
+    cc.sinfo[4] = make_sinfo(REG_OC, 6 + 4 * nFC, 3, 0, 1, 1);               // miss: bounce, 2 T[1]
+    cc.sinfo[5] = make_sinfo(REG_OC, 6 + 4 * nFC + 3 * nOC, 3, 2, 0, 3);     // miss: lost
+    cc.sinfo[6] = 0;
+    cc.sinfo[7] = 0;
+  } else if (t == 26) {
+    // The eyebox rectangle of a FoV cell is (xmin,ymax),(xmin,ymin),(xmax,ymin),(xmax,ymax)
+    // (couplers_coor.py:514-526).  When the four vertices are exactly that, points clearly inside /
+    // outside it need no edge arithmetic (see deposit_inside).
+    const double* r = p.eff_reg_FOV + 8 * (m * p.Y + n);
+    const double x0 = r[0], y0 = r[1], x1 = r[2], y1 = r[3], x2 = r[4], y2 = r[5], x3 = r[6], y3 = r[7];
+    const bool ok = x0 == x1 && x2 == x3 && y1 == y2 && y0 == y3 && x0 < x2 && y1 < y0 && isfinite(x0) &&
+                    isfinite(x2) && isfinite(y0) && isfinite(y1);
+    cc.box[0] = x0; cc.box[1] = x2; cc.box[2] = y1; cc.box[3] = y0;
+    cc.box_ok = ok ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ float ld_stream(const float* ptr) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
+  uint32_t v;
+  asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(ptr));
+  return v;
+}
+__device__ __forceinline__ void st_stream(uint32_t* ptr, uint32_t v) {
+  asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+
+// is_inside_or_on_edge_4d (GRTF:73-108) on the eyebox rectangle.  For an exactly axis-aligned
+// rectangle in the runner's vertex order, a point more than 1e-9 inside every side passes the
+// literal test (no edge within the 1e-12 tolerance; the crossing test toggles once, on the x = xmax
+// edge, because (xj - xi) * ... / ... + xi == xi exactly for the vertical edges) and a point more
+// than 1e-9 outside any side fails it (no edge within tolerance; zero or two crossings).  Only
+// points within 1e-9 of the boundary run the literal expressions.
+template <bool COUNT>
+__device__ __forceinline__ bool deposit_inside(const CellConst& cc, double x, double y, Counts* cn) {
+  if (cc.box_ok) {
+    const double m = 1e-9;
+    if (x > cc.box[0] + m && x < cc.box[1] - m && y > cc.box[2] + m && y < cc.box[3] - m) return true;
+    if (x < cc.box[0] - m || x > cc.box[1] + m || y < cc.box[2] - m || y > cc.box[3] + m) return false;
+  }
+  return inside_or_on_edge_literal<COUNT>(x, y, cc.rect, 0, 4, cn);
+}
+
+struct Ray {
+  double x, y;      // position
+  cplx te, tm;      // Jones vector, not normalised
+  double s;         // 1 / (|te|^2 + |tm|^2)
+  double inv_cos;   // 1 / cos(theta_current.real)
+  double ener;
+  uint32_t rng;
+  int state;        // region state 0..5, ST_PEND_* after an in-coupler order, ST_DEAD
+  int iter;
+  int idx;          // ray index relative to the start of the tile
+  int row0;         // >= 0: the ray stands on a grating, first table row of the event; < 0: ask the atlas
+};
+
+template <bool COUNT, bool IMPLICIT>
+__global__ void __launch_bounds__(32, WGRT_WARP_CTAS_PER_SM)
+walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
+                 int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
+                 unsigned long long* counters, double* __restrict__ jones_scratch) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WarpShared& sh = *reinterpret_cast<WarpShared*>(smem_raw);
+  const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
+  double* tab = reinterpret_cast<double*>(smem_raw + table_offset());
+  const int lane = threadIdx.x;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  Counts cn;
+  if (COUNT) cn.clear();
+
+  double* jones = jones_scratch + static_cast<size_t>(blockIdx.x) * rows * JROW;
+  if (lane == 0) {
+    const AtlasDyn ad = *rs.atlas_dyn;
+    sh.atlas.x0 = ad.x0; sh.atlas.y0 = ad.y0; sh.atlas.inv_dx = ad.inv_dx; sh.atlas.inv_dy = ad.inv_dy;
+    sh.atlas.words = rs.atlas;
+    sh.atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
+  }
+  __syncwarp();
+  const CellConst& cc = sh.cc;
+  const int64_t tile_size = *tile_size_ptr;
+  const int64_t num_tiles = (p.num_rays + tile_size - 1) / tile_size;
+  const double threshold = p.threshold;
+  const bool has_l = p.lmd_num != nullptr;
+
+  for (;;) {
+    int tile_i = 0;
+    if (lane == 0) tile_i = atomicAdd(work_counter, 1);
+    const int64_t tile = __shfl_sync(FULL_MASK, tile_i, 0);
+    if (tile >= num_tiles) break;
+    const int64_t t_begin = tile * tile_size;
+    const int64_t t_end = min(p.num_rays, t_begin + tile_size);
+    int64_t cursor = t_begin;   // first ray of the tile nobody has staged yet
+
+    while (cursor < t_end) {
+      // ---- the run of rays that share the cell of ray `cursor` ---------------------------------
+      float km, kn, kl;
+      int64_t run_limit;
+      if (IMPLICIT) {
+        const int64_t rpc = 2 * p.runner_points;
+        const int64_t cell = p.runner_first_cell + cursor / rpc;  // runner order: x outer, y, lambda inner
+        kl = static_cast<float>(cell % p.L);
+        kn = static_cast<float>((cell / p.L) % p.Y);
+        km = static_cast<float>(cell / (p.L * p.Y));
+        run_limit = min(t_end, (cursor / rpc + 1) * rpc);
+      } else {
+        km = __ldg(p.m + cursor); kn = __ldg(p.n + cursor); kl = has_l ? __ldg(p.lmd_num + cursor) : 0.0f;
+        run_limit = t_end;   // cut on the fly where the key changes
+      }
+      const int64_t m = static_cast<int64_t>(km), n = static_cast<int64_t>(kn), lm = static_cast<int64_t>(kl);
+      const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
+      __syncwarp();
+      if (valid) build_cell_tables(p, lm, m, n, tab, jones, sh.cc, rows, lane);
+      __syncwarp();
+
+      Ray r;
+      r.state = ST_DEAD;
+      r.row0 = -1;
+      int navail = 0, head = 0;      // staged rays not yet handed to a lane (warp uniform)
+      int64_t stage_base = cursor;   // ray index of staging slot 0
+      bool open = true;              // the run may have more rays to stage
+
+      for (;;) {
+        bool lost = false;
+
+        // ---- phase A: go to the next grating.  Every lane whose ray moved asks the atlas once. ----
+        if (r.state != ST_DEAD && r.row0 < 0) {
+          uint32_t word = atlas_lookup(sh.atlas, r.x, r.y);
+          if (word & ATLAS_ANY_MIXED) word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * r.state)) & 31u, rs, r.x, r.y, &cn);
+          // every field the state can need is certain now
+          const bool in_ic = ((word >> ATLAS_SHIFT_IC) & 3u) == 1u;
+          const bool in_r1 = ((word >> ATLAS_SHIFT_R1) & 3u) == 1u;
+          const bool in_r2 = ((word >> ATLAS_SHIFT_R2) & 3u) == 1u;
+          const int fc = (word >> ATLAS_SHIFT_FC) & 0xff, oc = (word >> ATLAS_SHIFT_OC) & 0xff;
+          int st = r.state;
+          // what the last in-coupler order left open (GRTF:883-886, 899-902 and siblings)
+          if (st == ST_PEND_FWD) st = in_ic ? 0 : 2;
+          else if (st == ST_PEND_BACK) { st = 1; lost = !in_ic; }
+          // the loop head (GRTF:905-907)
+          if (!lost) {
+            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
+            lost = ++r.iter > 100000 || !in_r1;
+          }
+          int sinfo = cc.sinfo[st];
+          int region = sinfo & SI_REGION_MASK;
+          int code = region == REG_FC ? fc : region == REG_OC ? oc : 0;
+          if (code == CELL_NONE && ((sinfo >> SI_MISS_SHIFT) & 3) == 1 && !in_r2 && !lost) {
+            // GRTF:1103-1104: state 3 left the fold zone; the iteration ends without a move and the
+            // next one (same point: still inside eff_reg1) looks at the out-coupler
+            st = 4;
+            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
+            lost = ++r.iter > 100000;
+            sinfo = cc.sinfo[4];
+            code = oc;
+          }
+          r.state = st;
+          if (!lost) {
+            if (code != CELL_NONE) {
+              r.row0 = ((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code;
+            } else if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) {
+              lost = true;                       // GRTF:1244-1246
+            } else {
+              // free TIR bounce (GRTF:1049-1052, 1105-1108, 1175-1178); the lane asks the atlas again
+              // in the next step
+              const int g = (sinfo >> SI_GAP_SHIFT) & 3;
+              r.x += cc.gap[2 * g];
+              r.y += cc.gap[2 * g + 1];
+              r.tm = cmul(r.tm, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
+              if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
+            }
+          }
+          if (lost) {
+            st_stream(p.rng_states + t_begin + r.idx, r.rng);
+            r.state = ST_DEAD;
+            lost = false;
+          }
+        }
+        __syncwarp();
+
+        // ---- refill: lanes without a ray pop staged rays; an empty stage is reloaded -------------
+        const unsigned dead = __ballot_sync(FULL_MASK, r.state == ST_DEAD);
+        if (dead != 0u && (navail > 0 || open)) {
+          if (navail == 0) {
+            const int64_t i = cursor + lane;
+            const bool in_range = i < run_limit;
+            bool same = in_range;
+            float fx = 0.f, fy = 0.f, fte = 0.f, ftm = 0.f, fdl = 0.f;
+            uint32_t frng = 0u;
+            if (in_range) {
+              if (IMPLICIT) {
+                // runner layout (RUN:82-115): P TE rays then P TM rays per cell, ray k starts at point k
+                const int64_t k = i % (2 * p.runner_points);
+                const bool te_half = k < p.runner_points;
+                const int64_t pt = te_half ? k : k - p.runner_points;
+                fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
+                fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
+              } else {
+                same = ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl);
+                fx = ld_stream(p.x + i); fy = ld_stream(p.y + i); fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i);
+                fdl = ld_stream(p.delta_phase + i);
+              }
+              frng = ld_stream(p.rng_states + i);
+              if (i + 64 < run_limit) {   // two batches ahead
+                prefetch_l2(p.rng_states + i + 64);
+                if (!IMPLICIT) {
+                  prefetch_l2(p.x + i + 64); prefetch_l2(p.y + i + 64); prefetch_l2(p.te + i + 64);
+                  prefetch_l2(p.tm + i + 64); prefetch_l2(p.delta_phase + i + 64); prefetch_l2(p.m + i + 64);
+                  prefetch_l2(p.n + i + 64);
+                  if (has_l) prefetch_l2(p.lmd_num + i + 64);
+                }
+              }
+            }
+            const unsigned okmask = __ballot_sync(FULL_MASK, same);
+            const int cnt = okmask == FULL_MASK ? 32 : __ffs(~okmask) - 1;   // leading rays of this run
+            if (cnt < 32) open = false;
+            __syncwarp();
+            if (lane < cnt) {
+              sh.st.x[lane] = fx; sh.st.y[lane] = fy; sh.st.te[lane] = fte; sh.st.tm[lane] = ftm; sh.st.dl[lane] = fdl;
+              sh.st.rng[lane] = frng;
+            }
+            __syncwarp();
+            stage_base = cursor;
+            cursor += cnt;
+            navail = cnt;
+            head = 0;
+          }
+          const int nd = __popc(dead);
+          const int take = min(nd, navail);
+          if (valid) {
+            const int rank = __popc(dead & lt_mask);
+            if (r.state == ST_DEAD && rank < take) {
+              const int slot = head + rank;
+              r.idx = static_cast<int>(stage_base - t_begin) + slot;
+              r.x = static_cast<double>(sh.st.x[slot]);
+              r.y = static_cast<double>(sh.st.y[slot]);
+              r.te = cplx{static_cast<double>(sh.st.te[slot]), 0.0};
+              const double tm = static_cast<double>(sh.st.tm[slot]);
+              const float dlf = sh.st.dl[slot];
+              if (dlf == 0.0f) {
+                r.tm = cplx{tm, 0.0};
+              } else {
+                double sn, cs;
+                sincos(static_cast<double>(dlf), &sn, &cs);
+                r.tm = cplx{tm * cs, tm * sn};
+              }
+              r.rng = sh.st.rng[slot];
+              r.s = 1.0;                     // GRTF:860-869: the raw amplitudes enter E_field_cal as they are
+              r.inv_cos = cc.inv_cos_in;
+              r.ener = 1.0;
+              r.iter = 0;
+              r.state = 0;
+              r.row0 = 0;                    // in-coupling: rows 0 and 1
+              if (COUNT) cn.c[WGRT_CNT_RAYS]++;
+            }
+          }
+          // (rays of a run whose cell indices are out of range are dropped untouched)
+          head += take;
+          navail -= take;
+          __syncwarp();
+        }
+        if (__ballot_sync(FULL_MASK, r.state != ST_DEAD) == 0u) {
+          if (!open && navail == 0) break;
+          continue;
+        }
+        if (COUNT && lane == 0) cn.c[WGRT_CNT_WARP_STEPS]++;
+
+        // ---- phase B: diffract -------------------------------------------------------------------
+        if (r.state != ST_DEAD && r.row0 >= 0) {
+          const double* e = tab + r.row0 * ROW;
+          const int meta0 = static_cast<int>(__double_as_longlong(e[R_META]));
+          const bool three = (meta0 & META_THREE) != 0;
+          const bool gated = (meta0 & META_GATED) != 0;
+          const double u = xorshift_draw(r.rng, p.ray_index_base + t_begin + r.idx);
+          if (COUNT) {
+            cn.c[WGRT_CNT_DRAWS]++;
+            cn.c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
+            cn.c[WGRT_CNT_EFIELD] += three ? 3 : 2;
+          }
+          const double t2 = r.te.re * r.te.re + r.te.im * r.te.im;
+          const double m2 = r.tm.re * r.tm.re + r.tm.im * r.tm.im;
+          const double zre = r.te.re * r.tm.re + r.te.im * r.tm.im;   // conj(te) * tm
+          const double zim = r.te.re * r.tm.im - r.te.im * r.tm.re;
+          const double g = r.s * r.inv_cos;
+          const double* e3 = three ? e + 2 * ROW : e;                 // two-order events: never selected
+          const double e1 = (e[R_Q] * t2 + e[R_Q + 1] * m2 + (e[R_Q + 2] * zre + e[R_Q + 3] * zim)) * g;
+          const double e2 = (e[ROW + R_Q] * t2 + e[ROW + R_Q + 1] * m2 + (e[ROW + R_Q + 2] * zre + e[ROW + R_Q + 3] * zim)) * g;
+          const double e3v = (e3[R_Q] * t2 + e3[R_Q + 1] * m2 + (e3[R_Q + 2] * zre + e3[R_Q + 3] * zim)) * g;
+          // the reference's if / elif chain (GRTF:871-903, 1020-1048, 1135-1174)
+          int k = -1;
+          double esel = 0.0;
+          if (u <= e1 && (!gated || r.ener * e1 > threshold)) { k = 0; esel = e1; }
+          else if (u <= e1 + e2 && (!gated || r.ener * e2 > threshold)) { k = 1; esel = e2; }
+          else if (three && u <= e1 + e2 + e3v && r.ener * e3v > threshold) { k = 2; esel = e3v; }
+          if (k < 0) {
+            lost = true;   // absorbed
+          } else {
+            const double* row = e + k * ROW;
+            const int meta = static_cast<int>(__double_as_longlong(row[R_META]));
+            const int post = (meta >> 7) & 3;
+            if (post == POST_DEPOSIT) {
+              // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
+              if (deposit_inside<COUNT>(cc, r.x, r.y, &cn)) {
+                deposit_bin(p, lm, m, n, r.x, r.y, cc.range[0], cc.range[1], cc.range[2], cc.range[3]);
+                if (COUNT) cn.c[WGRT_CNT_DEPOSITS]++;
+              }
+              lost = true;
+            } else {
+              // apply the chosen order's Jones matrix (GRTF:139-144)
+              const double2* jr = reinterpret_cast<const double2*>(jones + (r.row0 + k) * JROW);
+              const double2 j0 = jr[0], j1 = jr[1], j2 = jr[2], j3 = jr[3];
+              const cplx L0{j0.x, j0.y}, L1{j1.x, j1.y}, L2{j2.x, j2.y}, L3{j3.x, j3.y};
+              cplx nte{L0.re * r.te.re - L0.im * r.te.im + (L2.re * r.tm.re - L2.im * r.tm.im),
+                       L0.re * r.te.im + L0.im * r.te.re + (L2.re * r.tm.im + L2.im * r.tm.re)};
+              cplx ntm{L1.re * r.te.re - L1.im * r.te.im + (L3.re * r.tm.re - L3.im * r.tm.im),
+                       L1.re * r.te.im + L1.im * r.te.re + (L3.re * r.tm.im + L3.im * r.tm.re)};
+              double nt2 = nte.re * nte.re + nte.im * nte.im;
+              double nm2 = ntm.re * ntm.re + ntm.im * ntm.im;
+              // E_field_cal zeroes the phase of an output amplitude below 1e-20 (GRTF:147-148); the
+              // amplitudes it sees are those of the NORMALISED input, i.e. sqrt(n?2 * s)
+              const double eps2 = 1e-40;
+              double n2 = nt2 + nm2;
+              if (fmin(nt2, nm2) * r.s < eps2 || n2 < 1e-200) {   // rare
+                if (nt2 * r.s < eps2) nte = cplx{sqrt(nt2), 0.0};
+                if (nm2 * r.s < eps2) ntm = cplx{sqrt(nm2), 0.0};
+                if (n2 < 1e-200) {   // exact rescaling by a power of two: no rounding anywhere
+                  const double k2 = 0x1p332, k4 = 0x1p664;
+                  nte.re *= k2; nte.im *= k2; ntm.re *= k2; ntm.im *= k2;
+                  n2 *= k4;
+                }
+              }
+              r.te = nte;
+              r.tm = cmul(ntm, cc.ph1[meta & 3]);         // delta += T[tir] (GRTF:878 ff.)
+              r.s = __drcp_rn(n2);
+              const int gp = (meta >> 2) & 3;
+              r.x += cc.gap[2 * gp];
+              r.y += cc.gap[2 * gp + 1];
+              r.inv_cos = row[R_INVCOS];
+              r.ener *= esel;
+              r.state = (meta >> 4) & 7;   // region state, or "pending" after an in-coupler order
+              if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
+            }
+          }
+          r.row0 = -1;
+          if (lost) {
+            st_stream(p.rng_states + t_begin + r.idx, r.rng);
+            r.state = ST_DEAD;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (COUNT) cn.flush(counters);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile size: a tile should hold whole runs.  One block measures the first run.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pick_tile_warp_kernel(const __grid_constant__ wgrt_problem_t p, int* tile_size,
+                                                              int* work_counter) {
+  __shared__ int s_run;
+  if (threadIdx.x == 0) {
+    *work_counter = 0;
+    s_run = INT_MAX;
+  }
+  if (p.tile_hint) {
+    if (threadIdx.x == 0) *tile_size = static_cast<int>(p.tile_hint);
+    return;
+  }
+  if (p.runner_points > 0) {
+    if (threadIdx.x == 0) s_run = static_cast<int>(2 * p.runner_points < (1 << 16) ? 2 * p.runner_points : (1 << 16));
+  }
+  __syncthreads();
+  const int limit = static_cast<int>(p.num_rays < (1 << 16) ? p.num_rays : (1 << 16));
+  if (p.runner_points == 0) {
+    const bool has_l = p.lmd_num != nullptr;
+    const float km = p.m[0], kn = p.n[0], kl = has_l ? p.lmd_num[0] : 0.0f;
+    for (int i = 1 + threadIdx.x; i < limit; i += blockDim.x) {
+      if (p.m[i] != km || p.n[i] != kn || (has_l && p.lmd_num[i] != kl)) {
+        atomicMin(&s_run, i);
+        break;  // later indices of this thread are larger
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int64_t run = s_run == INT_MAX ? limit : s_run;
+    // a warp walks a tile alone: whole runs when they are 2 K - 8 K rays, long runs in equal pieces
+    // of at most 8 K rays, short runs grouped up to at least 2 K rays
+    const int64_t t_min = 2048, t_max = 8192;
+    int64_t t;
+    if (run > t_max) {
+      const int64_t pieces = (run + t_max - 1) / t_max;
+      t = (run + pieces - 1) / pieces;
+    } else if (run >= t_min) {
+      t = run;
+    } else {
+      t = run * ((t_min + run - 1) / run);
+    }
+    *tile_size = static_cast<int>(t > 32 ? t : 32);
+  }
+}
+
+}  // namespace
+
+size_t walk_warp_scratch_bytes(const wgrt_problem_t& p, int num_sms) {
+  const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
+  return static_cast<size_t>(num_sms) * 32 * rows * JROW * sizeof(double);   // at most 32 single-warp CTAs per SM
+}
+
+cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
+                             unsigned long long* counters, int num_sms, double* jones_scratch, cudaStream_t s) {
+  if (p.num_rays == 0) return cudaSuccess;
+  int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
+  pick_tile_warp_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter);
+  const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
+  const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double);
+  const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
+  const bool implicit = p.runner_points > 0;
+  auto kern = count ? (implicit ? walk_warp_kernel<true, true> : walk_warp_kernel<true, false>)
+                    : (implicit ? walk_warp_kernel<false, true> : walk_warp_kernel<false, false>);
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  int per_sm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+  if (err != cudaSuccess) return err;
+  if (per_sm < 1) per_sm = 1;
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("WGRT_WARPS_PER_SM");
+    cap = e ? atoi(e) : 0;
+  }
+  if (cap > 0 && per_sm > cap) per_sm = cap;
+  const int64_t min_tiles = (p.num_rays + 31) / 32;
+  const int64_t resident = static_cast<int64_t>(num_sms) * per_sm;
+  const int grid = static_cast<int>(resident < min_tiles ? resident : (min_tiles > 1 ? min_tiles : 1));
+  kern<<<grid, 32, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch);
+  return cudaGetLastError();
+}
+
+}  // namespace wgrt

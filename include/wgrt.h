@@ -151,6 +151,15 @@ typedef struct wgrt_problem {
    * [X, Y, C] as [1, X, Y, C] and bins [Y, X, EBy, EBx] as [1, Y, X, EBy, EBx].
    */
   double threshold;
+
+  /*
+   * Index of ray 0 of this launch in the caller's numbering of the whole job.  Only the reference's
+   * zero-state rule reads a ray's index: `if s == 0: s = 0x6D2B79F5 ^ (idx + 1)`
+   * (GPU_ray_tracing_functions.py:28-29, idx = thread index of the launch).  A launch that covers
+   * rays [b, b + num_rays) of a larger job (a pipeline chunk, a multi-GPU shard) passes b here so
+   * that a zero RNG state reseeds exactly as in the single launch over the whole job.  Normally 0.
+   */
+  int64_t ray_index_base;
 } wgrt_problem_t;
 
 /* Library / runtime ------------------------------------------------------------------------ */

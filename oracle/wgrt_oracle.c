@@ -47,9 +47,10 @@ typedef struct {
 } counters_t;
 
 /* GRTF:25-34 */
-static inline double draw_uniform(uint32_t* rng_states, int64_t index, counters_t* cn) {
+static inline double draw_uniform_at(uint32_t* rng_states, int64_t index, int64_t index_base, counters_t* cn) {
   uint32_t s = rng_states[index];
-  if (s == 0u) s = 0x6D2B79F5u ^ (uint32_t)(index + 1);
+  /* GRTF:28-29; index_base = wgrt_problem_t.ray_index_base (0 for a plain launch) */
+  if (s == 0u) s = 0x6D2B79F5u ^ (uint32_t)(index_base + index + 1);
   s ^= s << 13;
   s ^= s >> 17;
   s ^= s << 5;
@@ -267,7 +268,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
   jones4(p->lut_ic1, cell, Ci, 15, 20, 35, 40, Ete, Etm, dl, &o2, cn);
   e1 = (o1.te * o1.te + o1.tm * o1.tm) * c_ic2 / c_ic1 * p->n_g;
   e2 = (o2.te * o2.te + o2.tm * o2.tm) * c_ic3 / c_ic1 * p->n_g;
-  u = draw_uniform(p->rng_states, idx, cn);
+  u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
   cn->c[WGRT_CNT_DRAW2]++;
 #define TAKE(o, e, tir, gx, gy, costh)                 \
   do {                                                 \
@@ -309,7 +310,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
       }
       e1 = (o1.te * o1.te + o1.tm * o1.tm) * c_ic2 / cos_theta;
       e2 = (o2.te * o2.te + o2.tm * o2.tm) * c_ic3 / cos_theta;
-      u = draw_uniform(p->rng_states, idx, cn);
+      u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
       cn->c[WGRT_CNT_DRAW2]++;
       if (u <= e1) {
         TAKE(o1, e1, 0, 0, 1, c_ic2);
@@ -340,7 +341,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
         e1 = (o1.te * o1.te + o1.tm * o1.tm) * c_fc1 / cos_theta;
         e2 = (o2.te * o2.te + o2.tm * o2.tm) * c_fc2 / cos_theta;
         double ener1 = ener * e1, ener2 = ener * e2;
-        u = draw_uniform(p->rng_states, idx, cn);
+        u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
         cn->c[WGRT_CNT_DRAW2]++;
         if (u <= e1 && ener1 > threshold) {
           TAKE(o1, e1, 0, 0, 1, c_fc1);
@@ -389,7 +390,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
         e2 = (o2.te * o2.te + o2.tm * o2.tm) * c_oc2 / cos_theta;
         e3 = (o3.te * o3.te + o3.tm * o3.tm) * c_ic1 / cos_theta / p->n_g;
         double ener1 = ener * e1, ener2 = ener * e2, ener3 = ener * e3;
-        u = draw_uniform(p->rng_states, idx, cn);
+        u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
         cn->c[WGRT_CNT_DRAW3]++;
         if (u <= e1 && ener1 > threshold) {
           TAKE(o1, e1, 1, 2, 3, c_oc1);
@@ -524,7 +525,7 @@ int wgrt_oracle_xorshift(uint32_t* states, int64_t n, int draws, double* out_las
   memset(&cn, 0, sizeof cn);
   for (int64_t i = 0; i < n; ++i) {
     double u = 0.0;
-    for (int d = 0; d < draws; ++d) u = draw_uniform(states, i, &cn);
+    for (int d = 0; d < draws; ++d) u = draw_uniform_at(states, i, 0, &cn);
     if (out_last) out_last[i] = u;
   }
   return WGRT_OK;

@@ -53,6 +53,9 @@ def test_grid_index_equals_literal_scan(design, oracle):
         assert np.array_equal(lit, want), f"{name}: literal GPU scan vs oracle"
         bad = np.flatnonzero(grid != want)
         assert bad.size == 0, f"{name}: grid index differs at {pts[bad[:5]]} got {grid[bad[:5]]} want {want[bad[:5]]}"
+        atlas = locate(verts, off, pts[:, 0], pts[:, 1], 2)     # the warp walk's path: atlas word, then the grids
+        bad = np.flatnonzero(atlas != want)
+        assert bad.size == 0, f"{name}: atlas differs at {pts[bad[:5]]} got {atlas[bad[:5]]} want {want[bad[:5]]}"
         assert (want >= 0).sum() > 1000 and (want < 0).sum() > 1000
 
 
@@ -68,4 +71,5 @@ def test_grid_index_odd_ring_sets(oracle):
     pts = adversarial_points(verts, rs, 100000)
     want = oracle.locate(verts, off, pts[:, 0], pts[:, 1])
     assert np.array_equal(locate(verts, off, pts[:, 0], pts[:, 1], 1), want)
+    assert np.array_equal(locate(verts, off, pts[:, 0], pts[:, 1], 2), want)
     assert set(np.unique(want)) >= {-1, 0, 2, 3}
