@@ -19,7 +19,7 @@ Printed JSON line (rank 0):
            layout (the engine derives the rays from the start points: uploads LUTs + geometry +
            points, downloads the bins); e2e_dropin is the literal 33-array call (uploads the 12
            materialised ray arrays too) and e2e_job does the runner's K launches in one call
-  roofline dominant kernel (walk_fast_kernel) against the FP64 FMA peak measured live on this GPU
+  roofline dominant kernel (walk_warp_kernel) against the FP64 FMA peak measured live on this GPU
            (the path is FP64-issue bound, not HBM bound: SURVEY.md section 8d); roofline_hbm gives
            the algorithmic-bytes view against MEASURED_PEAKS.json
   cpu_baseline   the CPU oracle port (oracle/) on the host cores, bounded sample (rank 0, N = 1)
@@ -315,12 +315,12 @@ def main():
         "bounces_per_ray": bounces_all / max(rays_all, 1),
         "deposits": deposits_total,
         "step_ms_rank0": step_ms,
-        "gpu_launches": args.steps * 7,   # per launch: geometry hash, 4 region-index kernels (no-ops when unchanged), tile pick, walk
+        "gpu_launches": args.steps * 9,   # per launch: geometry hash, 6 region-index / atlas kernels (no-ops when unchanged), tile pick, walk
         "clocks": clocks.summary(),
     }
 
     if rank == 0:
-        # ---- roofline of the dominant kernel (walk_fast_kernel) ---------------------------------
+        # ---- roofline of the dominant kernel (walk_warp_kernel) ---------------------------------
         # literal-algorithm work per launch (straddling edges / cross products only exist in the
         # literal scan): one strict launch with counters from the same RNG states
         rng_t.copy_(rng_saved)
@@ -336,7 +336,7 @@ def main():
         walk_ms = float(np.mean(step_ms))         # region-index + tile-pick kernels are < 0.1 % of it
         ach = flops_per_launch / (walk_ms * 1e-3) / 1e12
         line["roofline"] = {
-            "kernel": "walk_fast_kernel", "bound": "fp64", "achieved": ach, "peak": p64.value, "unit": "TFLOP/s",
+            "kernel": "walk_warp_kernel", "bound": "fp64", "achieved": ach, "peak": p64.value, "unit": "TFLOP/s",
             "frac": ach / p64.value, "traffic": load_traffic(),
             "peak_source": "DFMA chain micro-benchmark run live in this process (wgrt_debug_fma_peak)",
             "algorithmic_flops_per_ray": flops_per_launch / max(cs["rays"], 1),
@@ -558,9 +558,9 @@ def reference_gpu_leg(args, dev_args, host_args, rng_saved, rng_final, eb_engine
 
 
 def load_traffic():
-    """DRAM bytes per launch of walk_fast_kernel from the committed ncu --set full capture, if any."""
+    """DRAM bytes per launch of walk_warp_kernel from the committed ncu --set full capture, if any."""
     try:
-        with open(os.path.join(ROOT, "profiles", "walk_fast_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "walk_warp_traffic.json")) as f:
             return json.load(f).get("dram_bytes_per_launch")
     except OSError:
         return None

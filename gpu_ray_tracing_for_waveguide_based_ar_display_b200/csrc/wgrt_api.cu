@@ -339,12 +339,31 @@ int host_chunk_target(int64_t num_rays, int num_iter) {
   const char* e = getenv("WGRT_HOST_CHUNKS");   // read at every call: tests force odd chunkings
   const int forced = e ? atoi(e) : 0;
   if (forced > 0) return forced;
-  // enough chunks to hide the transfers of the first and last one, few enough that a chunk is
-  // still several waves of tiles (about 4 M rays per wave of resident CTAs at runner-sized cells);
-  // measured on C2 (B200): 1 chunk 33.5 ms, 4: 20.8, 8: 19.4, 16: 18.6, 25: 18.4 (num_iter = 1)
-  (void)num_iter;
+  // enough chunks to hide the transfers of the first and last one, few enough that a chunk still
+  // fills the GPU: measured on C2 (B200, warp walk, tiles as below) for num_iter = 1: 2 chunks
+  // 24.5 ms, 4: 20.8, 8: 19.6, 16: 18.9; for num_iter = 4: 4: 49.1, 8: 46.5, 16: 48.5
   const int64_t by_size = num_rays / 7000000;
-  return static_cast<int>(by_size < 1 ? 1 : (by_size > 16 ? 16 : by_size));
+  const int64_t cap = num_iter > 1 ? 8 : 16;
+  return static_cast<int>(by_size < 1 ? 1 : (by_size > cap ? cap : by_size));
+}
+
+// Work tile of a chunk launch: a chunk holds far fewer cells than the whole job, so whole-cell tiles
+// would leave most of the ~4700 resident single-warp CTAs without work.  Aim at two tiles per
+// resident warp, not below ~1000 rays (the drain at the end of a tile is paid per tile), and with
+// the runner layout cut cells into equal pieces.
+uint32_t host_chunk_tile(int64_t chunk_rays, int64_t rays_per_cell, int num_sms) {
+  if (const char* e = getenv("WGRT_HOST_TILE")) return static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 0);
+  const int64_t resident = static_cast<int64_t>(num_sms) * 32;
+  int64_t t = chunk_rays / (2 * resident);
+  if (t < 1024) t = 1024;
+  if (rays_per_cell > 0) {
+    if (t >= rays_per_cell) return 0;                       // whole cells: the automatic choice
+    const int64_t pieces = (rays_per_cell + t - 1) / t;
+    t = (rays_per_cell + pieces - 1) / pieces;
+  } else if (t > 8192) {
+    return 0;
+  }
+  return static_cast<uint32_t>(t);
 }
 
 struct HostChunk {
@@ -560,7 +579,7 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
       cp.num_rays = c.rays;
       cp.rng_states = dp.rng_states + c.ray0;
       cp.ray_index_base = hp->ray_index_base + c.ray0;
-      if (const char* e = getenv("WGRT_HOST_TILE")) if (!cp.tile_hint && atoi(e) > 0) cp.tile_hint = atoi(e);
+      if (!cp.tile_hint && K > 1) cp.tile_hint = host_chunk_tile(c.rays, runner ? 2 * hp->runner_points : 0, w->num_sms);
       if (runner) {
         cp.runner_first_cell = c.cell0;
       } else {
