@@ -126,7 +126,8 @@ def _want(b: _Buf, name: str, dtype, ndim: int):
 
 def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int = 0,
                  runner_points: int = 0, runner_first_cell: int = 0, num_rays: Optional[int] = None,
-                 single_lambda: bool = False, threshold: float = 0.0) -> Tuple[WgrtProblem, list]:
+                 single_lambda: bool = False, threshold: float = 0.0,
+                 ray_index_base: int = 0, eb: Optional[Tuple[int, int]] = None) -> Tuple[WgrtProblem, list]:
     """Validate the 33 positional kernel arguments and fill a ``wgrt_problem_t``.
 
     ``host=True`` requires NumPy arrays (used for the host entry point and by the test oracle);
@@ -152,7 +153,8 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
             bufs.append(None)
             continue
         if a is None and (i in _DEAD_ARGS or (single_lambda and i == 8) or
-                          (runner_points > 0 and (6 <= i <= 11 or (i == 12 and host)))):
+                          (runner_points > 0 and (6 <= i <= 11 or (i == 12 and host))) or
+                          (nm == "matrix_EB" and host and eb is not None)):   # wgrt_trace_evaluate_host: bins stay on the device
             bufs.append(None)
             continue
         b = _describe(a, nm)
@@ -236,8 +238,13 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     if not (chans["lut_ic1"] == chans["lut_ic2"] == chans["lut_ic3"]) or \
             chans["lut_fc1"] != chans["lut_fc2"] or chans["lut_oc1"] != chans["lut_oc2"]:
         raise ValueError("LUTs of one coupler family must have the same channel count")
-    _want(B["matrix_EB"], "matrix_EB", np.float32, 5)
-    eb = B["matrix_EB"].shape
+    if B["matrix_EB"] is None:
+        eb = (L, Y, X, int(eb[0]), int(eb[1]))
+        if eb[3] <= 0 or eb[4] <= 0:
+            raise ValueError("eb: eyebox bin counts must be positive")
+    else:
+        _want(B["matrix_EB"], "matrix_EB", np.float32, 5)
+        eb = B["matrix_EB"].shape
     if eb[:3] != (L, Y, X):
         raise ValueError(f"matrix_EB: leading shape {eb[:3]} where (L, Y, X) = {(L, Y, X)} is required")
     if n_FC > 250 or n_OC > 250:
@@ -267,10 +274,11 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     p.C_ic, p.C_fc, p.C_oc = chans["lut_ic1"], chans["lut_fc1"], chans["lut_oc1"]
     p.lut_TIR, p.lut_gap = B["lut_TIR"].ptr, B["lut_gap"].ptr
     p.L, p.X, p.Y = L, X, Y
-    p.matrix_EB, p.EBy, p.EBx = B["matrix_EB"].ptr, eb[3], eb[4]
+    p.matrix_EB, p.EBy, p.EBx = (B["matrix_EB"].ptr if B["matrix_EB"] is not None else None), eb[3], eb[4]
     p.flags = flags
     p.tile_hint = tile_hint
     p.threshold = float(threshold)
+    p.ray_index_base = int(ray_index_base)
     return p, [b.owner for b in bufs if b is not None]
 
 
@@ -300,12 +308,13 @@ class RayWalkKernel:
     """Stand-in for the Numba dispatcher of ``process_rays_kernel_pro_fullColor``."""
 
     def __init__(self, flags: int = 0, tile_hint: int = 0, runner: Optional[Tuple[int, int, int]] = None,
-                 single_lambda: bool = False, threshold: float = 0.0):
+                 single_lambda: bool = False, threshold: float = 0.0, ray_index_base: int = 0):
         self.flags = flags
         self.tile_hint = tile_hint
         self.runner = runner      # (points P, first cell, num_rays) or None
         self.single_lambda = single_lambda
         self.threshold = threshold
+        self.ray_index_base = ray_index_base   # index of ray 0 of a launch in the whole job (shards)
 
     def __getitem__(self, config) -> _Launcher:
         if not isinstance(config, tuple):
@@ -315,21 +324,23 @@ class RayWalkKernel:
         return _Launcher(self, config[2] if len(config) > 2 else None)
 
     def configured(self, *, strict: Optional[bool] = None, counters: Optional[bool] = None,
-                   tile_hint: Optional[int] = None) -> "RayWalkKernel":
-        """A copy with engine options changed (strict = literal thread-per-ray walk)."""
+                   tile_hint: Optional[int] = None, ray_index_base: Optional[int] = None) -> "RayWalkKernel":
+        """A copy with engine options changed (strict = literal thread-per-ray walk;
+        ray_index_base = position of this launch's ray 0 in the whole job, for shards)."""
         f = self.flags
         if strict is not None:
             f = (f | _capi.WGRT_FLAG_STRICT) if strict else (f & ~_capi.WGRT_FLAG_STRICT)
         if counters is not None:
             f = (f | _capi.WGRT_FLAG_COUNTERS) if counters else (f & ~_capi.WGRT_FLAG_COUNTERS)
         return RayWalkKernel(f, self.tile_hint if tile_hint is None else tile_hint, self.runner,
-                             self.single_lambda, self.threshold)
+                             self.single_lambda, self.threshold,
+                             self.ray_index_base if ray_index_base is None else int(ray_index_base))
 
     def runner_layout(self, points: int, num_rays: int, first_cell: int = 0) -> "RayWalkKernel":
         """Launch on the runner's implicit ray layout (include/wgrt.h): ``x_v`` / ``y_v`` are the
         ``points`` start points, m_v .. delta_phase_v may be ``None``."""
         return RayWalkKernel(self.flags, self.tile_hint, (int(points), int(first_cell), int(num_rays)),
-                             self.single_lambda, self.threshold)
+                             self.single_lambda, self.threshold, self.ray_index_base)
 
     def _launch(self, args, stream):
         lib = _capi.load_library()
@@ -365,7 +376,8 @@ class RayWalkKernel:
         rp, rc, rn = self.runner if self.runner else (0, 0, None)
         prob, keep = pack_problem(dev_args, host=False, flags=self.flags, tile_hint=self.tile_hint,
                                   runner_points=rp, runner_first_cell=rc, num_rays=rn,
-                                  single_lambda=self.single_lambda, threshold=self.threshold)
+                                  single_lambda=self.single_lambda, threshold=self.threshold,
+                                  ray_index_base=self.ray_index_base)
         h = _stream_handle(stream)
         if any_host:
             import torch

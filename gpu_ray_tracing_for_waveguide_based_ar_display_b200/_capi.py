@@ -59,7 +59,7 @@ _lib: Optional[C.CDLL] = None
 # every symbol include/wgrt.h declares
 EXPORTED_SYMBOLS = (
     "wgrt_version", "wgrt_problem_size", "wgrt_last_error", "wgrt_device_count", "wgrt_release",
-    "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host",
+    "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host", "wgrt_trace_evaluate_host",
     "wgrt_counters_read", "wgrt_counters_reset",
     "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
     "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host",
@@ -89,6 +89,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_trace_fullcolor.argtypes = [C.POINTER(WgrtProblem), C.c_void_p]
     lib.wgrt_trace_fullcolor_host.restype = C.c_int
     lib.wgrt_trace_fullcolor_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_void_p]
+    lib.wgrt_trace_evaluate_host.restype = C.c_int
+    lib.wgrt_trace_evaluate_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p]
     lib.wgrt_counters_read.restype = C.c_int
     lib.wgrt_counters_read.argtypes = [C.c_void_p, C.c_int]
     lib.wgrt_counters_reset.restype = C.c_int

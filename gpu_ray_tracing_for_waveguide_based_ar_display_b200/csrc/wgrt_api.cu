@@ -176,7 +176,7 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
   return WGRT_OK;
 }
 
-int validate(const wgrt_problem_t* p) {
+int validate(const wgrt_problem_t* p, bool need_bins = true) {
   if (!p) return fail(WGRT_ERR_INVALID, "null problem");
   if (p->num_rays < 0) return fail(WGRT_ERR_INVALID, "num_rays < 0");
   if (!(p->threshold >= 0.0)) return fail(WGRT_ERR_INVALID, "threshold must be >= 0");
@@ -203,7 +203,8 @@ int validate(const wgrt_problem_t* p) {
   }
   NEED(IC); NEED(FC); NEED(FC_offset); NEED(OC); NEED(OC_offset); NEED(eff_reg1); NEED(eff_reg2);
   NEED(eff_reg_FOV); NEED(eff_reg_FOV_range); NEED(lut_ic1); NEED(lut_ic2); NEED(lut_ic3); NEED(lut_fc1);
-  NEED(lut_fc2); NEED(lut_oc1); NEED(lut_oc2); NEED(lut_TIR); NEED(lut_gap); NEED(matrix_EB);
+  NEED(lut_fc2); NEED(lut_oc1); NEED(lut_oc2); NEED(lut_TIR); NEED(lut_gap);
+  if (need_bins) NEED(matrix_EB);
 #undef NEED
   return WGRT_OK;
 }
@@ -366,6 +367,14 @@ uint32_t host_chunk_tile(int64_t chunk_rays, int64_t rays_per_cell, int num_sms)
   return static_cast<uint32_t>(t);
 }
 
+// Optional evaluation stage of the host entry (wgrt_trace_evaluate_host): the bins stay on the device,
+// the pupil sums / per-cell totals (row f1) are reduced there and only those come down.
+struct EvalSpec {
+  int mask_size, step_y, step_x;
+  float* perceive;    // host [L, Y, X, n_epy, n_epx] or NULL
+  float* cell_sums;   // host [L, Y, X] or NULL
+};
+
 struct HostChunk {
   int64_t ray0 = 0, rays = 0;        // launch-relative ray range walked by this chunk
   int64_t cell0 = 0;                 // runner layout: first cell of the chunk (global cell index)
@@ -375,9 +384,27 @@ struct HostChunk {
 
 }  // namespace
 
+namespace {
+int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, const EvalSpec* ev);
+}
+
 extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter, float* timings_ms) {
+  return trace_host_impl(hp, num_iter, timings_ms, nullptr);
+}
+
+extern "C" int wgrt_trace_evaluate_host(const wgrt_problem_t* hp, int num_iter, int mask_size, int step_y, int step_x,
+                                        float* perceive, float* cell_sums, float* timings_ms) {
+  if (mask_size <= 0 || step_y <= 0 || step_x <= 0) return fail(WGRT_ERR_INVALID, "bad pupil mask / steps");
+  if (hp && static_cast<size_t>(hp->EBy * hp->EBx) * 4 > 200 * 1024)
+    return fail(WGRT_ERR_UNSUPPORTED, "eyebox tile larger than 200 KB of shared memory");
+  const EvalSpec ev{mask_size, step_y, step_x, perceive, cell_sums};
+  return trace_host_impl(hp, num_iter, timings_ms, &ev);
+}
+
+namespace {
+int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, const EvalSpec* ev) {
   std::lock_guard<std::mutex> lk(g_mu);
-  int rc = validate(hp);
+  int rc = validate(hp, ev == nullptr);
   if (rc != WGRT_OK) return rc;
   if (num_iter < 0) return fail(WGRT_ERR_INVALID, "num_iter < 0");
   for (int s = 0; s < 2; ++s) {
@@ -398,7 +425,9 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
   const size_t eb_b = cells * tile_b;
   const bool runner = hp->runner_points > 0;
   const bool seed_rng = runner && hp->rng_states == nullptr;
-  const bool zero_bins = (hp->flags & WGRT_FLAG_BINS_ZERO) != 0;
+  // with an evaluation stage and no host bin array the bins live and die on the device
+  const bool bins_to_host = hp->matrix_EB != nullptr;
+  const bool zero_bins = (hp->flags & WGRT_FLAG_BINS_ZERO) != 0 || !bins_to_host;
   if (!runner && N && !hp->rng_states) return fail(WGRT_ERR_INVALID, "null pointer: rng_states");
 
   // ---- device staging: full-shape copies of every array (arena, grow-only) --------------------
@@ -441,6 +470,15 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
       {hp->matrix_EB, (void**)&dp.matrix_EB, eb_b, !zero_bins && !runner},
   };
   items.insert(items.end(), shared_items.begin(), shared_items.end());
+  float *d_perceive = nullptr, *d_cells = nullptr;
+  size_t perceive_b = 0;
+  if (ev) {
+    const size_t n_epy = hp->EBy >= ev->mask_size ? static_cast<size_t>((hp->EBy - ev->mask_size) / ev->step_y + 1) : 0;
+    const size_t n_epx = hp->EBx >= ev->mask_size ? static_cast<size_t>((hp->EBx - ev->mask_size) / ev->step_x + 1) : 0;
+    perceive_b = cells * n_epy * n_epx * 4;
+    items.push_back({nullptr, (void**)&d_perceive, perceive_b, false});
+    items.push_back({nullptr, (void**)&d_cells, cells * 4, false});
+  }
   size_t total = 0;
   for (auto& it : items) total += padded(it.bytes);
   CUDA_TRY(w->arena.reserve(total));
@@ -600,13 +638,20 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
     if (k == 0) CUDA_TRY(cudaEventRecord(span[4], s_out));
     if (c.rays && hp->rng_states)
       CUDA_TRY(cudaMemcpyAsync(hp->rng_states + c.ray0, dp.rng_states + c.ray0, static_cast<size_t>(c.rays) * 4, D2H, s_out));
-    if (runner) {
+    if (runner && bins_to_host) {
       const size_t o0 = static_cast<size_t>(c.out_m0), ocols = static_cast<size_t>(c.out_m1 - c.out_m0);
       CUDA_TRY(copy2d({(char*)hp->matrix_EB + o0 * tile_b, (const char*)dp.matrix_EB + o0 * tile_b, X * tile_b, X * tile_b,
                        ocols * tile_b, L * Y}, D2H, s_out));
-    } else if (k == K - 1) {
+    } else if (k == K - 1 && bins_to_host) {
       CUDA_TRY(cudaMemcpyAsync(hp->matrix_EB, dp.matrix_EB, eb_b, D2H, s_out));
     }
+  }
+  if (ev && cells) {
+    // the D2H stream has waited for every chunk's walk: reduce the finished bins where they are
+    CUDA_TRY(launch_pupil_sums(dp.matrix_EB, hp->L, hp->Y, hp->X, hp->EBy, hp->EBx, ev->mask_size, ev->step_y, ev->step_x,
+                               d_perceive, d_cells, s_out));
+    if (ev->perceive && perceive_b) CUDA_TRY(cudaMemcpyAsync(ev->perceive, d_perceive, perceive_b, D2H, s_out));
+    if (ev->cell_sums) CUDA_TRY(cudaMemcpyAsync(ev->cell_sums, d_cells, cells * 4, D2H, s_out));
   }
   CUDA_TRY(cudaEventRecord(span[5], s_out));
   // end of the walk stage: the later of the two walk streams (the D2H stream waited for both)
@@ -621,6 +666,7 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
     for (int k = 0; k < 3; ++k) CUDA_TRY(cudaEventElapsedTime(&timings_ms[k], span[2 * k], span[2 * k + 1]));
   return WGRT_OK;
 }
+}  // namespace
 
 extern "C" {
 

@@ -63,7 +63,9 @@ def run_partitioned(scene: si.Scene, points: np.ndarray, trace: Callable, num_it
     """Trace this rank's share of ``scene`` for ``num_iter`` launches and all-reduce the bins.
 
     ``trace(*args33)`` is the launch callable (e.g. ``kernel[grid, block]``); it must mutate
-    ``rng_states`` and ``matrix_EB`` in place like the reference kernel.  Returns
+    ``rng_states`` and ``matrix_EB`` in place like the reference kernel.  A ``RayWalkKernel`` may be
+    passed instead: it is then launched with ``ray_index_base`` = this rank's first ray, so that even a
+    zero RNG state reseeds (GRTF:28-29) as in the single launch over the whole job.  Returns
     ``(matrix_EB, rng_states, (first_ray, last_ray))`` -- bins summed over all ranks, and this
     rank's slice of the global RNG state array.
     """
@@ -75,6 +77,8 @@ def run_partitioned(scene: si.Scene, points: np.ndarray, trace: Callable, num_it
     m = scene.meta
     L = scene.eb_shape[0]
     rays, span = shard_rays(points, m["num_FOV_x"], m["num_FOV_y"], L, m["num_rays_per_FoV"], world_size, rank)
+    if hasattr(trace, "configured"):
+        trace = trace.configured(ray_index_base=span[0])[(rays.num_rays + 255) // 256, 256]
     full = scene.rays
     scene.rays = rays
     try:

@@ -17,7 +17,7 @@ import numpy as np
 from . import _capi
 from .GPU_ray_tracing_functions import pack_problem
 
-__all__ = ["trace_full_color"]
+__all__ = ["trace_full_color", "trace_and_evaluate"]
 
 
 def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float, luts: Dict[str, np.ndarray],
@@ -59,11 +59,63 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
             geom["eff_reg1"], geom["eff_reg2"], geom["eff_reg_FOV"], geom["eff_reg_FOV_range"],
             luts["lut_ic1"], luts["lut_ic2"], luts["lut_ic3"], luts["lut_fc1"], luts["lut_fc2"],
             luts["lut_oc1"], luts["lut_oc2"], geom["lut_TIR"], geom["lut_gap"], matrix_EB)
+    # ray 0 of this call is ray first_cell * num_rays_per_FoV of the runner's whole job (only the
+    # reference's zero-state reseed rule, GRTF:28-29, reads a ray's index)
     prob, keep = pack_problem(args, host=True, flags=flags, runner_points=P, runner_first_cell=first_cell,
-                              num_rays=N)
+                              num_rays=N, ray_index_base=first_cell * num_rays_per_FoV)
     tms = (C.c_float * 3)()
     _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), int(num_iter), tms), lib)
     if timings is not None:
         timings[:] = list(tms)
     del keep
     return matrix_EB
+
+
+def trace_and_evaluate(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float, luts: Dict[str, np.ndarray],
+                       num_rays_per_FoV: int, num_iter: int = 4, eb: Tuple[int, int] = (80, 120),
+                       mask_size: int = 30, step_y: int = 8, step_x: int = 12, flags: int = 0,
+                       timings: Optional[list] = None, full_evaluation: bool = True) -> dict:
+    """The runner from its inputs to its evaluation (gpu_ray_tracing_pro_fullColor.py:59-198) with the
+    bin tensor never leaving the device.
+
+    Walks ``num_iter`` launches over the runner's ray layout, reduces the pupil-mask sums
+    (AR_system_evaluation_functions.py:68-109) and the per-cell totals (RUN:186) on the device and
+    downloads only those (a few MB instead of 864 MB at the default size), then finishes the
+    reference's ``evaluation()`` on the host.  Returns a dict with ``efficiency`` (RUN:186-192, per
+    wavelength), ``matrix_eye_perceive`` (normalised as RUN:197 does) and, with ``full_evaluation``,
+    ``delta_e``, ``U_fov``, ``U_EB``, ``output_image`` as the reference's ``evaluation()`` returns them.
+    """
+    from . import AR_system_evaluation_functions as EV
+    lib = _capi.load_library()
+    P = num_rays_per_FoV // 2
+    if points.shape != (P, 2) or 2 * P != num_rays_per_FoV:
+        raise ValueError("points must be [num_rays_per_FoV/2, 2]")
+    L, X, Y, _ = geom["lut_TIR"].shape
+    N = L * X * Y * num_rays_per_FoV
+    px = np.ascontiguousarray(points[:, 0], dtype=np.float32)
+    py = np.ascontiguousarray(points[:, 1], dtype=np.float32)
+    n_epy = (eb[0] - mask_size) // step_y + 1 if eb[0] >= mask_size else 0
+    n_epx = (eb[1] - mask_size) // step_x + 1 if eb[1] >= mask_size else 0
+    perceive = np.zeros((L, Y, X, n_epy, n_epx), dtype=np.float32)
+    cells = np.zeros((L, Y, X), dtype=np.float32)
+    args = (px, py, None, None, None, None, None, None, None, None, None, None, None,
+            geom["IC"], geom["FC"], geom["FC_offset"], geom["OC"], geom["OC_offset"], float(n_g),
+            geom["eff_reg1"], geom["eff_reg2"], geom["eff_reg_FOV"], geom["eff_reg_FOV_range"],
+            luts["lut_ic1"], luts["lut_ic2"], luts["lut_ic3"], luts["lut_fc1"], luts["lut_fc2"],
+            luts["lut_oc1"], luts["lut_oc2"], geom["lut_TIR"], geom["lut_gap"], None)
+    prob, keep = pack_problem(args, host=True, flags=flags, runner_points=P, runner_first_cell=0, num_rays=N, eb=eb)
+    tms = (C.c_float * 3)()
+    _capi.check(lib.wgrt_trace_evaluate_host(C.byref(prob), int(num_iter), mask_size, step_y, step_x,
+                                             perceive.ctypes.data, cells.ctypes.data, tms), lib)
+    if timings is not None:
+        timings[:] = list(tms)
+    del keep
+    # RUN:186-192 with num_rays = all rays of one launch
+    out = {"efficiency": cells.astype(np.float64).sum(axis=(1, 2)) / N / num_iter * 3,
+           "cell_sums": cells,
+           "matrix_eye_perceive": perceive / np.float32(num_rays_per_FoV) / np.float32(num_iter)}   # RUN:197 is linear
+    if full_evaluation:
+        shape_only = np.broadcast_to(np.float32(0), (L, Y, X, eb[0], eb[1]))
+        out["delta_e"], out["U_fov"], out["U_EB"], out["output_image"] = EV.evaluation(
+            shape_only, matrix_eye_perceive=out["matrix_eye_perceive"])
+    return out

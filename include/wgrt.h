@@ -199,6 +199,19 @@ int wgrt_trace_fullcolor(const wgrt_problem_t* dev_problem, void* stream);
  */
 int wgrt_trace_fullcolor_host(const wgrt_problem_t* host_problem, int num_iter, float* timings_ms);
 
+/*
+ * wgrt_trace_fullcolor_host followed, on the device, by the evaluation reductions of
+ * wgrt_eval_pupil_sums (below) -- the runner's region gpu_ray_tracing_pro_fullColor.py:145-198 up to
+ * the pupil-mask sums (AR_system_evaluation_functions.py:68-109) and per-cell totals (RUN:186) in one
+ * call.  `perceive` [L, Y, X, n_epy, n_epx] and `cell_sums` [L, Y, X] are HOST float32 arrays (either
+ * may be NULL) and hold sums of the RAW counts (the reference divides the bins by num_rays_per_FoV *
+ * num_iter first, RUN:197; the sums are linear).  host_problem->matrix_EB may be NULL: the bins then
+ * start at zero, never leave the device, and only the reductions (a few MB instead of the 864 MB
+ * bin tensor at the default size) come back.
+ */
+int wgrt_trace_evaluate_host(const wgrt_problem_t* host_problem, int num_iter, int mask_size, int step_y,
+                             int step_x, float* perceive, float* cell_sums, float* timings_ms);
+
 /* Counters accumulated by launches that carried WGRT_FLAG_COUNTERS (device-wide, since reset). */
 int wgrt_counters_read(uint64_t* out, int n);
 int wgrt_counters_reset(void);

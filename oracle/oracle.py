@@ -51,12 +51,13 @@ def lib() -> C.CDLL:
 
 
 def trace(*args, first: int = 0, count: Optional[int] = None, num_threads: int = 0,
-          counters: bool = False, single_lambda: bool = False, threshold: float = 0.0):
+          counters: bool = False, single_lambda: bool = False, threshold: float = 0.0, ray_index_base: int = 0):
     """Same 33 positional arguments as the reference kernel, all host NumPy arrays
     (32 with ``single_lambda=True``: the argument list of ``process_rays_kernel_pro``)."""
     if single_lambda:
         args = tuple(args[:8]) + (None,) + tuple(args[8:])
-    prob, keep = pack_problem(args, host=True, single_lambda=single_lambda, threshold=threshold)
+    prob, keep = pack_problem(args, host=True, single_lambda=single_lambda, threshold=threshold,
+                              ray_index_base=ray_index_base)
     n = prob.num_rays if count is None else count
     cnt = np.zeros(WGRT_NUM_COUNTERS, dtype=np.uint64)
     nt = num_threads or (os.cpu_count() or 1)

@@ -80,3 +80,26 @@ def test_pupil_sums_other_shapes():
                 want = (EB[..., iy * sy:iy * sy + mask, ix * sx:ix * sx + mask] * disc).sum(axis=(-1, -2))
                 assert np.array_equal(out[..., iy, ix], want)
         assert np.array_equal(cells, EB.sum(axis=(-1, -2)))
+
+
+@pytest.mark.gpu
+def test_trace_and_evaluate_keeps_bins_on_the_device():
+    """runner.trace_and_evaluate == runner.trace_full_color followed by the evaluation mirror, with the
+    pupil sums / cell totals bit-equal (same kernel, same bins) and the maps within 1e-5."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner, synthetic_inputs as si
+    rpc, it = 400, 2
+    scene = si.make_scene(6, 5, 2, seed=21, eff=dict(incouple=0.9, ic_zero=0.95, fc_zero=0.8, fc_turn=0.15, outcouple=0.2))
+    pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 22)
+    EB = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=it)
+    assert EB.sum() > 1000
+    want_p, want_c = EV.pupil_sums(EB)
+    got = runner.trace_and_evaluate(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=it)
+    assert np.array_equal(got["cell_sums"], want_c)
+    assert np.array_equal(got["matrix_eye_perceive"] * np.float32(rpc) * np.float32(it), want_p) or \
+        np.allclose(got["matrix_eye_perceive"], want_p / rpc / it, rtol=1e-6, atol=0)
+    d_e, U_fov, U_EB, img = EV.evaluation(EB / np.float32(rpc) / np.float32(it))
+    assert got["U_fov"] == pytest.approx(U_fov, rel=1e-5) and got["U_EB"] == pytest.approx(U_EB, rel=1e-5)
+    assert got["delta_e"] == pytest.approx(d_e, rel=1e-5)
+    np.testing.assert_allclose(got["output_image"], img, rtol=1e-5, atol=1e-6)
+    eff = EV.efficiency_per_colour(EB, scene.eb_shape[0] * 6 * 5 * rpc, it)
+    np.testing.assert_allclose(got["efficiency"], eff, rtol=1e-12)

@@ -275,6 +275,22 @@ def test_host_pipeline_chunking_is_invisible(chunks, oracle, monkeypatch):
     lib = _capi.load_library()
     _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 2, None), lib)
     assert np.array_equal(EB, base + want[0]) and np.array_equal(rng, want[1])
+    # (e) zero RNG states reseed from the ray's index in the WHOLE job (GRTF:28-29), whatever chunk or
+    #     shard the ray ends up in
+    zeros = np.arange(7, scene.rays.num_rays, 131)
+    rng0 = scene.rays.rng_states.copy(); rng0[zeros] = 0
+    EB_o = scene.new_matrix_EB(); rng_o = rng0.copy()
+    oracle.trace(*scene.kernel_args(EB_o, rng_o))
+    EB = scene.new_matrix_EB(); rng = rng0.copy()
+    prob, keep = GRTF.pack_problem(scene.kernel_args(EB, rng), host=True)
+    _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), 1, None), lib)
+    assert np.array_equal(rng, rng_o) and np.array_equal(EB, EB_o)
+    lo, hi = 17 * rpc, 83 * rpc                      # a shard launched on its own
+    scene.rays = full.take(slice(lo, hi))
+    EB = scene.new_matrix_EB(); rng = rng0[lo:hi].copy()
+    KERNEL.configured(ray_index_base=lo)[1, 256](*scene.kernel_args(EB, rng))
+    scene.rays = full
+    assert np.array_equal(rng, rng_o[lo:hi])
 
 
 # ---------------------------------------------------------------------------- single-wavelength twin (row f3)
