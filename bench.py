@@ -50,6 +50,9 @@ WORKLOADS = {
     # name: (num_FOV_x, num_FOV_y, rays_per_FoV, (EBy, EBx))
     "c2_default_fullcolor_100x75x3x5000": (100, 75, 5000, (80, 120)),
     "small_20x15x3x2000": (20, 15, 2000, (80, 120)),
+    # BASELINE.json configs[2]: dense FoV sweep, PARTITIONED over the ranks (strong scaling): contiguous
+    # cell ranges per rank, one NCCL all-reduce of the bins, result checked against the 1-GPU job
+    "c3_dense_fov_41x41x3x10000": (41, 41, 10000, (80, 120)),
 }
 
 
@@ -210,11 +213,118 @@ def reference_arm(args, nx, ny, rpc, eb):
 
 
 # ------------------------------------------------------------------------------------------------
+def partitioned_arm(args, nx, ny, rpc, eb):
+    """Strong scaling on BASELINE.json configs[2]: the job's FoV-wavelength cells are split into contiguous
+    ranges (multi_gpu.cell_range), every rank walks its range device resident with the runner layout and
+    the GLOBAL RNG seeds (RUN:158) for K launches, then one NCCL all-reduce sums the bins.  Rank 0 checks
+    the reduced bins against the same job walked on its GPU alone: they must be bit-equal."""
+    import torch
+    import torch.distributed as dist
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, multi_gpu, synthetic_inputs as si
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _capi.load_library()
+    scene = si.make_scene(nx, ny, 2, eb=eb, seed=2024)             # tables; the rays are implicit
+    pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2025)
+    L = scene.eb_shape[0]
+    n_cells = nx * ny * L
+    c0, c1 = multi_gpu.cell_range(n_cells, world, rank)
+    stream = torch.cuda.current_stream()
+
+    def to_dev(a):
+        v = a.view(np.float64) if a.dtype == np.complex128 else a
+        t = torch.from_numpy(np.ascontiguousarray(v.view(np.int32) if v.dtype == np.uint32 else v)).cuda()
+        return GRTF._TorchAlias(t, a.shape, a.dtype)
+
+    g = {k: to_dev(v) for k, v in scene.geom.items()}
+    lt = {k: to_dev(v) for k, v in scene.luts.items()}
+    d_px, d_py = to_dev(pts[:, 0].astype(np.float32)), to_dev(pts[:, 1].astype(np.float32))
+
+    def job(first_cell, cells, counters=False):
+        n = cells * rpc
+        rng = to_dev(si.initial_rng_states(n, offset=first_cell * rpc))
+        ebt = to_dev(scene.new_matrix_EB())
+        k = GRTF.process_rays_kernel_pro_fullColor.configured(counters=counters, ray_index_base=first_cell * rpc)
+        k = k.runner_layout(rpc // 2, n, first_cell)
+        a = [d_px, d_py] + [None] * 10 + [rng, g["IC"], g["FC"], g["FC_offset"], g["OC"], g["OC_offset"], scene.n_g,
+                                           g["eff_reg1"], g["eff_reg2"], g["eff_reg_FOV"], g["eff_reg_FOV_range"],
+                                           lt["lut_ic1"], lt["lut_ic2"], lt["lut_ic3"], lt["lut_fc1"], lt["lut_fc2"],
+                                           lt["lut_oc1"], lt["lut_oc2"], g["lut_TIR"], g["lut_gap"], ebt]
+        return k[1, 256, stream], a, rng, ebt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launch, a, rng, ebt = job(c0, c1 - c0)
+    rng0 = rng._t.clone()
+    for _ in range(max(args.warmup, 3)):
+        launch(*a)
+    if world > 1:
+        dist.all_reduce(ebt._t)                                   # NCCL warm-up
+    torch.cuda.synchronize()
+    rng._t.copy_(rng0); ebt._t.zero_()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            launch(*a)
+        if world > 1:
+            dist.all_reduce(ebt._t)
+        ev1.record(stream)
+        barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    # bounces of the timed launches: replay with counters
+    claunch, ca, crng, cebt = job(c0, c1 - c0, counters=True)
+    _capi.reset_counters()
+    for _ in range(args.steps):
+        claunch(*ca)
+    cnt = _capi.read_counters()
+    bt = torch.tensor([cnt["bounces"], cnt["rays"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(bt)
+    del crng, cebt
+    same = None
+    if rank == 0:
+        flaunch, fa, frng, febt = job(0, n_cells)
+        for _ in range(args.steps):
+            flaunch(*fa)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(febt._t, ebt._t))
+        line = {"metric": METRIC, "value": float(bt[0].item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / max(args.steps, 1),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "num_FOV_x": nx, "num_FOV_y": ny, "wavelengths": L,
+                           "rays_per_FoV": rpc, "rays_per_launch_all_gpus": n_cells * rpc, "eyebox_bins": list(eb),
+                           "partition": f"contiguous FoV-wavelength cell ranges, {n_cells} cells over {world} ranks, "
+                                        "global RNG seeds, one NCCL all-reduce of the bins inside the timed region",
+                           "l2_policy": "runner layout: per-launch inputs are the RNG states (2 GB over all ranks) > L2"},
+                "rays_per_s": float(bt[1].item()) / (ms * 1e-3), "full_colour_wall_ms": ms,
+                "deposits": float(ebt._t.sum(dtype=torch.float64).item()),
+                "reduced_bins_bit_equal_to_single_gpu_job": same,
+                "gpu_launches": args.steps * 9, "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     nx, ny, rpc, eb = WORKLOADS[args.workload]
     if args.impl == "reference":
         reference_arm(args, nx, ny, rpc, eb)
+        return
+    if args.workload.startswith("c3_"):
+        partitioned_arm(args, nx, ny, rpc, eb)
         return
 
     import torch

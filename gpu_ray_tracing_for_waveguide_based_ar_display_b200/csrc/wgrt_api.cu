@@ -348,23 +348,11 @@ int host_chunk_target(int64_t num_rays, int num_iter) {
   return static_cast<int>(by_size < 1 ? 1 : (by_size > cap ? cap : by_size));
 }
 
-// Work tile of a chunk launch: a chunk holds far fewer cells than the whole job, so whole-cell tiles
-// would leave most of the ~4700 resident single-warp CTAs without work.  Aim at two tiles per
-// resident warp, not below ~1000 rays (the drain at the end of a tile is paid per tile), and with
-// the runner layout cut cells into equal pieces.
-uint32_t host_chunk_tile(int64_t chunk_rays, int64_t rays_per_cell, int num_sms) {
-  if (const char* e = getenv("WGRT_HOST_TILE")) return static_cast<uint32_t>(atoi(e) > 0 ? atoi(e) : 0);
-  const int64_t resident = static_cast<int64_t>(num_sms) * 32;
-  int64_t t = chunk_rays / (2 * resident);
-  if (t < 1024) t = 1024;
-  if (rays_per_cell > 0) {
-    if (t >= rays_per_cell) return 0;                       // whole cells: the automatic choice
-    const int64_t pieces = (rays_per_cell + t - 1) / t;
-    t = (rays_per_cell + pieces - 1) / pieces;
-  } else if (t > 8192) {
-    return 0;
-  }
-  return static_cast<uint32_t>(t);
+// Work tile of a chunk launch: chosen by the walk itself from the launch size (launch_walk_warp);
+// WGRT_HOST_TILE=<rays> overrides it for experiments.
+uint32_t host_chunk_tile() {
+  const char* e = getenv("WGRT_HOST_TILE");
+  return static_cast<uint32_t>(e && atoi(e) > 0 ? atoi(e) : 0);
 }
 
 // Optional evaluation stage of the host entry (wgrt_trace_evaluate_host): the bins stay on the device,
@@ -617,7 +605,7 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
       cp.num_rays = c.rays;
       cp.rng_states = dp.rng_states + c.ray0;
       cp.ray_index_base = hp->ray_index_base + c.ray0;
-      if (!cp.tile_hint && K > 1) cp.tile_hint = host_chunk_tile(c.rays, runner ? 2 * hp->runner_points : 0, w->num_sms);
+      if (!cp.tile_hint && K > 1) cp.tile_hint = host_chunk_tile();
       if (runner) {
         cp.runner_first_cell = c.cell0;
       } else {

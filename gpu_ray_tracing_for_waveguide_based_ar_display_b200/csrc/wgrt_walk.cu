@@ -609,7 +609,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
 // tile size: a tile should hold whole runs.  One block measures the first run.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) pick_tile_warp_kernel(const __grid_constant__ wgrt_problem_t p, int* tile_size,
-                                                              int* work_counter) {
+                                                              int* work_counter, int tile_cap) {
   __shared__ int s_run;
   if (threadIdx.x == 0) {
     *work_counter = 0;
@@ -637,9 +637,12 @@ __global__ void __launch_bounds__(1024) pick_tile_warp_kernel(const __grid_const
   __syncthreads();
   if (threadIdx.x == 0) {
     const int64_t run = s_run == INT_MAX ? limit : s_run;
-    // a warp walks a tile alone: whole runs when they are 2 K - 8 K rays, long runs in equal pieces
-    // of at most 8 K rays, short runs grouped up to at least 2 K rays
-    const int64_t t_min = 2048, t_max = 8192;
+    // a warp walks a tile alone.  Whole runs when they fit; long runs in equal pieces; short runs
+    // grouped.  `tile_cap` = rays of the launch / (4 x resident warps): small launches (pipeline
+    // chunks, multi-GPU shards) cut their cells into pieces so that every resident warp gets several
+    // tiles, but never below ~1250 rays (the drain at the end of a tile is paid per tile)
+    const int64_t t_max = tile_cap < 1250 ? 1250 : (tile_cap > 8192 ? 8192 : tile_cap);
+    const int64_t t_min = t_max / 2;
     int64_t t;
     if (run > t_max) {
       const int64_t pieces = (run + t_max - 1) / t_max;
@@ -664,7 +667,6 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
                              unsigned long long* counters, int num_sms, double* jones_scratch, cudaStream_t s) {
   if (p.num_rays == 0) return cudaSuccess;
   int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
-  pick_tile_warp_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter);
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
@@ -686,6 +688,8 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const int64_t min_tiles = (p.num_rays + 31) / 32;
   const int64_t resident = static_cast<int64_t>(num_sms) * per_sm;
   const int grid = static_cast<int>(resident < min_tiles ? resident : (min_tiles > 1 ? min_tiles : 1));
+  const int64_t tcap = p.num_rays / (4 * resident);
+  pick_tile_warp_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter, static_cast<int>(tcap > (1 << 20) ? (1 << 20) : tcap));
   kern<<<grid, 32, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch);
   return cudaGetLastError();
 }
