@@ -46,8 +46,10 @@ constexpr int R_INVCOS = 4;        // 1 / cos(theta_new)
 constexpr int R_META = 5;          // bit field, see below
 constexpr int JROW = 8;            // doubles per Jones row in the scratch
 constexpr int ST_DEAD = -1, ST_PEND_FWD = 6, ST_PEND_BACK = 7;
+// Resident single-warp CTAs per SM the kernel is compiled for.  Measured on C2: 32 (64 registers, a few
+// spills) 11.14 ms, 28 (72 registers, no spills) 10.8 ms, 24 (80 registers) 11.1 ms.
 #ifndef WGRT_WARP_CTAS_PER_SM
-#define WGRT_WARP_CTAS_PER_SM 32
+#define WGRT_WARP_CTAS_PER_SM 28
 #endif
 enum { POST_NONE = 0, POST_IC_FWD = 1, POST_IC_BACK = 2, POST_DEPOSIT = 3 };
 enum { EV_INIT = 0, EV_S0, EV_S1, EV_S2, EV_S3, EV_S4, EV_S5, NUM_EV };
