@@ -127,7 +127,8 @@ def _want(b: _Buf, name: str, dtype, ndim: int):
 def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int = 0,
                  runner_points: int = 0, runner_first_cell: int = 0, num_rays: Optional[int] = None,
                  single_lambda: bool = False, threshold: float = 0.0,
-                 ray_index_base: int = 0, eb: Optional[Tuple[int, int]] = None) -> Tuple[WgrtProblem, list]:
+                 ray_index_base: int = 0, eb: Optional[Tuple[int, int]] = None,
+                 rng_seed_offset: int = 0) -> Tuple[WgrtProblem, list]:
     """Validate the 33 positional kernel arguments and fill a ``wgrt_problem_t``.
 
     ``host=True`` requires NumPy arrays (used for the host entry point and by the test oracle);
@@ -158,6 +159,9 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
             bufs.append(None)
             continue
         b = _describe(a, nm)
+        if nm == "matrix_EB" and host and not b.is_host and (flags & _capi.WGRT_FLAG_BINS_DEVICE):
+            bufs.append(b)          # host entry accumulating into the caller's device tensor
+            continue
         if b.is_host != host:
             raise TypeError(f"{nm}: expected a {'host' if host else 'device'} buffer")
         bufs.append(b)
@@ -279,6 +283,7 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     p.tile_hint = tile_hint
     p.threshold = float(threshold)
     p.ray_index_base = int(ray_index_base)
+    p.rng_seed_offset = int(rng_seed_offset)
     return p, [b.owner for b in bufs if b is not None]
 
 

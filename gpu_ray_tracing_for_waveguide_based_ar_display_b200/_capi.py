@@ -17,6 +17,7 @@ WGRT_OK = 0
 WGRT_FLAG_STRICT = 0x1
 WGRT_FLAG_COUNTERS = 0x2
 WGRT_FLAG_BINS_ZERO = 0x4
+WGRT_FLAG_BINS_DEVICE = 0x8
 WGRT_NUM_COUNTERS = 16
 COUNTER_NAMES = ("rays", "bounces", "draws", "draw2", "draw3", "efield", "iters", "deposits",
                  "poly_tests", "edge_visits", "straddle", "cross", "exact_fallback", "warp_steps", "warp_batches")
@@ -46,7 +47,7 @@ class WgrtProblem(C.Structure):
         ("matrix_EB", C.c_void_p), ("EBy", C.c_int64), ("EBx", C.c_int64),
         ("flags", C.c_uint32), ("tile_hint", C.c_uint32),
         ("runner_points", C.c_int64), ("runner_first_cell", C.c_int64),
-        ("threshold", C.c_double), ("ray_index_base", C.c_int64),
+        ("threshold", C.c_double), ("ray_index_base", C.c_int64), ("rng_seed_offset", C.c_int64),
     ]
 
 

@@ -414,15 +414,17 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
   const bool runner = hp->runner_points > 0;
   const bool seed_rng = runner && hp->rng_states == nullptr;
   // with an evaluation stage and no host bin array the bins live and die on the device
-  const bool bins_to_host = hp->matrix_EB != nullptr;
-  const bool zero_bins = (hp->flags & WGRT_FLAG_BINS_ZERO) != 0 || !bins_to_host;
+  const bool bins_on_device = (hp->flags & WGRT_FLAG_BINS_DEVICE) != 0;   // caller's device tensor, used in place
+  if (bins_on_device && !hp->matrix_EB) return fail(WGRT_ERR_INVALID, "WGRT_FLAG_BINS_DEVICE needs matrix_EB");
+  const bool bins_to_host = hp->matrix_EB != nullptr && !bins_on_device;
+  const bool zero_bins = (hp->flags & WGRT_FLAG_BINS_ZERO) != 0 || (!bins_to_host && !bins_on_device);
   if (!runner && N && !hp->rng_states) return fail(WGRT_ERR_INVALID, "null pointer: rng_states");
 
   // ---- device staging: full-shape copies of every array (arena, grow-only) --------------------
   struct Item { const void* src; void** dst; size_t bytes; bool upfront; };
   wgrt_problem_t dp = *hp;
   dp.gap_x = dp.gap_y = dp.pol = dp.azi = nullptr;  // never read by the walk
-  dp.flags &= ~WGRT_FLAG_BINS_ZERO;
+  dp.flags &= ~(WGRT_FLAG_BINS_ZERO | WGRT_FLAG_BINS_DEVICE);
   const size_t ray_b = N * 4, pts_b = static_cast<size_t>(hp->runner_points) * 4;
   const size_t ic_b = fov * hp->C_ic * 16, fc_b = fov * hp->C_fc * 16, oc_b = fov * hp->C_oc * 16;  // per wavelength (and slice)
   std::vector<Item> items;
@@ -455,7 +457,7 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
       {hp->lut_oc1, (void**)&dp.lut_oc1, L * hp->n_OC * oc_b, tables_upfront},
       {hp->lut_oc2, (void**)&dp.lut_oc2, L * hp->n_OC * oc_b, tables_upfront},
       {hp->lut_TIR, (void**)&dp.lut_TIR, cells * 32, tables_upfront}, {hp->lut_gap, (void**)&dp.lut_gap, cells * 64, tables_upfront},
-      {hp->matrix_EB, (void**)&dp.matrix_EB, eb_b, !zero_bins && !runner},
+      {bins_on_device ? nullptr : hp->matrix_EB, (void**)&dp.matrix_EB, bins_on_device ? 0 : eb_b, !zero_bins && !runner},
   };
   items.insert(items.end(), shared_items.begin(), shared_items.end());
   float *d_perceive = nullptr, *d_cells = nullptr;
@@ -475,6 +477,7 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
     *it.dst = (it.bytes || it.src) ? ar.take(it.bytes) : nullptr;
     if (!*it.dst && (it.bytes || it.src)) return fail(WGRT_ERR_CUDA, "arena overflow");
   }
+  if (bins_on_device) dp.matrix_EB = hp->matrix_EB;
 
   // ---- chunk plan ------------------------------------------------------------------------------
   std::vector<HostChunk> chunks;
@@ -582,7 +585,7 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
       CUDA_TRY(table(dp.lut_gap, hp->lut_gap, Y * 64, L));
       CUDA_TRY(table(dp.eff_reg_FOV, hp->eff_reg_FOV, Y * 64, 1));
       CUDA_TRY(table(dp.eff_reg_FOV_range, hp->eff_reg_FOV_range, Y * 32, 1));
-      if (!zero_bins) {
+      if (!zero_bins && !bins_on_device) {
         const size_t o0 = static_cast<size_t>(c.out_m0), ocols = static_cast<size_t>(c.out_m1 - c.out_m0);
         CUDA_TRY(copy2d({(char*)dp.matrix_EB + o0 * tile_b, (const char*)hp->matrix_EB + o0 * tile_b, X * tile_b,
                          X * tile_b, ocols * tile_b, L * Y}, H2D, s_in));
@@ -613,7 +616,8 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
         cp.delta_phase += c.ray0;
         if (cp.lmd_num) cp.lmd_num += c.ray0;
       }
-      if (seed_rng) CUDA_TRY(launch_seed_rng(cp.rng_states, c.rays, c.cell0 * 2 * hp->runner_points, s_run));
+      if (seed_rng)
+        CUDA_TRY(launch_seed_rng(cp.rng_states, c.rays, c.cell0 * 2 * hp->runner_points + hp->rng_seed_offset, s_run));
       for (int it = 0; it < num_iter; ++it) {
         rc = trace_device(*w, cp, s_run, 1 + static_cast<int>(k & 1), false);
         if (rc != WGRT_OK) return rc;

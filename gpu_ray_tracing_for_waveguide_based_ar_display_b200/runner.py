@@ -24,8 +24,8 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
                      num_rays_per_FoV: int, num_iter: int = 4, eb: Tuple[int, int] = (80, 120),
                      first_cell: int = 0, num_cells: Optional[int] = None,
                      matrix_EB: Optional[np.ndarray] = None, rng_states: Optional[np.ndarray] = None,
-                     flags: int = 0, timings: Optional[list] = None, bins_start_zero: Optional[bool] = None
-                     ) -> np.ndarray:
+                     flags: int = 0, timings: Optional[list] = None, bins_start_zero: Optional[bool] = None,
+                     rng_seed_offset: int = 0) -> np.ndarray:
     """Trace ``num_iter`` launches of the full-colour walk over the runner's ray layout.
 
     points      [num_rays_per_FoV/2, 2] start points (``generate_points_in_polygon`` output)
@@ -35,8 +35,12 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
     matrix_EB   optional preallocated float32 [L, Y, X, EBy, EBx] host array.  When omitted a
                 zeroed one is created and never uploaded (it is cleared on the device);
                 ``bins_start_zero=True`` declares a caller-provided array to be all zero, too.
+                A DEVICE buffer (anything with ``__cuda_array_interface__``) is used in place: the
+                launches accumulate into it and nothing is downloaded (multi-GPU jobs reduce the bins
+                over NVLink before anybody reads them).
     rng_states  optional uint32 host array for this cell range; when omitted the states are seeded
-                on the device as the runner seeds them (RUN:158) and discarded.
+                on the device as the runner seeds them (RUN:158) and discarded.  ``rng_seed_offset``
+                shifts the ray index of that seeding rule (independent streams for replicated jobs).
     Returns the bin tensor (host).
     """
     lib = _capi.load_library()
@@ -54,6 +58,8 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
         bins_start_zero = True
     if bins_start_zero:
         flags |= _capi.WGRT_FLAG_BINS_ZERO
+    if not isinstance(matrix_EB, np.ndarray) and hasattr(matrix_EB, "__cuda_array_interface__"):
+        flags |= _capi.WGRT_FLAG_BINS_DEVICE
     args = (px, py, None, None, None, None, None, None, None, None, None, None, rng_states,
             geom["IC"], geom["FC"], geom["FC_offset"], geom["OC"], geom["OC_offset"], float(n_g),
             geom["eff_reg1"], geom["eff_reg2"], geom["eff_reg_FOV"], geom["eff_reg_FOV_range"],
@@ -62,7 +68,8 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
     # ray 0 of this call is ray first_cell * num_rays_per_FoV of the runner's whole job (only the
     # reference's zero-state reseed rule, GRTF:28-29, reads a ray's index)
     prob, keep = pack_problem(args, host=True, flags=flags, runner_points=P, runner_first_cell=first_cell,
-                              num_rays=N, ray_index_base=first_cell * num_rays_per_FoV)
+                              num_rays=N, ray_index_base=first_cell * num_rays_per_FoV,
+                              rng_seed_offset=rng_seed_offset)
     tms = (C.c_float * 3)()
     _capi.check(lib.wgrt_trace_fullcolor_host(C.byref(prob), int(num_iter), tms), lib)
     if timings is not None:

@@ -34,6 +34,10 @@ extern "C" {
 #define WGRT_FLAG_BINS_ZERO 0x4u /* host entry only: matrix_EB starts at zero (as the runner
                                   * creates it, RUN:37) -> clear it on the device instead of
                                   * uploading it */
+#define WGRT_FLAG_BINS_DEVICE 0x8u /* host entry only: matrix_EB is a DEVICE pointer (all other
+                                   * buffers stay host pointers): the launches accumulate into the
+                                   * caller's device tensor and nothing is downloaded -- for callers
+                                   * that reduce the bins over several GPUs before reading them */
 
 /* ---- event counters (uint64 each) ------------------------------------------------------ */
 enum {
@@ -160,6 +164,14 @@ typedef struct wgrt_problem {
    * that a zero RNG state reseeds exactly as in the single launch over the whole job.  Normally 0.
    */
   int64_t ray_index_base;
+
+  /*
+   * Host entry, runner layout, rng_states == NULL only: added to the ray index in the device-side
+   * seeding rule, state[i] = 0x9E3779B9 * (runner_first_cell * 2P + i + rng_seed_offset + 1) -- so that
+   * replicas of one job (weak scaling: more Monte-Carlo samples per FoV) walk independent streams
+   * without uploading RNG arrays.  Normally 0 (the runner's seeds, RUN:158).
+   */
+  int64_t rng_seed_offset;
 } wgrt_problem_t;
 
 /* Library / runtime ------------------------------------------------------------------------ */

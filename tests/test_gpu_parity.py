@@ -293,6 +293,31 @@ def test_host_pipeline_chunking_is_invisible(chunks, oracle, monkeypatch):
     assert np.array_equal(rng, rng_o[lo:hi])
 
 
+def test_host_entry_device_bins_and_seed_offset(oracle):
+    """WGRT_FLAG_BINS_DEVICE: the host entry accumulates into the caller's device tensor and downloads
+    nothing; rng_seed_offset shifts the device-side seeding rule (replicated jobs, independent streams)."""
+    import torch
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
+    rpc = 200
+    scene = si.make_scene(5, 4, rpc, seed=43)
+    pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 44)
+    n = 5 * 4 * 3 * rpc
+    for off in (0, 3 * n):
+        rng = si.initial_rng_states(n, offset=off)
+        want = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, rng_states=rng)
+        dev = torch.full(scene.eb_shape, 2.0, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        alias = GRTF._TorchAlias(dev, scene.eb_shape, np.float32)
+        out = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, matrix_EB=alias,
+                                      rng_seed_offset=off)
+        assert out is alias
+        assert np.array_equal(dev.cpu().numpy(), want + 2.0)        # accumulated in place, device-seeded streams
+        out = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, matrix_EB=alias,
+                                      rng_seed_offset=off, bins_start_zero=True)
+        assert np.array_equal(dev.cpu().numpy(), want)               # cleared on the device first
+    assert want.sum() > 0
+
+
 # ---------------------------------------------------------------------------- single-wavelength twin (row f3)
 @pytest.mark.parametrize("mode", ["fast", "strict"])
 def test_single_lambda_twin(mode):

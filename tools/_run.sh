@@ -1,6 +1,2 @@
-D=gpu_ray_tracing_for_waveguide_based_ar_display_b200
-cp $D/libwgrt.so /tmp/libwgrt_base.so
-for v in W P base; do
-  if [ $v = base ]; then cp /tmp/libwgrt_base.so $D/libwgrt.so; else cp $D/csrc/build/libwgrt_$v.so $D/libwgrt.so; fi
-  echo "variant $v"; python tools/quick_perf.py --rays 5000 --iters 4 2>&1 | tail -1 | cut -c1-110
-done
+python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 > gpurun_out/bench_r1_2gpu_c.json 2> gpurun_out/bench_r1_2gpu_c.err; tail -c 600 gpurun_out/bench_r1_2gpu_c.err
