@@ -142,6 +142,37 @@ def test_pack_problem_runner_layout(small_scene):
         GRTF.pack_problem([pts[:5], pts] + b[2:], host=True, runner_points=24, num_rays=1728)
 
 
+def test_pack_problem_shard_and_evaluate_fields(small_scene):
+    """ray_index_base / rng_seed_offset reach the struct; the evaluate entry may omit matrix_EB (eb=...);
+    a device matrix_EB is accepted by the host entry only with WGRT_FLAG_BINS_DEVICE."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi
+    a = _args(small_scene)
+    prob, _ = GRTF.pack_problem(a, host=True, ray_index_base=12345, rng_seed_offset=777)
+    assert prob.ray_index_base == 12345 and prob.rng_seed_offset == 777
+    prob, _ = GRTF.pack_problem(a, host=True)
+    assert prob.ray_index_base == 0 and prob.rng_seed_offset == 0
+    pts = np.zeros(24, np.float32)
+    b = [pts, pts] + [None] * 10 + [None] + a[13:32] + [None]
+    prob, _ = GRTF.pack_problem(b, host=True, runner_points=24, num_rays=1728, eb=(40, 60))
+    assert not prob.matrix_EB and (prob.EBy, prob.EBx) == (40, 60)
+    with pytest.raises((TypeError, ValueError)):
+        GRTF.pack_problem(b, host=True, runner_points=24, num_rays=1728)          # no bins and no eb
+    with pytest.raises(ValueError):
+        GRTF.pack_problem(b, host=True, runner_points=24, num_rays=1728, eb=(0, 60))
+
+    class FakeDevice:                                                             # quacks like a device tensor
+        __cuda_array_interface__ = {"data": (0xdead0000, False), "shape": (3, 3, 4, 80, 120), "typestr": "<f4",
+                                    "strides": None, "version": 3}
+    c = list(a); c[32] = FakeDevice()
+    with pytest.raises(TypeError):
+        GRTF.pack_problem(c, host=True)                                           # device bins without the flag
+    prob, _ = GRTF.pack_problem(c, host=True, flags=_capi.WGRT_FLAG_BINS_DEVICE)
+    assert prob.matrix_EB == 0xdead0000 and prob.flags & _capi.WGRT_FLAG_BINS_DEVICE
+    k = GRTF.process_rays_kernel_pro_fullColor.configured(ray_index_base=99)
+    assert k.ray_index_base == 99 and k.runner_layout(4, 16).ray_index_base == 99
+    assert GRTF.process_rays_kernel_pro_fullColor.ray_index_base == 0
+
+
 def test_kernel_object_surface():
     k = GRTF.process_rays_kernel_pro_fullColor
     launcher = k[1024, 256]

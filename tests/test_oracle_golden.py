@@ -103,3 +103,28 @@ def test_single_lambda_twin_matches_reference(oracle):
     oracle.trace(*args, single_lambda=True, threshold=1e-15)
     assert np.array_equal(rng, g["rng_states"])
     assert np.array_equal(EB, want) and EB.sum() > 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/GPU_ray_tracing_functions.py"),
+                    reason="the reference sources only exist in the build container")
+def test_reference_kernels_compile_to_ptx():
+    """oracle/build_ref_ptx.py: the reference's own Numba kernels -> PTX (what the GPU box launches as
+    the reference).  Checks the manifest: both kernels, Numba's kernel ABI laid out for 33 / 32 arguments,
+    and that the PTX really is the reference's code (its module and function names are mangled into the
+    entry point)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "oracle", "build_ref_ptx.py")], check=True,
+                   stdout=subprocess.DEVNULL, env={k: v for k, v in os.environ.items() if k != "NUMBA_ENABLE_CUDASIM"})
+    with open(os.path.join(root, "oracle", "_ref", "manifest.json")) as f:
+        man = json.load(f)
+    full, pro = man["kernels"]["process_rays_kernel_pro_fullColor"], man["kernels"]["process_rays_kernel_pro"]
+    assert len(full["params"]) == 33 and len(pro["params"]) == 32
+    assert "GPU_ray_tracing_functions" in full["entry"] and "process_rays_kernel_pro_fullColor" in full["entry"]
+    assert full["params"][18] == {"kind": "scalar", "dtype": "float64"}          # n_g
+    assert full["params"][32] == {"kind": "array", "ndim": 5, "dtype": "float32"}  # matrix_EB
+    for k in (full, pro):
+        ptx = open(os.path.join(root, "oracle", "_ref", k["ptx"])).read()
+        assert ".visible .entry " + k["entry"] in ptx and "fma.rn.f64" in ptx
