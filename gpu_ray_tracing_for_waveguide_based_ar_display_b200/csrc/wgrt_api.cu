@@ -383,8 +383,7 @@ extern "C" int wgrt_trace_fullcolor_host(const wgrt_problem_t* hp, int num_iter,
 extern "C" int wgrt_trace_evaluate_host(const wgrt_problem_t* hp, int num_iter, int mask_size, int step_y, int step_x,
                                         float* perceive, float* cell_sums, float* timings_ms) {
   if (mask_size <= 0 || step_y <= 0 || step_x <= 0) return fail(WGRT_ERR_INVALID, "bad pupil mask / steps");
-  if (hp && static_cast<size_t>(hp->EBy * hp->EBx) * 4 > 200 * 1024)
-    return fail(WGRT_ERR_UNSUPPORTED, "eyebox tile larger than 200 KB of shared memory");
+  if (mask_size > 220) return fail(WGRT_ERR_UNSUPPORTED, "pupil mask wider than 220 bins");
   const EvalSpec ev{mask_size, step_y, step_x, perceive, cell_sums};
   return trace_host_impl(hp, num_iter, timings_ms, &ev);
 }
@@ -789,8 +788,7 @@ int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf,
   std::lock_guard<std::mutex> lk(g_mu);
   if (!dev_EB || L < 0 || Yf < 0 || Xf < 0 || EBy <= 0 || EBx <= 0 || mask_size <= 0 || step_y <= 0 || step_x <= 0)
     return fail(WGRT_ERR_INVALID, "bad arguments");
-  if ((size_t)(EBy * EBx) * 4 > 200 * 1024)
-    return fail(WGRT_ERR_UNSUPPORTED, "eyebox tile larger than 200 KB of shared memory");
+  if (mask_size > 220) return fail(WGRT_ERR_UNSUPPORTED, "pupil mask wider than 220 bins");
   CUDA_TRY(launch_pupil_sums(dev_EB, L, Yf, Xf, EBy, EBx, mask_size, step_y, step_x, dev_out, dev_cell_sums,
                              static_cast<cudaStream_t>(stream)));
   return WGRT_OK;

@@ -1045,6 +1045,85 @@ __global__ void __launch_bounds__(256) pupil_sums_kernel(const float* __restrict
   }
 }
 
+// Dense pupil sampling (down to the full pupil convolution the reference comments out as "super
+// long", AR_system_evaluation_functions.py:75-89) and eyebox tiles too large for shared memory
+// (BASELINE config 4: 320 x 480 bins): one CTA per (tile, block of output positions).  The CTA stages
+// the window of bins its outputs need as ROW PREFIX SUMS; the disc mask is a contiguous column range
+// [a_r, b_r] in each of its rows, so an output is sum_r (P[y0+r][x0+b_r+1] - P[y0+r][x0+a_r]):
+// 2 * mask loads instead of ~0.785 * mask^2.  Bins are integer counts, float32 prefix sums of fewer than
+// 2^24 counts are exact, so the result equals the direct sum bit for bit.
+__global__ void __launch_bounds__(256) pupil_window_kernel(const float* __restrict__ EB, int EBy, int EBx, int mask,
+                                                           int step_y, int step_x, int n_epy, int n_epx, int boy, int box,
+                                                           int blocks_x, float* __restrict__ out) {
+  extern __shared__ float s_pre[];              // [win_rows][win_cols + 1]
+  __shared__ short s_a[256], s_b[256];          // column range of the disc in mask row r (mask <= 256)
+  const int64_t tile = blockIdx.x;
+  const int by = blockIdx.y / blocks_x, bx = blockIdx.y - by * blocks_x;
+  const int oy0 = by * boy, ox0 = bx * box;
+  const int ny = min(boy, n_epy - oy0), nx = min(box, n_epx - ox0);
+  const int wy0 = oy0 * step_y, wx0 = ox0 * step_x;
+  const int win_rows = (ny - 1) * step_y + mask, win_cols = (nx - 1) * step_x + mask;
+  const int pitch = (box - 1) * step_x + mask + 1;
+  const float radius = mask * 0.5f, ctr = radius - 0.5f;
+  for (int r = threadIdx.x; r < mask; r += blockDim.x) {
+    int a = mask, b = -1;
+    const float dy = r - ctr;
+    for (int c = 0; c < mask; ++c) {
+      const float dx = c - ctr;
+      if (sqrtf(dx * dx + dy * dy) <= radius) { a = min(a, c); b = c; }   // same rule as pupil_sums_kernel / EVAL:68-73
+    }
+    s_a[r] = static_cast<short>(a);
+    s_b[r] = static_cast<short>(b);
+  }
+  const float* src = EB + tile * static_cast<int64_t>(EBy) * EBx;
+  // one warp per window row: inclusive scan of the row into s_pre[row][1..], s_pre[row][0] = 0
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int row = warp; row < win_rows; row += nwarps) {
+    const float* g = src + static_cast<int64_t>(wy0 + row) * EBx + wx0;
+    float* pr = s_pre + row * pitch;
+    if (lane == 0) pr[0] = 0.f;
+    float carry = 0.f;
+    for (int c0 = 0; c0 < win_cols; c0 += 32) {
+      const int c = c0 + lane;
+      float v = c < win_cols ? __ldg(g + c) : 0.f;
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(FULL_MASK, v, o);
+        if (lane >= o) v += t;
+      }
+      v += carry;
+      if (c < win_cols) pr[c + 1] = v;
+      carry = __shfl_sync(FULL_MASK, v, 31);
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < ny * nx; q += blockDim.x) {
+    const int iy = q / nx, ix = q - iy * nx;
+    const float* base = s_pre + (iy * step_y) * pitch + ix * step_x;
+    float acc = 0.f;
+    for (int r = 0; r < mask; ++r) {
+      const int a = s_a[r], b = s_b[r];
+      if (b >= a) acc += base[r * pitch + b + 1] - base[r * pitch + a];
+    }
+    out[(tile * n_epy + (oy0 + iy)) * n_epx + (ox0 + ix)] = acc;
+  }
+}
+
+// per-cell totals straight from global memory (tiles of any size)
+__global__ void __launch_bounds__(256) cell_sums_kernel(const float* __restrict__ EB, int64_t npix, float* __restrict__ cell_sums) {
+  const float* src = EB + static_cast<int64_t>(blockIdx.x) * npix;
+  float local = 0.f;
+  for (int64_t i = threadIdx.x; i < npix; i += blockDim.x) local += __ldg(src + i);
+  __shared__ float s_red[8];
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL_MASK, local, o);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot += s_red[w];
+    cell_sums[blockIdx.x] = tot;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s) {
@@ -1108,14 +1187,40 @@ cudaError_t launch_pupil_sums(const float* EB, int64_t L, int64_t Yf, int64_t Xf
   if (tiles == 0) return cudaSuccess;
   const int n_epy = EBy >= mask ? static_cast<int>((EBy - mask) / step_y + 1) : 0;
   const int n_epx = EBx >= mask ? static_cast<int>((EBx - mask) / step_x + 1) : 0;
-  const size_t smem = static_cast<size_t>(EBy * EBx) * sizeof(float);
-  cudaError_t err = cudaFuncSetAttribute(pupil_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
-  pupil_sums_kernel<<<static_cast<unsigned>(tiles), 256, smem, s>>>(EB, tiles, static_cast<int>(EBy),
-                                                                   static_cast<int>(EBx), mask, step_y, step_x,
-                                                                   n_epy, n_epx, (n_epy && n_epx) ? out : nullptr,
-                                                                   cell_sums);
+  const size_t tile_smem = static_cast<size_t>(EBy * EBx) * sizeof(float);
+  const bool sparse_sampling = static_cast<int64_t>(n_epy) * n_epx <= 256 && tile_smem <= 200 * 1024;
+  if (sparse_sampling) {
+    // the reference's sampled eye positions (7 x 8 at the default size): the whole tile in shared memory
+    cudaError_t err = cudaFuncSetAttribute(pupil_sums_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(tile_smem));
+    if (err != cudaSuccess) return err;
+    pupil_sums_kernel<<<static_cast<unsigned>(tiles), 256, tile_smem, s>>>(EB, tiles, static_cast<int>(EBy),
+                                                                          static_cast<int>(EBx), mask, step_y, step_x,
+                                                                          n_epy, n_epx, (n_epy && n_epx) ? out : nullptr,
+                                                                          cell_sums);
+    return cudaGetLastError();
+  }
+  if (cell_sums) cell_sums_kernel<<<static_cast<unsigned>(tiles), 256, 0, s>>>(EB, EBy * EBx, cell_sums);
+  if (out && n_epy && n_epx) {
+    if (mask > 256) return cudaErrorInvalidValue;
+    // block of output positions per CTA: its window of row prefix sums must fit ~96 KB
+    int boy = n_epy < 16 ? n_epy : 16, box = n_epx < 64 ? n_epx : 64;
+    auto window_bytes = [&](int by_, int bx_) {
+      return static_cast<size_t>((by_ - 1) * step_y + mask) * ((bx_ - 1) * step_x + mask + 1) * sizeof(float);
+    };
+    while (window_bytes(boy, box) > 96 * 1024 && (boy > 1 || box > 1)) {
+      if (box >= boy && box > 1) box = (box + 1) / 2; else boy = (boy + 1) / 2;
+    }
+    const size_t smem = window_bytes(boy, box);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;   // a pupil mask wider than ~220 bins
+    cudaError_t err = cudaFuncSetAttribute(pupil_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    const int blocks_y = (n_epy + boy - 1) / boy, blocks_x = (n_epx + box - 1) / box;
+    if (static_cast<int64_t>(blocks_y) * blocks_x > 65535) return cudaErrorInvalidValue;
+    pupil_window_kernel<<<dim3(static_cast<unsigned>(tiles), static_cast<unsigned>(blocks_y * blocks_x)), 256, smem, s>>>(
+        EB, static_cast<int>(EBy), static_cast<int>(EBx), mask, step_y, step_x, n_epy, n_epx, boy, box, blocks_x, out);
+  }
   return cudaGetLastError();
 }
 

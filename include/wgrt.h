@@ -263,6 +263,10 @@ int wgrt_debug_fma_peak(double* fp64_tflops, double* fp32_tflops);
  *   cell_sums[l, fy, fx] = sum of EB[l, fy, fx, :, :]   (gpu_ray_tracing_pro_fullColor.py:186).
  * EB is float32 [L, Yf, Xf, EBy, EBx]; out is float32 [L, Yf, Xf, n_epy, n_epx] with
  * n_ep* = (EB* - mask_size) / step_* + 1; either output may be NULL.
+ * Any step down to 1 (the full pupil convolution the reference leaves commented out as too slow,
+ * AR_system_evaluation_functions.py:75-89) and eyebox tiles of any size (BASELINE config 4: 320 x 480
+ * bins) are supported: dense sampling runs on row prefix sums, which are exact for the integer counts
+ * the walk produces (fewer than 2^24 per tile); mask_size <= 220.
  * wgrt_eval_pupil_sums takes DEVICE pointers and is asynchronous on `stream`;
  * wgrt_eval_pupil_sums_host takes HOST pointers and is synchronous.
  */

@@ -65,7 +65,11 @@ def test_evaluation_end_to_end_on_gpu():
 @pytest.mark.gpu
 def test_pupil_sums_other_shapes():
     rs = np.random.default_rng(3)
-    for shape, mask, sy, sx in (((1, 2, 3, 40, 50), 30, 8, 12), ((2, 1, 1, 64, 64), 16, 1, 1), ((1, 1, 2, 20, 20), 30, 8, 12)):
+    for shape, mask, sy, sx in (((1, 2, 3, 40, 50), 30, 8, 12), ((2, 1, 1, 64, 64), 16, 1, 1), ((1, 1, 2, 20, 20), 30, 8, 12),
+                                ((1, 2, 2, 80, 120), 30, 1, 1),        # the full pupil convolution (EVAL:75-89)
+                                ((1, 1, 2, 320, 480), 120, 1, 1),      # BASELINE config 4: 614 KB tiles, every pupil position
+                                ((2, 1, 1, 320, 480), 120, 32, 48),    # ... sampled as the reference samples
+                                ((1, 1, 1, 97, 131), 31, 3, 5)):       # ragged sizes, odd mask
         EB = rs.integers(0, 5, size=shape).astype(np.float32)
         lib = EV._capi.load_library()
         n_epy = (shape[3] - mask) // sy + 1 if shape[3] >= mask else 0
@@ -75,10 +79,15 @@ def test_pupil_sums_other_shapes():
                                                      cells.ctypes.data), lib)
         yy, xx = np.ogrid[:mask, :mask]
         disc = (np.sqrt((xx - (mask / 2 - 0.5)) ** 2 + (yy - (mask / 2 - 0.5)) ** 2) <= mask / 2)
-        for iy in range(n_epy):
-            for ix in range(n_epx):
-                want = (EB[..., iy * sy:iy * sy + mask, ix * sx:ix * sx + mask] * disc).sum(axis=(-1, -2))
-                assert np.array_equal(out[..., iy, ix], want)
+        if n_epy * n_epx > 4000:
+            # dense sampling: check against FFT-free direct correlation on a subset of positions
+            pos = [(int(a), int(b)) for a, b in zip(rs.integers(0, n_epy, 300), rs.integers(0, n_epx, 300))]
+            pos += [(0, 0), (n_epy - 1, n_epx - 1), (0, n_epx - 1), (n_epy - 1, 0)]
+        else:
+            pos = [(iy, ix) for iy in range(n_epy) for ix in range(n_epx)]
+        for iy, ix in pos:
+            want = (EB[..., iy * sy:iy * sy + mask, ix * sx:ix * sx + mask] * disc).sum(axis=(-1, -2))
+            assert np.array_equal(out[..., iy, ix], want), (shape, iy, ix)
         assert np.array_equal(cells, EB.sum(axis=(-1, -2)))
 
 
