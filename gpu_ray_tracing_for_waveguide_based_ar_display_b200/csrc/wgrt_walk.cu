@@ -138,15 +138,21 @@ struct alignas(16) CellConst {
   int pad_[3];
 };
 
-struct Stage {     // the next rays of the run, raw, as loaded (coalesced) from the SoA arrays
-  float x[32], y[32], te[32], tm[32], dl[32];
-  uint32_t rng[32];
+// Rays whose in-coupling draw picked an order wait here (a per-warp stack) for a free lane: the raw
+// ray as loaded, its index, its RNG state after the draw, the order (bit 31 of idx) and the order's
+// efficiency; the lane that pops an entry applies the order in phase B.
+constexpr int QUEUE_CAP = 48;
+struct Queue {
+  double esel[QUEUE_CAP];
+  uint32_t idx[QUEUE_CAP];
+  uint32_t rng[QUEUE_CAP];
+  float x[QUEUE_CAP], y[QUEUE_CAP], te[QUEUE_CAP], tm[QUEUE_CAP], dl[QUEUE_CAP];
 };
 
 struct alignas(16) WarpShared {
   Atlas atlas;
   CellConst cc;
-  Stage st;
+  Queue q;
 };
 
 __host__ __device__ constexpr size_t table_offset() { return (sizeof(WarpShared) + 15) & ~size_t(15); }
@@ -370,185 +376,162 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       Ray r;
       r.state = ST_DEAD;
       r.row0 = -1;
-      int navail = 0, head = 0;      // staged rays not yet handed to a lane (warp uniform)
-      int64_t stage_base = cursor;   // ray index of staging slot 0
-      bool open = true;              // the run may have more rays to stage
+      int qn = 0;          // survivors of in-coupling waiting for a lane (warp uniform)
+      bool open = true;    // the run may have more rays nobody has in-coupled yet
 
       for (;;) {
-        bool lost = false;
-
-        // ---- phase A: go to the next grating.  Every lane whose ray moved asks the atlas once. ----
-        if (r.state != ST_DEAD && r.row0 < 0) {
-          uint32_t word = atlas_lookup(sh.atlas, r.x, r.y);
-          if (word & ATLAS_ANY_MIXED) word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * r.state)) & 31u, rs, r.x, r.y, &cn);
-          // every field the state can need is certain now
-          const bool in_ic = ((word >> ATLAS_SHIFT_IC) & 3u) == 1u;
-          const bool in_r1 = ((word >> ATLAS_SHIFT_R1) & 3u) == 1u;
-          const bool in_r2 = ((word >> ATLAS_SHIFT_R2) & 3u) == 1u;
-          const int fc = (word >> ATLAS_SHIFT_FC) & 0xff, oc = (word >> ATLAS_SHIFT_OC) & 0xff;
-          int st = r.state;
-          // what the last in-coupler order left open (GRTF:883-886, 899-902 and siblings)
-          if (st == ST_PEND_FWD) st = in_ic ? 0 : 2;
-          else if (st == ST_PEND_BACK) { st = 1; lost = !in_ic; }
-          // the loop head (GRTF:905-907)
-          if (!lost) {
-            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
-            lost = ++r.iter > 100000 || !in_r1;
-          }
-          int sinfo = cc.sinfo[st];
-          int region = sinfo & SI_REGION_MASK;
-          int code = region == REG_FC ? fc : region == REG_OC ? oc : 0;
-          if (code == CELL_NONE && ((sinfo >> SI_MISS_SHIFT) & 3) == 1 && !in_r2 && !lost) {
-            // GRTF:1103-1104: state 3 left the fold zone; the iteration ends without a move and the
-            // next one (same point: still inside eff_reg1) looks at the out-coupler
-            st = 4;
-            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
-            lost = ++r.iter > 100000;
-            sinfo = cc.sinfo[4];
-            code = oc;
-          }
-          r.state = st;
-          if (!lost) {
-            if (code != CELL_NONE) {
-              r.row0 = ((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code;
-            } else if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) {
-              lost = true;                       // GRTF:1244-1246
-            } else {
-              // free TIR bounce (GRTF:1049-1052, 1105-1108, 1175-1178); the lane asks the atlas again
-              // in the next step
-              const int g = (sinfo >> SI_GAP_SHIFT) & 3;
-              r.x += cc.gap[2 * g];
-              r.y += cc.gap[2 * g + 1];
-              r.tm = cmul(r.tm, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
-              if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
-            }
-          }
-          if (lost) {
-            st_stream(p.rng_states + t_begin + r.idx, r.rng);
-            r.state = ST_DEAD;
-            lost = false;
-          }
-        }
-        __syncwarp();
-
-        // ---- refill: lanes without a ray pop staged rays; an empty stage is reloaded -------------
+        // ---- in-coupling decisions, 32 rays at a time, every lane busy (GRTF:860-904 up to the
+        //      draw): whenever fewer survivors are queued than lanes are free.  About three quarters
+        //      of the rays end right here; their position is never even loaded. -----------------
         const unsigned dead = __ballot_sync(FULL_MASK, r.state == ST_DEAD);
-        if (dead != 0u && (navail > 0 || open)) {
-          if (navail == 0) {
-            const int64_t i = cursor + lane;
-            const bool in_range = i < run_limit;
-            bool same = in_range;
-            float fx = 0.f, fy = 0.f, fte = 0.f, ftm = 0.f, fdl = 0.f;
-            uint32_t frng = 0u;
-            if (in_range) {
-              if (IMPLICIT) {
-                // runner layout (RUN:82-115): P TE rays then P TM rays per cell, ray k starts at point k
-                const int64_t k = i % (2 * p.runner_points);
-                const bool te_half = k < p.runner_points;
-                const int64_t pt = te_half ? k : k - p.runner_points;
-                fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
-                fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
-              } else {
-                same = ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl);
-                fx = ld_stream(p.x + i); fy = ld_stream(p.y + i); fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i);
-                fdl = ld_stream(p.delta_phase + i);
-              }
-              frng = ld_stream(p.rng_states + i);
-              if (i + 64 < run_limit) {   // two batches ahead
-                prefetch_l2(p.rng_states + i + 64);
-                if (!IMPLICIT) {
-                  prefetch_l2(p.x + i + 64); prefetch_l2(p.y + i + 64); prefetch_l2(p.te + i + 64);
-                  prefetch_l2(p.tm + i + 64); prefetch_l2(p.delta_phase + i + 64); prefetch_l2(p.m + i + 64);
-                  prefetch_l2(p.n + i + 64);
-                  if (has_l) prefetch_l2(p.lmd_num + i + 64);
-                }
-              }
+        const int nd = __popc(dead);
+        while (open && qn < nd && qn <= QUEUE_CAP - 32) {
+          const int64_t i = cursor + lane;
+          bool same = i < run_limit;
+          float fx = 0.f, fy = 0.f, fte = 0.f, ftm = 0.f, fdl = 0.f;
+          uint32_t frng = 0u;
+          if (same) {
+            if (IMPLICIT) {
+              // runner layout (RUN:82-115): P TE rays then P TM rays per cell, ray k starts at point k
+              const int64_t kk = i % (2 * p.runner_points);
+              const bool te_half = kk < p.runner_points;
+              const int64_t pt = te_half ? kk : kk - p.runner_points;
+              fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
+              fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
+            } else {
+              same = ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl);
+              fx = ld_stream(p.x + i); fy = ld_stream(p.y + i);
+              fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i); fdl = ld_stream(p.delta_phase + i);
             }
-            const unsigned okmask = __ballot_sync(FULL_MASK, same);
-            const int cnt = okmask == FULL_MASK ? 32 : __ffs(~okmask) - 1;   // leading rays of this run
-            if (cnt < 32) open = false;
-            __syncwarp();
-            if (lane < cnt) {
-              sh.st.x[lane] = fx; sh.st.y[lane] = fy; sh.st.te[lane] = fte; sh.st.tm[lane] = ftm; sh.st.dl[lane] = fdl;
-              sh.st.rng[lane] = frng;
-            }
-            __syncwarp();
-            stage_base = cursor;
-            cursor += cnt;
-            navail = cnt;
-            head = 0;
-          }
-          const int nd = __popc(dead);
-          const int take = min(nd, navail);
-          if (valid) {
-            const int rank = __popc(dead & lt_mask);
-            if (r.state == ST_DEAD && rank < take) {
-              const int slot = head + rank;
-              r.idx = static_cast<int>(stage_base - t_begin) + slot;
-              r.x = static_cast<double>(sh.st.x[slot]);
-              r.y = static_cast<double>(sh.st.y[slot]);
-              r.te = cplx{static_cast<double>(sh.st.te[slot]), 0.0};
-              const double tm = static_cast<double>(sh.st.tm[slot]);
-              const float dlf = sh.st.dl[slot];
-              if (dlf == 0.0f) {
-                r.tm = cplx{tm, 0.0};
-              } else {
-                double sn, cs;
-                sincos(static_cast<double>(dlf), &sn, &cs);
-                r.tm = cplx{tm * cs, tm * sn};
+            frng = ld_stream(p.rng_states + i);
+            if (i + 64 < run_limit) {   // two batches ahead
+              prefetch_l2(p.rng_states + i + 64);
+              if (!IMPLICIT) {
+                prefetch_l2(p.x + i + 64); prefetch_l2(p.y + i + 64);
+                prefetch_l2(p.te + i + 64); prefetch_l2(p.tm + i + 64); prefetch_l2(p.delta_phase + i + 64);
+                prefetch_l2(p.m + i + 64); prefetch_l2(p.n + i + 64);
+                if (has_l) prefetch_l2(p.lmd_num + i + 64);
               }
-              r.rng = sh.st.rng[slot];
-              r.s = 1.0;                     // GRTF:860-869: the raw amplitudes enter E_field_cal as they are
-              r.inv_cos = cc.inv_cos_in;
-              r.ener = 1.0;
-              r.iter = 0;
-              r.state = 0;
-              r.row0 = 0;                    // in-coupling: rows 0 and 1
-              if (COUNT) cn.c[WGRT_CNT_RAYS]++;
             }
           }
-          // (rays of a run whose cell indices are out of range are dropped untouched)
-          head += take;
-          navail -= take;
+          const unsigned okmask = __ballot_sync(FULL_MASK, same);
+          const int cnt = okmask == FULL_MASK ? 32 : __ffs(~okmask) - 1;   // leading rays of this run
+          if (cnt < 32) open = false;
+          int k = -1;
+          double esel = 0.0;
+          if (lane < cnt && valid) {   // (rays of a run whose cell indices are out of range are left untouched)
+            if (COUNT) {
+              cn.c[WGRT_CNT_RAYS]++; cn.c[WGRT_CNT_DRAWS]++; cn.c[WGRT_CNT_DRAW2]++; cn.c[WGRT_CNT_EFIELD] += 2;
+            }
+            const double u = xorshift_draw(frng, p.ray_index_base + i);
+            const double te = static_cast<double>(fte), tm = static_cast<double>(ftm);
+            cplx w{tm, 0.0};
+            if (fdl != 0.0f) {
+              double sn, cs;
+              sincos(static_cast<double>(fdl), &sn, &cs);
+              w = cplx{tm * cs, tm * sn};
+            }
+            // GRTF:860-869: the raw amplitudes enter E_field_cal as they are (s = 1)
+            const double t2 = te * te, m2 = w.re * w.re + w.im * w.im, zre = te * w.re, zim = te * w.im;
+            const double g = cc.inv_cos_in;
+            const double e1 = (tab[R_Q] * t2 + tab[R_Q + 1] * m2 + (tab[R_Q + 2] * zre + tab[R_Q + 3] * zim)) * g;
+            const double e2 = (tab[ROW + R_Q] * t2 + tab[ROW + R_Q + 1] * m2 + (tab[ROW + R_Q + 2] * zre + tab[ROW + R_Q + 3] * zim)) * g;
+            if (u <= e1) { k = 0; esel = e1; }                 // GRTF:871: no energy gate here
+            else if (u <= e1 + e2) { k = 1; esel = e2; }       // GRTF:887
+            else st_stream(p.rng_states + i, frng);            // GRTF:903-904: absorbed
+          }
+          const unsigned surv = __ballot_sync(FULL_MASK, k >= 0);
+          if (k >= 0) {
+            const int slot = qn + __popc(surv & lt_mask);
+            sh.q.idx[slot] = static_cast<uint32_t>(i - t_begin) | (static_cast<uint32_t>(k) << 31);
+            sh.q.rng[slot] = frng;
+            sh.q.esel[slot] = esel;
+            sh.q.x[slot] = fx; sh.q.y[slot] = fy; sh.q.te[slot] = fte; sh.q.tm[slot] = ftm; sh.q.dl[slot] = fdl;
+          }
+          qn += __popc(surv);
+          cursor += cnt;
+          __syncwarp();
+        }
+
+        // ---- free lanes pop survivors: re-read the ray; phase B applies the order already chosen --
+        if (nd && qn) {
+          const int take = min(nd, qn);
+          const int rank = __popc(dead & lt_mask);
+          if (r.state == ST_DEAD && rank < take) {
+            const int slot = qn - 1 - rank;
+            const uint32_t e = sh.q.idx[slot];
+            r.idx = static_cast<int>(e & 0x7fffffffu);
+            r.rng = sh.q.rng[slot];
+            r.ener = sh.q.esel[slot];        // ener = 1 * efficiency of the in-coupled order (GRTF:882)
+            r.x = static_cast<double>(sh.q.x[slot]);
+            r.y = static_cast<double>(sh.q.y[slot]);
+            const double te = static_cast<double>(sh.q.te[slot]), tm = static_cast<double>(sh.q.tm[slot]);
+            const float fdl = sh.q.dl[slot];
+            r.te = cplx{te, 0.0};
+            r.tm = cplx{tm, 0.0};
+            if (fdl != 0.0f) {
+              double sn, cs;
+              sincos(static_cast<double>(fdl), &sn, &cs);
+              r.tm = cplx{tm * cs, tm * sn};
+            }
+            r.s = 1.0;
+            r.inv_cos = cc.inv_cos_in;
+            r.iter = -1;                     // marks "order already chosen"
+            r.state = 0;
+            r.row0 = static_cast<int>(e >> 31);   // the chosen in-coupling row (0 or 1)
+          }
+          qn -= take;
           __syncwarp();
         }
         if (__ballot_sync(FULL_MASK, r.state != ST_DEAD) == 0u) {
-          if (!open && navail == 0) break;
+          if (!open && qn == 0) break;
           continue;
         }
         if (COUNT && lane == 0) cn.c[WGRT_CNT_WARP_STEPS]++;
+        bool lost = false;
 
-        // ---- phase B: diffract -------------------------------------------------------------------
-        if (r.state != ST_DEAD && r.row0 >= 0) {
-          const double* e = tab + r.row0 * ROW;
-          const int meta0 = static_cast<int>(__double_as_longlong(e[R_META]));
-          const bool three = (meta0 & META_THREE) != 0;
-          const bool gated = (meta0 & META_GATED) != 0;
-          const double u = xorshift_draw(r.rng, p.ray_index_base + t_begin + r.idx);
-          if (COUNT) {
-            cn.c[WGRT_CNT_DRAWS]++;
-            cn.c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
-            cn.c[WGRT_CNT_EFIELD] += three ? 3 : 2;
+        // ---- phase B1: diffract -- draw and pick the order ------------------------------------------
+        const bool at_event = r.state != ST_DEAD && r.row0 >= 0;
+        int k = -1;
+        double esel = 1.0;
+        if (at_event) {
+          if (r.iter >= 0) {
+            const double* e = tab + r.row0 * ROW;
+            const int meta0 = static_cast<int>(__double_as_longlong(e[R_META]));
+            const bool three = (meta0 & META_THREE) != 0;
+            const bool gated = (meta0 & META_GATED) != 0;
+            const double u = xorshift_draw(r.rng, p.ray_index_base + t_begin + r.idx);
+            if (COUNT) {
+              cn.c[WGRT_CNT_DRAWS]++;
+              cn.c[three ? WGRT_CNT_DRAW3 : WGRT_CNT_DRAW2]++;
+              cn.c[WGRT_CNT_EFIELD] += three ? 3 : 2;
+            }
+            const double t2 = r.te.re * r.te.re + r.te.im * r.te.im;
+            const double m2 = r.tm.re * r.tm.re + r.tm.im * r.tm.im;
+            const double zre = r.te.re * r.tm.re + r.te.im * r.tm.im;   // conj(te) * tm
+            const double zim = r.te.re * r.tm.im - r.te.im * r.tm.re;
+            const double g = r.s * r.inv_cos;
+            const double* e3 = three ? e + 2 * ROW : e;                 // two-order events: never selected
+            const double e1 = (e[R_Q] * t2 + e[R_Q + 1] * m2 + (e[R_Q + 2] * zre + e[R_Q + 3] * zim)) * g;
+            const double e2 = (e[ROW + R_Q] * t2 + e[ROW + R_Q + 1] * m2 + (e[ROW + R_Q + 2] * zre + e[ROW + R_Q + 3] * zim)) * g;
+            const double e3v = (e3[R_Q] * t2 + e3[R_Q + 1] * m2 + (e3[R_Q + 2] * zre + e3[R_Q + 3] * zim)) * g;
+            // the reference's if / elif chain (GRTF:919-953, 1020-1048, 1135-1174)
+            if (u <= e1 && (!gated || r.ener * e1 > threshold)) { k = 0; esel = e1; }
+            else if (u <= e1 + e2 && (!gated || r.ener * e2 > threshold)) { k = 1; esel = e2; }
+            else if (three && u <= e1 + e2 + e3v && r.ener * e3v > threshold) { k = 2; esel = e3v; }
+          } else {
+            r.iter = 0;   // a popped survivor: row0 IS the chosen in-coupling row, ener already holds its efficiency
+            k = 0;
           }
-          const double t2 = r.te.re * r.te.re + r.te.im * r.te.im;
-          const double m2 = r.tm.re * r.tm.re + r.tm.im * r.tm.im;
-          const double zre = r.te.re * r.tm.re + r.te.im * r.tm.im;   // conj(te) * tm
-          const double zim = r.te.re * r.tm.im - r.te.im * r.tm.re;
-          const double g = r.s * r.inv_cos;
-          const double* e3 = three ? e + 2 * ROW : e;                 // two-order events: never selected
-          const double e1 = (e[R_Q] * t2 + e[R_Q + 1] * m2 + (e[R_Q + 2] * zre + e[R_Q + 3] * zim)) * g;
-          const double e2 = (e[ROW + R_Q] * t2 + e[ROW + R_Q + 1] * m2 + (e[ROW + R_Q + 2] * zre + e[ROW + R_Q + 3] * zim)) * g;
-          const double e3v = (e3[R_Q] * t2 + e3[R_Q + 1] * m2 + (e3[R_Q + 2] * zre + e3[R_Q + 3] * zim)) * g;
-          // the reference's if / elif chain (GRTF:871-903, 1020-1048, 1135-1174)
-          int k = -1;
-          double esel = 0.0;
-          if (u <= e1 && (!gated || r.ener * e1 > threshold)) { k = 0; esel = e1; }
-          else if (u <= e1 + e2 && (!gated || r.ener * e2 > threshold)) { k = 1; esel = e2; }
-          else if (three && u <= e1 + e2 + e3v && r.ener * e3v > threshold) { k = 2; esel = e3v; }
+        }
+        __syncwarp();   // one copy of the code below, run by every lane that has an order to apply
+
+        // ---- phase B2: apply the chosen order -----------------------------------------------------------
+        if (at_event) {
           if (k < 0) {
             lost = true;   // absorbed
           } else {
-            const double* row = e + k * ROW;
+            const double* row = tab + (r.row0 + k) * ROW;
             const int meta = static_cast<int>(__double_as_longlong(row[R_META]));
             const int post = (meta >> 7) & 3;
             if (post == POST_DEPOSIT) {
@@ -569,8 +552,6 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
                        L1.re * r.te.im + L1.im * r.te.re + (L3.re * r.tm.im + L3.im * r.tm.re)};
               double nt2 = nte.re * nte.re + nte.im * nte.im;
               double nm2 = ntm.re * ntm.re + ntm.im * ntm.im;
-              // E_field_cal zeroes the phase of an output amplitude below 1e-20 (GRTF:147-148); the
-              // amplitudes it sees are those of the NORMALISED input, i.e. sqrt(n?2 * s)
               const double eps2 = 1e-40;
               double n2 = nt2 + nm2;
               if (fmin(nt2, nm2) * r.s < eps2 || n2 < 1e-200) {   // rare
@@ -595,6 +576,53 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             }
           }
           r.row0 = -1;
+          if (lost) {
+            st_stream(p.rng_states + t_begin + r.idx, r.rng);
+            r.state = ST_DEAD;
+            lost = false;
+          }
+        }
+        __syncwarp();
+
+        // ---- phase A: go to the next grating.  Every lane whose ray moved asks the atlas once. ----
+        if (r.state != ST_DEAD && r.row0 < 0) {
+          uint32_t word = atlas_lookup(sh.atlas, r.x, r.y);
+          if (word & ATLAS_ANY_MIXED) word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * r.state)) & 31u, rs, r.x, r.y, &cn);
+          const bool in_ic = ((word >> ATLAS_SHIFT_IC) & 3u) == 1u;
+          const bool in_r1 = ((word >> ATLAS_SHIFT_R1) & 3u) == 1u;
+          const bool in_r2 = ((word >> ATLAS_SHIFT_R2) & 3u) == 1u;
+          const int fc = (word >> ATLAS_SHIFT_FC) & 0xff, oc = (word >> ATLAS_SHIFT_OC) & 0xff;
+          int st = r.state;
+          if (st == ST_PEND_FWD) st = in_ic ? 0 : 2;
+          else if (st == ST_PEND_BACK) { st = 1; lost = !in_ic; }
+          if (!lost) {
+            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
+            lost = ++r.iter > 100000 || !in_r1;
+          }
+          int sinfo = cc.sinfo[st];
+          int region = sinfo & SI_REGION_MASK;
+          int code = region == REG_FC ? fc : region == REG_OC ? oc : 0;
+          if (code == CELL_NONE && ((sinfo >> SI_MISS_SHIFT) & 3) == 1 && !in_r2 && !lost) {
+            st = 4;
+            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
+            lost = ++r.iter > 100000;
+            sinfo = cc.sinfo[4];
+            code = oc;
+          }
+          r.state = st;
+          if (!lost) {
+            if (code != CELL_NONE) {
+              r.row0 = ((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code;
+            } else if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) {
+              lost = true;                       // GRTF:1244-1246
+            } else {
+              const int g = (sinfo >> SI_GAP_SHIFT) & 3;
+              r.x += cc.gap[2 * g];
+              r.y += cc.gap[2 * g + 1];
+              r.tm = cmul(r.tm, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
+              if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
+            }
+          }
           if (lost) {
             st_stream(p.rng_states + t_begin + r.idx, r.rng);
             r.state = ST_DEAD;
