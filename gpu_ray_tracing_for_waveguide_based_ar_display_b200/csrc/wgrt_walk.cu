@@ -516,9 +516,13 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double e2 = (e[ROW + R_Q] * t2 + e[ROW + R_Q + 1] * m2 + (e[ROW + R_Q + 2] * zre + e[ROW + R_Q + 3] * zim)) * g;
             const double e3v = (e3[R_Q] * t2 + e3[R_Q + 1] * m2 + (e3[R_Q + 2] * zre + e3[R_Q + 3] * zim)) * g;
             // the reference's if / elif chain (GRTF:919-953, 1020-1048, 1135-1174)
-            if (u <= e1 && (!gated || r.ener * e1 > threshold)) { k = 0; esel = e1; }
-            else if (u <= e1 + e2 && (!gated || r.ener * e2 > threshold)) { k = 1; esel = e2; }
-            else if (three && u <= e1 + e2 + e3v && r.ener * e3v > threshold) { k = 2; esel = e3v; }
+            // (evaluated without branches: the three tests are cheap, a divergent chain is not)
+            const double e12 = e1 + e2;
+            const bool ok1 = u <= e1 && (!gated || r.ener * e1 > threshold);
+            const bool ok2 = u <= e12 && (!gated || r.ener * e2 > threshold);
+            const bool ok3 = three && u <= e12 + e3v && r.ener * e3v > threshold;
+            k = ok1 ? 0 : ok2 ? 1 : ok3 ? 2 : -1;
+            esel = ok1 ? e1 : ok2 ? e2 : e3v;
           } else {
             r.iter = 0;   // a popped survivor: row0 IS the chosen in-coupling row, ener already holds its efficiency
             k = 0;
