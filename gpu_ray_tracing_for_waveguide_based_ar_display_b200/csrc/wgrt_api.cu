@@ -60,7 +60,7 @@ struct Workspace {
   int num_sms = 0;
   DeviceBuf cells[NUM_REGIONS], detail[NUM_REGIONS], rowmask[NUM_REGIONS], coarse[NUM_REGIONS], rowmask_c[NUM_REGIONS];
   DeviceBuf atlas;   // uint32 [ATLAS_N * ATLAS_N] level 1, then [ATLAS_N2 * ATLAS_N2] level 2
-  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | AtlasDyn @ 256 | tile counters @ 512 | hash state @ 768 | counters @ 1024
+  DeviceBuf small;   // RegionDyn[NUM_REGIONS] | AtlasDyn @ 256 | tile counters @ 512 | hash state @ 768 | counters @ 1024 | Region[NUM_REGIONS] @ 1280
   bool index_stale = true;  // the index buffers were (re)allocated or used by a debug call
   DeviceBuf jones[3];   // per-warp Jones-matrix scratch of the warp walk, one per launch slot
   DeviceBuf arena;   // staging for the host entry points
@@ -170,6 +170,7 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
   }
   rs.atlas = static_cast<uint32_t*>(w.atlas.ptr);
   rs.atlas_dyn = w.atlas_dyn();
+  rs.regions = static_cast<char*>(w.small.ptr) + 1280;
   rs.dyn = w.dyn();
   rs.hash_state = w.hash_state();
   rs.dirty = w.hash_state() + 1;

@@ -171,6 +171,7 @@ struct RegionSet {
   RegionStatic st[NUM_REGIONS];
   uint32_t* atlas;                  // device [ATLAS_N * ATLAS_N] then [ATLAS_N2 * ATLAS_N2]
   AtlasDyn* atlas_dyn;              // device
+  void* regions;                    // device Region[NUM_REGIONS] (wgrt_region.cuh), refreshed at every index build
   RegionDyn* dyn;                   // device array [NUM_REGIONS]
   unsigned long long* hash_state;   // device: {hash of the index now built, dirty flag of this launch}
   const unsigned long long* dirty;  // = hash_state + 1

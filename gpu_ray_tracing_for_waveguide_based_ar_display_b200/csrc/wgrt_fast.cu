@@ -920,6 +920,10 @@ __device__ __forceinline__ bool atlas_field_mixed(int r, uint32_t word) {
 }
 
 __global__ void region_atlas_kernel(const __grid_constant__ RegionSet rs) {
+  // the region descriptors the walk's rare exact path reads: refreshed at EVERY build (the vertex
+  // pointers may have changed even when the content hash, and with it the index, did not)
+  if (blockIdx.x == 0 && threadIdx.x < NUM_REGIONS)
+    region_load(static_cast<Region*>(rs.regions)[threadIdx.x], rs.st[threadIdx.x], rs.dyn[threadIdx.x]);
   if (!*rs.dirty) return;
   double xmin, ymin, w, h;
   atlas_bbox(rs, xmin, ymin, w, h);

@@ -213,8 +213,8 @@ __device__ __forceinline__ int atlas_hit(uint32_t word, int shift, const Region&
 // is still MIXED after the two atlas levels is answered by that set's own grid / literal scan and
 // patched into the word.  One call site for all sets: the rare path is compiled once.
 template <bool COUNT>
-__device__ __noinline__ uint32_t atlas_resolve(uint32_t word, uint32_t need, const RegionSet& rs, double x, double y,
-                                               Counts* cn) {
+__device__ __noinline__ uint32_t atlas_resolve(uint32_t word, uint32_t need, const Region* __restrict__ regions, double x,
+                                               double y, Counts* cn) {
 #pragma unroll 1
   for (int r = 0; r < NUM_REGIONS; ++r) {
     if (!((need >> r) & 1u)) continue;
@@ -224,9 +224,7 @@ __device__ __noinline__ uint32_t atlas_resolve(uint32_t word, uint32_t need, con
     const uint32_t mask = multi ? 0xffu : 3u;
     const uint32_t f = (word >> shift) & mask;
     if (f != (multi ? static_cast<uint32_t>(CELL_AMBIG) : 2u)) continue;
-    Region reg;
-    region_load(reg, rs.st[r], rs.dyn[r]);
-    const int hit = region_locate<COUNT>(reg, x, y, cn);
+    const int hit = region_locate<COUNT>(regions[r], x, y, cn);
     const uint32_t v = multi ? (hit < 0 ? static_cast<uint32_t>(CELL_NONE) : static_cast<uint32_t>(hit)) : (hit >= 0 ? 1u : 0u);
     word = (word & ~(mask << shift)) | (v << shift);
   }

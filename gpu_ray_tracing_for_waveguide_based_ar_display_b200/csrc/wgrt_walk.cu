@@ -591,7 +591,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         // ---- phase A: go to the next grating.  Every lane whose ray moved asks the atlas once. ----
         if (r.state != ST_DEAD && r.row0 < 0) {
           uint32_t word = atlas_lookup(sh.atlas, r.x, r.y);
-          if (word & ATLAS_ANY_MIXED) word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * r.state)) & 31u, rs, r.x, r.y, &cn);
+          if (word & ATLAS_ANY_MIXED) word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * r.state)) & 31u, static_cast<const Region*>(rs.regions), r.x, r.y, &cn);
           const bool in_ic = ((word >> ATLAS_SHIFT_IC) & 3u) == 1u;
           const bool in_r1 = ((word >> ATLAS_SHIFT_R1) & 3u) == 1u;
           const bool in_r2 = ((word >> ATLAS_SHIFT_R2) & 3u) == 1u;
