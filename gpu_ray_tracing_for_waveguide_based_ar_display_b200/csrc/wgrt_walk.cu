@@ -7,17 +7,20 @@
 //    the rays arrive cell by cell, gpu_ray_tracing_pro_fullColor.py:82-115) and walks them alone.
 //    No block barriers, no cross-warp queues; the end-of-cell drain (lanes idling while the longest
 //    paths finish) is paid once per ~5000 rays per warp instead of once per ~1250.
-//  * In-coupling is just another grating event.  A lane whose ray ended pops the next ray of the run
-//    from a 32-entry staging buffer (filled with coalesced loads, cut where the cell key changes: run
-//    detection costs nothing extra) and takes part in the very next event phase.
-//  * A step has two phases.  Phase A ("go to the next grating"): every lane that moved asks the
-//    ATLAS (wgrt_region.cuh) -- one L1-resident word answers in-coupler / effective region 1 / 2 /
-//    fold slice / out-coupler slice at once -- resolves what the previous event left pending, and
-//    free-bounces (GRTF:1049-1052, 1102-1108, 1175-1178) until it stands on a grating or is lost.
-//    Phase B ("diffract"): all lanes that stand on a grating draw, evaluate the efficiencies of ALL
-//    orders at once from per-cell quadratic forms (4 FMAs per order instead of a Jones application
-//    per order in a divergent if-chain), pick the order exactly as the reference's if/elif chain
-//    does, and apply one Jones matrix -- the chosen one.
+//  * In-coupling decisions are taken 32 rays at a time with every lane busy (coalesced loads, cut where
+//    the cell key changes: run detection costs nothing extra); the ~72 % of rays absorbed there never
+//    reach the walk.  Survivors wait on a per-warp shared-memory stack (raw ray, RNG state, chosen
+//    order) until a lane is free.
+//  * A step = refill, phase B, phase A.  Phase B ("diffract"): lanes that stand on a grating draw,
+//    evaluate the efficiencies of ALL orders at once from per-cell quadratic forms (4 FMAs per order
+//    instead of a Jones application per order in a divergent if-chain) and pick the order exactly as
+//    the reference's if/elif chain does; after a __syncwarp() ONE copy of the order application runs
+//    for all of them and for the lanes that just popped a survivor -- one Jones matrix, the chosen
+//    one.  Phase A ("go to the next grating"): every lane whose ray moved asks the ATLAS
+//    (wgrt_region.cuh) -- one L1-resident word answers in-coupler / effective region 1 / 2 / fold
+//    slice / out-coupler slice at once -- resolves what an in-coupler order left pending, and either
+//    stands on a grating, is lost, or free-bounces (GRTF:1049-1052, 1102-1108, 1175-1178) and asks
+//    again in the next step.
 //  * The polarisation state is the un-normalised complex Jones vector (te, tm) plus s = 1/|v|^2.
 //    E_field_cal's cos / sin / hypot / atan2 / wrap (GRTF:136-150) and the per-event normalisation
 //    (GRTF:876-877 ff.) disappear: efficiencies are v^H M v * s with M = J^H J precomputed per cell
