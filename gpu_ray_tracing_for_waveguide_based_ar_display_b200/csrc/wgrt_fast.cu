@@ -887,7 +887,7 @@ __global__ void region_fine_kernel(const __grid_constant__ RegionSet rs) {
 
 // The atlas (wgrt_region.cuh).  Level 1: one thread per cell classifies the cell against all five
 // region sets, looking at every edge; thread 0 publishes the atlas geometry.  Level 2: one block per
-// level-1 cell with a MIXED field re-classifies its 32 x 32 sub-cells for the MIXED sets only.
+// level-1 cell with a MIXED field re-classifies its 64 x 64 sub-cells for the MIXED sets only.
 __device__ __forceinline__ void atlas_bbox(const RegionSet& rs, double& xmin, double& ymin, double& w, double& h) {
   double xmax = -INFINITY, ymax = -INFINITY;
   xmin = INFINITY; ymin = INFINITY;

@@ -163,8 +163,8 @@ __device__ __forceinline__ void region_locate_multi(const Region* const (&regs)[
 //            CELL_NONE (no slice), CELL_AMBIG (MIXED)
 //   bit 31   some field of the word is MIXED
 // Two levels over the union of the sets' bounding boxes: 64 x 64 words (16 KB, L1 resident) and,
-// under level-1 cells with a MIXED field, 32 x 32 finer words each (2048 x 2048 overall, L2
-// resident) in the same format.  A field still MIXED at level 2 defers to that set's own two-level
+// under level-1 cells with a MIXED field, 64 x 64 finer words each (4096 x 4096 overall, the touched
+// part L2 resident) in the same format.  A field still MIXED at level 2 defers to that set's own two-level
 // grid (region_locate above), which ends in the reference's literal edge expressions; every other
 // field is certain for every point that maps to the cell (same safety margin as the per-set grids).
 // Points outside the atlas are outside every ring's bounding box.
