@@ -342,10 +342,10 @@ int host_chunk_target(int64_t num_rays, int num_iter) {
   const int forced = e ? atoi(e) : 0;
   if (forced > 0) return forced;
   // enough chunks to hide the transfers of the first and last one, few enough that a chunk still
-  // fills the GPU: measured on C2 (B200, warp walk, tiles as below) for num_iter = 1: 2 chunks
-  // 24.5 ms, 4: 20.8, 8: 19.6, 16: 18.9; for num_iter = 4: 4: 49.1, 8: 46.5, 16: 48.5
-  const int64_t by_size = num_rays / 7000000;
-  const int64_t cap = num_iter > 1 ? 8 : 16;
+  // fills the GPU: measured on C2 (B200, warp walk) for num_iter = 1: 8 chunks 19.3 ms, 16: 18.7,
+  // 25: 18.2; for num_iter = 4: 4 chunks 41.2 ms, 8: 37.9, 12: 37.4, 16: 38.1, 25: 43.1
+  const int64_t by_size = num_rays / 4500000;
+  const int64_t cap = num_iter > 1 ? 12 : 25;
   return static_cast<int>(by_size < 1 ? 1 : (by_size > cap ? cap : by_size));
 }
 

@@ -204,7 +204,7 @@ int wgrt_trace_fullcolor(const wgrt_problem_t* dev_problem, void* stream);
  * while the next columns are walked); with explicit ray arrays a chunk is a range of rays and the
  * bins come down after the last one.  Rays are independent and own their RNG stream, so the result
  * is bit-identical to num_iter launches over the whole ray set.  WGRT_HOST_CHUNKS=<n> in the
- * environment forces the number of chunks (default: by job size, at most 16).
+ * environment forces the number of chunks (default: by job size, at most 25).
  * `timings_ms`, if not NULL, receives the device-event SPANS {first H2D start -> last H2D end,
  * first launch start -> last launch end, first D2H start -> last D2H end} in milliseconds; the
  * spans overlap, their sum exceeds the wall time.
