@@ -10,9 +10,11 @@ with open(os.path.join(ROOT, "profiles", "r1_bench_final.json"), "w") as f:
     f.write(json.dumps(line) + "\n")
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
 agg = collections.OrderedDict()
+each = collections.defaultdict(list)
 for r in rows:
     name = r[4].split("(")[0].replace("wgrt::<unnamed>::", "").replace("void ", "")
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[-1])
+    each[name].append(float(r[-1]))
 tot = sum(a[1] for a in agg.values())
 out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-reference-gpu",
        "(per-launch times under ncu are serialised and cold-cache; what must agree with bench.py is the SHARE of the step.",
@@ -21,10 +23,13 @@ out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python
        f"{'kernel':45s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'avg ms':>9s}"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k[:45]:45s} {n:8d} {t / 1e6:10.3f} {t / tot * 100:6.2f}% {t / n / 1e6:9.4f}")
-step = sum(agg[k][1] / agg[k][0] for k in agg if k.startswith(("region_", "pick_tile")))
-walk = agg["walk_warp_kernel<0, 0>"][1] / agg["walk_warp_kernel<0, 0>"][0]
-out.append(f"per step: walk_warp {walk / 1e6:.3f} ms of {(walk + step) / 1e6:.3f} ms = {walk / (walk + step) * 100:.2f} % "
-           f"(bench.py: {line['ms_per_step']:.2f} ms per step)")
+import statistics
+step = sum(statistics.median(each[k]) for k in each if k.startswith(("region_", "pick_tile")))
+walk = statistics.median(each["walk_warp_kernel<0, 0>"])
+first = sum(each[k][0] for k in each if k.startswith("region_"))
+out.append(f"per step (median launch of each kernel): walk_warp {walk / 1e6:.3f} ms of {(walk + step) / 1e6:.3f} ms = "
+           f"{walk / (walk + step) * 100:.2f} % (bench.py: {line['ms_per_step']:.2f} ms per step); "
+           f"the region index + atlas build of the FIRST launch of a geometry: {first / 1e6:.2f} ms")
 open(os.path.join(ROOT, "profiles", "r1_launch_shares_final.txt"), "w").write("\n".join(out) + "\n")
 import shutil
 shutil.copy(launches, os.path.join(ROOT, "profiles", "r1_launches_final_bench_steps2.csv"))
