@@ -1,4 +1,6 @@
-// wgrt_fast.cu -- the production ray walk for sm_100a and the region-index builder.
+// wgrt_fast.cu -- the region-index / atlas builder, the evaluation kernels, and the round's FIRST
+// fast walk (CTA per cell).  The production walk is wgrt_walk.cu (warp per cell); the kernel below
+// stays selectable with WGRT_WALK=cta for A/B measurements and runs the same parity suite.
 //
 // Same Monte-Carlo walk as process_rays_kernel_pro_fullColor (GRTF:833-1246), re-designed:
 //
