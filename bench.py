@@ -18,14 +18,21 @@ Printed JSON line (rank 0):
            buffers, copies inside the timed region, every step.  The headline uses the runner
            layout (the engine derives the rays from the start points: uploads LUTs + geometry +
            points, downloads the bins); e2e_dropin is the literal 33-array call (uploads the 12
-           materialised ray arrays too) and e2e_job does the runner's K launches in one call
+           materialised ray arrays too), e2e_job does the runner's K launches in one call, and
+           e2e_eval adds the evaluation's pupil sums with the bins never leaving the device
+           ("full-colour eval wall time").  At N > 1: per rank upload + walk into device bins, ONE
+           NCCL reduce-scatter, D2H of the rank's 1/N slice of the reduced bins
+  reference_numba_cuda   the reference's OWN kernel (Numba -> PTX built from /root/reference in the build
+           container, oracle/_ref) on the same device-resident inputs: the second baseline of
+           BASELINE.json, and the full-size parity check (bins and RNG states bit-equal)
   roofline dominant kernel (walk_warp_kernel) against the FP64 FMA peak measured live on this GPU
            (the path is FP64-issue bound, not HBM bound: SURVEY.md section 8d); roofline_hbm gives
            the algorithmic-bytes view against MEASURED_PEAKS.json
   cpu_baseline   the CPU oracle port (oracle/) on the host cores, bounded sample (rank 0, N = 1)
 Multi-GPU (torchrun): weak scaling -- every rank walks the full workload with its own RNG streams
 (more Monte-Carlo samples per FoV), then ONE NCCL all-reduce of the bin tensor inside the timed
-region.  --impl reference times the CPU oracle port on all host threads (rank 0 only).
+region.  --workload c3_dense_fov_41x41x3x10000 is the PARTITIONED (strong-scaling) arm on BASELINE
+configs[2].  --impl reference times the CPU oracle port on all host threads (rank 0 only).
 """
 from __future__ import annotations
 
