@@ -427,17 +427,14 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
   dp.flags &= ~(WGRT_FLAG_BINS_ZERO | WGRT_FLAG_BINS_DEVICE);
   const size_t ray_b = N * 4, pts_b = static_cast<size_t>(hp->runner_points) * 4;
   const size_t ic_b = fov * hp->C_ic * 16, fc_b = fov * hp->C_fc * 16, oc_b = fov * hp->C_oc * 16;  // per wavelength (and slice)
-  std::vector<Item> items;
-  if (runner) {
-    dp.m = dp.n = dp.lmd_num = dp.te = dp.tm = dp.delta_phase = nullptr;
-    items = {{hp->x, (void**)&dp.x, pts_b, true}, {hp->y, (void**)&dp.y, pts_b, true}};
-  } else {
-    items = {{hp->x, (void**)&dp.x, ray_b, false}, {hp->y, (void**)&dp.y, ray_b, false},
-             {hp->m, (void**)&dp.m, ray_b, false}, {hp->n, (void**)&dp.n, ray_b, false},
-             {hp->lmd_num, (void**)&dp.lmd_num, hp->lmd_num ? ray_b : 0, false},
-             {hp->te, (void**)&dp.te, ray_b, false}, {hp->tm, (void**)&dp.tm, ray_b, false},
-             {hp->delta_phase, (void**)&dp.delta_phase, ray_b, false}};
-  }
+  if (runner) dp.m = dp.n = dp.lmd_num = dp.te = dp.tm = dp.delta_phase = nullptr;
+  std::vector<Item> items =
+      runner ? std::vector<Item>{{hp->x, (void**)&dp.x, pts_b, true}, {hp->y, (void**)&dp.y, pts_b, true}}
+             : std::vector<Item>{{hp->x, (void**)&dp.x, ray_b, false}, {hp->y, (void**)&dp.y, ray_b, false},
+                                 {hp->m, (void**)&dp.m, ray_b, false}, {hp->n, (void**)&dp.n, ray_b, false},
+                                 {hp->lmd_num, (void**)&dp.lmd_num, hp->lmd_num ? ray_b : 0, false},
+                                 {hp->te, (void**)&dp.te, ray_b, false}, {hp->tm, (void**)&dp.tm, ray_b, false},
+                                 {hp->delta_phase, (void**)&dp.delta_phase, ray_b, false}};
   const size_t n_ray_items = items.size();
   items.push_back({nullptr, (void**)&dp.rng_states, ray_b, false});
   const bool tables_upfront = !runner;   // runner layout: the per-cell tables go up column range by column range
