@@ -86,24 +86,29 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_enter, self.t_exit = index, [], None, 0.0, float("inf")
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()                     # nvidia-smi needs ~0.1 s to start: the timed region is shorter than that
+            while not self.rows and time.time() - t0 < 2.0:
+                time.sleep(0.005)
+            self.t_enter = time.time()           # rows that arrived before now were sampled before the timed region
         except OSError:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([c.strip() for c in line.split(",")] + [time.time()])
 
     def __exit__(self, *exc):
+        self.t_exit = time.time()
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -114,7 +119,12 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        # samples taken DURING the timed region (arrival time within it, 25 ms slack for the pipe); a region
+        # shorter than the 20 ms sampling period may hold none: then the first sample after it started
+        rows = [r for r in self.rows if self.t_enter <= r[-1] <= self.t_exit + 0.025]
+        if not rows:
+            rows = [r for r in self.rows if r[-1] >= self.t_enter][:1] or self.rows[-1:]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -375,6 +385,8 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         launch(*dev_args)
+    if world > 1:
+        dist.all_reduce(eb_t)        # NCCL warm-up at the timed message size (first use sets up its channels)
     torch.cuda.synchronize()
     eb_t.zero_()
     rng_saved = rng_t.clone()
@@ -659,34 +671,60 @@ def main():
 
 def e2e_multi_gpu(args, scene, rpc, N, world, rank, stream):
     """End to end on N GPUs, the way a multi-GPU job runs (north_star: "one NCCL reduce of the bin tensors
-    over NVLink at the end"): every step each rank uploads its inputs from pinned host memory (LUTs,
-    geometry, start points -- wgrt_trace_fullcolor_host pipelines the upload under the walk), walks the
-    full C2 ray set with its own RNG streams into a DEVICE bin tensor (WGRT_FLAG_BINS_DEVICE), then ONE
-    NCCL reduce-scatter sums the bins over the ranks and each rank downloads its 1/N slice of the reduced
-    tensor to pinned host memory (N x 864 MB through the hosts's PCIe would be the bottleneck otherwise:
-    measured 57 ms per step at N = 4 against 19 ms at N = 1)."""
+    over NVLink at the end").  Every step, from pinned host memory to pinned host memory:
+      1. the job's inputs enter the node ONCE: each rank uploads 1/N of every RCWA / geometry table over its
+         own PCIe link and an NCCL all-gather over NVLink completes the tables on every GPU (N ranks
+         uploading the same 360 MB through one host were measured host bound: 27.7 ms per step at N = 8);
+      2. each rank seeds its own RNG streams on the device (RUN:158 with a rank offset) and walks the full
+         C2 ray set through the reference-shaped kernel object (runner layout) into a device bin tensor;
+      3. ONE NCCL reduce-scatter sums the bins over the ranks and each rank downloads its 1/N slice of
+         the reduced tensor (N x 864 MB of bins through the host: 57 ms per step at N = 4)."""
     import torch
     import torch.distributed as dist
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
-    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, runner, synthetic_inputs as si
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, synthetic_inputs as si
     pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2024 + 1)
-    keep, geom_p, luts_p = [], {}, {}
-    for src, dst in ((scene.geom, geom_p), (scene.luts, luts_p)):
-        for k, a in src.items():
-            tpin, view = pinned_like(a)
-            keep.append(tpin); dst[k] = view
+    tables = dict(scene.geom); tables.update(scene.luts)
+    tables["px"] = pts[:, 0].astype(np.float32); tables["py"] = pts[:, 1].astype(np.float32)
+    host, dev, alias, sharded = {}, {}, {}, {}
+    h2d = 0
+    for k, a in tables.items():
+        tpin, _ = pinned_like(a)
+        host[k] = tpin.view(-1)
+        dev[k] = torch.empty_like(host[k], device="cuda")
+        alias[k] = GRTF._TorchAlias(dev[k], a.shape, a.dtype)
+        sharded[k] = host[k].numel() % world == 0 and a.nbytes >= (1 << 20)
+        h2d += a.nbytes // world if sharded[k] else a.nbytes
     shape = scene.eb_shape
     numel = int(np.prod(shape))
     assert numel % world == 0
     eb_dev = torch.zeros(numel, dtype=torch.float32, device="cuda")
     eb_alias = GRTF._TorchAlias(eb_dev, shape, np.float32)
+    rng_dev = torch.empty(N, dtype=torch.int32, device="cuda")
+    rng_alias = GRTF._TorchAlias(rng_dev, (N,), np.uint32)
     part_dev = torch.empty(numel // world, dtype=torch.float32, device="cuda")
     part_host = torch.empty(numel // world, dtype=torch.float32).pin_memory()
-    h2d = sum(a.nbytes for a in list(geom_p.values()) + list(luts_p.values())) + pts.shape[0] * 8
+    golden = int(np.int64(0x9E3779B9) - (1 << 32))                      # the multiplier as a wrapping int32
+    kern = GRTF.process_rays_kernel_pro_fullColor.configured(ray_index_base=rank * N).runner_layout(rpc // 2, N)
+
+    def launch_args():
+        g = alias
+        return [g["px"], g["py"]] + [None] * 10 + [rng_alias, g["IC"], g["FC"], g["FC_offset"], g["OC"], g["OC_offset"],
+                scene.n_g, g["eff_reg1"], g["eff_reg2"], g["eff_reg_FOV"], g["eff_reg_FOV_range"], g["lut_ic1"], g["lut_ic2"],
+                g["lut_ic3"], g["lut_fc1"], g["lut_fc2"], g["lut_oc1"], g["lut_oc2"], g["lut_TIR"], g["lut_gap"], eb_alias]
 
     def step():
-        runner.trace_full_color(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1, matrix_EB=eb_alias,
-                                bins_start_zero=True, rng_seed_offset=rank * N)
+        for k in host:
+            if sharded[k]:
+                n = host[k].numel() // world
+                dev[k][rank * n:(rank + 1) * n].copy_(host[k][rank * n:(rank + 1) * n], non_blocking=True)
+                dist.all_gather_into_tensor(dev[k], dev[k][rank * n:(rank + 1) * n])
+            else:
+                dev[k].copy_(host[k], non_blocking=True)
+        torch.arange(rank * N + 1, rank * N + N + 1, dtype=torch.int32, device="cuda", out=rng_dev)
+        rng_dev.mul_(golden)                                             # RUN:158, wrapping 32-bit product
+        eb_dev.zero_()
+        kern[1, 256, stream](*launch_args())
         dist.reduce_scatter_tensor(part_dev, eb_dev)
         part_host.copy_(part_dev, non_blocking=True)
         torch.cuda.synchronize()
@@ -700,32 +738,26 @@ def e2e_multi_gpu(args, scene, rpc, N, world, rank, stream):
     tw = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     wall = float(tw.item())
-    # bounces of one such job on this rank: replay it device resident with counters, same seeds
-    _capi.reset_counters()
-    def to_dev(a):
-        v = a.view(np.float64) if a.dtype == np.complex128 else a
-        t = torch.from_numpy(np.ascontiguousarray(v.view(np.int32) if v.dtype == np.uint32 else v)).cuda()
-        return GRTF._TorchAlias(t, a.shape, a.dtype)
-    g = {k: to_dev(v) for k, v in scene.geom.items()}
-    lt = {k: to_dev(v) for k, v in scene.luts.items()}
-    d_rng = to_dev(si.initial_rng_states(N, offset=rank * N))
+    # check: the same job walked from explicitly seeded host states, counters on, then summed over the ranks
+    d_rng = torch.from_numpy(si.initial_rng_states(N, offset=rank * N).view(np.int32)).cuda()
+    seeds_ok = bool(torch.equal(torch.arange(rank * N + 1, rank * N + N + 1, dtype=torch.int32, device="cuda").mul_(golden), d_rng))
     chk = torch.zeros(numel, dtype=torch.float32, device="cuda")
-    ck = GRTF.process_rays_kernel_pro_fullColor.configured(counters=True).runner_layout(rpc // 2, N)
-    ck[1, 256, stream](to_dev(pts[:, 0].astype(np.float32)), to_dev(pts[:, 1].astype(np.float32)), *([None] * 10), d_rng,
-                       g["IC"], g["FC"], g["FC_offset"], g["OC"], g["OC_offset"], scene.n_g, g["eff_reg1"], g["eff_reg2"],
-                       g["eff_reg_FOV"], g["eff_reg_FOV_range"], lt["lut_ic1"], lt["lut_ic2"], lt["lut_ic3"], lt["lut_fc1"],
-                       lt["lut_fc2"], lt["lut_oc1"], lt["lut_oc2"], g["lut_TIR"], g["lut_gap"],
-                       GRTF._TorchAlias(chk, shape, np.float32))
+    a = launch_args()
+    a[12] = GRTF._TorchAlias(d_rng, (N,), np.uint32)
+    a[32] = GRTF._TorchAlias(chk, shape, np.float32)
+    _capi.reset_counters()
+    kern.configured(counters=True)[1, 256, stream](*a)
     c1 = _capi.read_counters()
-    dist.all_reduce(chk)                                        # what the reduce-scatter must have produced
+    dist.all_reduce(chk)
     n = numel // world
-    same = bool(torch.equal(chk[rank * n:(rank + 1) * n].cpu(), part_host))
+    same = seeds_ok and bool(torch.equal(chk[rank * n:(rank + 1) * n].cpu(), part_host))
     tv = torch.tensor([float(c1["bounces"]), 1.0 if same else 0.0], device="cuda", dtype=torch.float64)
     dist.all_reduce(tv)
     return {"value": float(tv[0].item()) * args.steps / wall, "unit": UNIT, "ms_per_step": wall / max(args.steps, 1) * 1e3,
             "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(numel * 4),
-            "api": "per rank: runner.trace_full_color -> wgrt_trace_fullcolor_host (runner layout, WGRT_FLAG_BINS_DEVICE, "
-                   "rank-specific seeds), then one NCCL reduce-scatter of the bins and a D2H of the rank's 1/N slice",
+            "api": "per rank: H2D of 1/N of every table + NCCL all-gather, device-side seeding, "
+                   "GRTF.process_rays_kernel_pro_fullColor (runner layout) into device bins, one NCCL reduce-scatter, "
+                   "D2H of the rank's 1/N slice of the reduced bins",
             "reduced_slices_bit_equal_to_device_run": bool(tv[1].item() == world)}
 
 
