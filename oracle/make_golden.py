@@ -62,13 +62,25 @@ SCENES = {
     "walk_deep": dict(num_FOV_x=3, num_FOV_y=3, num_rays_per_FoV=400, seed=23, lmd_subset=None, num_iter=1,
                       eff=dict(incouple=0.9, incouple_m1=0.08, ic_zero=0.9, ic_cross=0.05, fc_zero=0.7,
                                fc_turn=0.28, oc_zero=0.85, oc_cross=0.06, outcouple=0.06)),
+    # BASELINE config 4: high-resolution eyebox bins (320 x 480 per FoV cell)
+    "walk_fine": dict(num_FOV_x=3, num_FOV_y=3, num_rays_per_FoV=240, seed=31, lmd_subset=None, num_iter=1,
+                      eb=(320, 480),
+                      eff=dict(incouple=0.9, ic_zero=0.95, fc_zero=0.8, fc_turn=0.15, outcouple=0.1)),
+    # BASELINE config 5: thin plate, wide FoV, 15 fold slices, strong turn orders (long, branching walks)
+    "walk_thin": dict(num_FOV_x=3, num_FOV_y=2, num_rays_per_FoV=300, seed=37, lmd_subset=None, num_iter=1,
+                      design=dict(t=0.3, num_FC=15, fov_x_deg=24.0),
+                      eff=dict(incouple=0.9, incouple_m1=0.08, ic_zero=0.9, ic_cross=0.05, fc_zero=0.6, fc_turn=0.3,
+                               oc_zero=0.85, oc_cross=0.06, outcouple=0.05)),
 }
 
 
 def scene_from_recipe(r):
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200.synthetic_inputs import make_scene
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.couplers_coor import WaveguideDesign
+    design = WaveguideDesign(**r["design"]) if r.get("design") else None
     return make_scene(r["num_FOV_x"], r["num_FOV_y"], r["num_rays_per_FoV"], seed=r["seed"],
-                      lmd_subset=r.get("lmd_subset"), eff=r.get("eff"))
+                      lmd_subset=r.get("lmd_subset"), eff=r.get("eff"), eb=tuple(r.get("eb", (80, 120))),
+                      design=design)
 
 
 def input_digest(scene) -> str:

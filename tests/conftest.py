@@ -22,8 +22,13 @@ def load_golden_walk(name):
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import synthetic_inputs as si
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     recipe = ast.literal_eval(str(g["recipe"]))
+    design = None
+    if recipe.get("design"):
+        from gpu_ray_tracing_for_waveguide_based_ar_display_b200.couplers_coor import WaveguideDesign
+        design = WaveguideDesign(**recipe["design"])
     scene = si.make_scene(recipe["num_FOV_x"], recipe["num_FOV_y"], recipe["num_rays_per_FoV"],
-                          seed=recipe["seed"], lmd_subset=recipe.get("lmd_subset"), eff=recipe.get("eff"))
+                          seed=recipe["seed"], lmd_subset=recipe.get("lmd_subset"), eff=recipe.get("eff"),
+                          eb=tuple(recipe.get("eb", (80, 120))), design=design)
     return scene, g
 
 

@@ -43,7 +43,7 @@ def assert_same(a, b, what):
 
 
 # ---------------------------------------------------------------------------- golden fixtures
-@pytest.mark.parametrize("name", ["walk_small", "walk_c1", "walk_mid", "walk_deep"])
+@pytest.mark.parametrize("name", ["walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin"])
 @pytest.mark.parametrize("mode", ["fast", "strict"])
 def test_golden_fixture(name, mode):
     scene, g = load_golden_walk(name)

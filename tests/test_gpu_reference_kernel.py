@@ -61,7 +61,7 @@ def assert_same(a, b, what):
 def test_reference_kernel_reproduces_simulator_golden():
     """The PTX really is the reference: it reproduces the fixtures its CPU simulator produced."""
     from conftest import golden_bins, load_golden_walk
-    for name in ("walk_small", "walk_c1", "walk_mid", "walk_deep"):
+    for name in ("walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin"):
         scene, g = load_golden_walk(name)
         got = run_reference(scene, int(g["num_iter"]))
         assert_same(got, (golden_bins(g), g["rng_states"]), name)

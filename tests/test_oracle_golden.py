@@ -7,7 +7,7 @@ import pytest
 
 from conftest import GOLDEN, golden_bins, input_digest, load_golden_walk
 
-WALKS = ["walk_small", "walk_c1", "walk_mid", "walk_deep"]
+WALKS = ["walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin"]
 
 
 @pytest.mark.parametrize("name", WALKS)
