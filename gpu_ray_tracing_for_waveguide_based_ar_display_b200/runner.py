@@ -126,3 +126,51 @@ def trace_and_evaluate(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: flo
         out["delta_e"], out["U_fov"], out["U_EB"], out["output_image"] = EV.evaluation(
             shape_only, matrix_eye_perceive=out["matrix_eye_perceive"])
     return out
+
+
+def main(argv=None) -> int:
+    """``python -m gpu_ray_tracing_for_waveguide_based_ar_display_b200.runner`` -- the reference runner script
+    (gpu_ray_tracing_pro_fullColor.py:11-210) end to end on this engine: design -> LUTs -> start points ->
+    ``num_iter`` launches -> efficiencies and evaluation, printed like the reference prints them.  The RCWA
+    LUT files of the reference are not redistributable / reachable, so synthetic LUTs of the same shapes
+    stand in unless ``--lut-dir`` points at a directory holding the reference's seven ``lut_*_fullColor.npy``."""
+    import argparse
+    import os
+    import time
+    from . import GPU_ray_tracing_functions as GRTF
+    from . import synthetic_inputs as si
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--fov", type=int, nargs=2, default=(100, 75), metavar=("X", "Y"))      # RUN:16-17
+    ap.add_argument("--rays-per-fov", type=int, default=5000)                               # RUN:61
+    ap.add_argument("--num-iter", type=int, default=4)                                      # RUN:60
+    ap.add_argument("--eyebox-bins", type=int, nargs=2, default=(80, 120), metavar=("Y", "X"))  # RUN:37
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--lut-dir", default=None)
+    a = ap.parse_args(argv)
+    print("=" * 60 + f"\n{'GPU Ray Tracing Simulation (B200 engine)':^60}\n" + "=" * 60)
+    scene = si.make_scene(a.fov[0], a.fov[1], 2, eb=tuple(a.eyebox_bins), seed=a.seed, build_rays=False)
+    luts = scene.luts
+    if a.lut_dir:
+        luts = {k: np.ascontiguousarray(np.load(os.path.join(a.lut_dir, f"{k}_fullColor.npy")).astype(np.complex128))
+                for k in ("lut_ic1", "lut_ic2", "lut_ic3", "lut_fc1", "lut_fc2", "lut_oc1", "lut_oc2")}
+    points = GRTF.generate_points_in_polygon(scene.geom["IC"], a.rays_per_fov // 2, rng=np.random.default_rng(a.seed))
+    num_rays = a.fov[0] * a.fov[1] * 3 * a.rays_per_fov
+    print(f"Rays per launch : {num_rays:,}   launches : {a.num_iter}")
+    t0 = time.perf_counter()
+    res = trace_and_evaluate(points, scene.geom, scene.n_g, luts, a.rays_per_fov, num_iter=a.num_iter,
+                             eb=tuple(a.eyebox_bins))
+    dt = time.perf_counter() - t0
+    print(f"Number of rays traced : {num_rays * a.num_iter:,}")
+    print(f"Trace + evaluation time : {dt:.3f} s")
+    eff = res["efficiency"]
+    print("Efficiency (Red)     : {:8.3f} %".format(eff[2] * 100))
+    print("Efficiency (Green)   : {:8.3f} %".format(eff[1] * 100))
+    print("Efficiency (Blue)    : {:8.3f} %".format(eff[0] * 100))
+    print("Color dispersion     : {:8.2f}".format(res["delta_e"]))
+    print("FoV uniformity       : {:8.2f} %".format(res["U_fov"] * 100))
+    print("Eyebox uniformity    : {:8.2f} %".format(res["U_EB"] * 100))
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

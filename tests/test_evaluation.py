@@ -112,3 +112,13 @@ def test_trace_and_evaluate_keeps_bins_on_the_device():
     np.testing.assert_allclose(got["output_image"], img, rtol=1e-5, atol=1e-6)
     eff = EV.efficiency_per_colour(EB, scene.eb_shape[0] * 6 * 5 * rpc, it)
     np.testing.assert_allclose(got["efficiency"], eff, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_runner_main_prints_the_reference_report(capsys):
+    """The runner script equivalent (RUN:11-210) end to end at a small size."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
+    assert runner.main(["--fov", "6", "5", "--rays-per-fov", "400", "--num-iter", "2"]) == 0
+    out = capsys.readouterr().out
+    for key in ("Number of rays traced : 72,000", "Efficiency (Red)", "Color dispersion", "FoV uniformity", "Eyebox uniformity"):
+        assert key in out, out
