@@ -712,6 +712,10 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
                     : (implicit ? walk_warp_kernel<false, true> : walk_warp_kernel<false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
+  if (const char* e = getenv("WGRT_SMEM_CARVEOUT")) {   // experiment: percent of the 228 KB given to shared memory
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
+    if (err != cudaSuccess) return err;
+  }
   int per_sm = 0;
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
   if (err != cudaSuccess) return err;
