@@ -283,7 +283,7 @@ def partitioned_arm(args, nx, ny, rpc, eb):
     for _ in range(max(args.warmup, 3)):
         launch(*a)
     if world > 1:
-        dist.all_reduce(ebt._t)                                   # NCCL warm-up
+        multi_gpu.reduce_bins(ebt._t)                             # NCCL warm-up
     torch.cuda.synchronize()
     rng._t.copy_(rng0); ebt._t.zero_()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,7 +293,7 @@ def partitioned_arm(args, nx, ny, rpc, eb):
         for _ in range(args.steps):
             launch(*a)
         if world > 1:
-            dist.all_reduce(ebt._t)
+            multi_gpu.reduce_bins(ebt._t)
         ev1.record(stream)
         barrier()
     t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
@@ -347,7 +347,7 @@ def main():
     import torch
     import torch.distributed as dist
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
-    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, synthetic_inputs as si
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, multi_gpu, synthetic_inputs as si
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -386,7 +386,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         launch(*dev_args)
     if world > 1:
-        dist.all_reduce(eb_t)        # NCCL warm-up at the timed message size (first use sets up its channels)
+        multi_gpu.reduce_bins(eb_t)  # NCCL warm-up at the timed message size (first use sets up its channels)
     torch.cuda.synchronize()
     eb_t.zero_()
     rng_saved = rng_t.clone()
@@ -400,7 +400,7 @@ def main():
             launch(*dev_args)
             ev[k + 1].record(stream)
         if world > 1:
-            dist.all_reduce(eb_t)
+            multi_gpu.reduce_bins(eb_t)     # one NCCL all-reduce, as uint8 when that is exact (multi_gpu.py)
         ev[args.steps + 1].record(stream)
         barrier()
     rng_final = rng_t.clone()
@@ -437,7 +437,7 @@ def main():
         "config": {"workload": args.workload, "num_FOV_x": nx, "num_FOV_y": ny, "wavelengths": 3,
                    "rays_per_FoV": rpc, "rays_per_launch_per_gpu": N, "eyebox_bins": list(eb),
                    "l2_policy": "inputs (4.1 GB of ray state per launch) exceed the 126 MB L2; no flush needed",
-                   "partition": "replicated design, rank-specific RNG streams, one NCCL all-reduce of the bins"
+                   "partition": "replicated design, rank-specific RNG streams, one NCCL all-reduce of the bins (as uint8 when exact)"
                    if world > 1 else "single GPU"},
         "rays_per_s": rays_all / (total_ms_max * 1e-3),
         "full_colour_wall_ms": total_ms_max,

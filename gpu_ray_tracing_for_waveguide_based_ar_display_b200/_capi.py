@@ -63,7 +63,7 @@ EXPORTED_SYMBOLS = (
     "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host", "wgrt_trace_evaluate_host",
     "wgrt_counters_read", "wgrt_counters_reset",
     "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
-    "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host",
+    "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host", "wgrt_bins_pack_u8", "wgrt_bins_unpack_u8",
 )
 
 
@@ -90,6 +90,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_trace_fullcolor.argtypes = [C.POINTER(WgrtProblem), C.c_void_p]
     lib.wgrt_trace_fullcolor_host.restype = C.c_int
     lib.wgrt_trace_fullcolor_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_void_p]
+    lib.wgrt_bins_pack_u8.restype = C.c_int
+    lib.wgrt_bins_pack_u8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wgrt_bins_unpack_u8.restype = C.c_int
+    lib.wgrt_bins_unpack_u8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wgrt_trace_evaluate_host.restype = C.c_int
     lib.wgrt_trace_evaluate_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]

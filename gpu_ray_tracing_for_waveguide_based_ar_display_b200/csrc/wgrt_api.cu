@@ -792,6 +792,30 @@ int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf,
   return WGRT_OK;
 }
 
+int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!dev_bins || !dev_out || !dev_stats || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(dev_bins) & 15) ||
+      (reinterpret_cast<uintptr_t>(dev_out) & 3))
+    return fail(WGRT_ERR_INVALID, "bins_pack_u8: n must be a multiple of 4, bins 16-byte and out 4-byte aligned");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(launch_bins_pack_u8(dev_bins, n, dev_out, dev_stats, w->num_sms, static_cast<cudaStream_t>(stream)));
+  return WGRT_OK;
+}
+
+int wgrt_bins_unpack_u8(const uint8_t* dev_in, int64_t n, float* dev_bins, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!dev_bins || !dev_in || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(dev_bins) & 15) ||
+      (reinterpret_cast<uintptr_t>(dev_in) & 3))
+    return fail(WGRT_ERR_INVALID, "bins_unpack_u8: n must be a multiple of 4, bins 16-byte and in 4-byte aligned");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(launch_bins_unpack_u8(dev_in, n, dev_bins, w->num_sms, static_cast<cudaStream_t>(stream)));
+  return WGRT_OK;
+}
+
 int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
                               int mask_size, int step_y, int step_x, float* out, float* cell_sums) {
   if (!EB || EBy <= 0 || EBx <= 0 || mask_size <= 0 || step_y <= 0 || step_x <= 0)

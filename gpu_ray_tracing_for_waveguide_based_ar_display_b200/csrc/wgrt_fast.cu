@@ -1114,6 +1114,44 @@ __global__ void __launch_bounds__(256) pupil_window_kernel(const float* __restri
   }
 }
 
+// Bin tensor <-> uint8 for the exact narrow all-reduce (multi_gpu.reduce_bins): one pass that converts,
+// and reports the largest entry and whether any entry is not an integer in [0, 255].
+__global__ void __launch_bounds__(256) bins_pack_u8_kernel(const float4* __restrict__ in, int64_t n4, uint32_t* __restrict__ out,
+                                                           unsigned* __restrict__ stats) {
+  float vmax = 0.f;
+  bool bad = false;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(in + i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float c = fminf(fmaxf(f[k], 0.f), 255.f);
+      const uint32_t q = static_cast<uint32_t>(c);
+      bad |= !(static_cast<float>(q) == f[k]);        // negative, > 255, fractional or NaN
+      vmax = fmaxf(vmax, c);
+      w |= q << (8 * k);
+    }
+    out[i] = w;
+  }
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(FULL_MASK, vmax, o));
+  const unsigned any_bad = __ballot_sync(FULL_MASK, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(stats, __float_as_uint(vmax));          // non-negative floats order like their bit patterns
+    if (any_bad) atomicOr(stats + 1, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) bins_unpack_u8_kernel(const uint32_t* __restrict__ in, int64_t n4, float4* __restrict__ out) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t w = __ldg(in + i);
+    out[i] = make_float4(static_cast<float>(w & 255u), static_cast<float>((w >> 8) & 255u),
+                         static_cast<float>((w >> 16) & 255u), static_cast<float>(w >> 24));
+  }
+}
+
 // per-cell totals straight from global memory (tiles of any size)
 __global__ void __launch_bounds__(256) cell_sums_kernel(const float* __restrict__ EB, int64_t npix, float* __restrict__ cell_sums) {
   const float* src = EB + static_cast<int64_t>(blockIdx.x) * npix;
@@ -1184,6 +1222,21 @@ cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const doub
   const unsigned blocks = static_cast<unsigned>((n + 127) / 128);
   if (counters) locate_grid_kernel<true><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters, via_atlas);
   else locate_grid_kernel<false><<<blocks, 128, 0, s>>>(rs, region, px, py, n, out, counters, via_atlas);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, int num_sms, cudaStream_t s) {
+  cudaError_t err = cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned), s);
+  if (err != cudaSuccess || n == 0) return err;
+  bins_pack_u8_kernel<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(bins), n / 4,
+                                                  reinterpret_cast<uint32_t*>(out), stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bins_unpack_u8(const uint8_t* in, int64_t n, float* bins, int num_sms, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  bins_unpack_u8_kernel<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(in), n / 4,
+                                                    reinterpret_cast<float4*>(bins));
   return cudaGetLastError();
 }
 

@@ -276,6 +276,17 @@ int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf,
 int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
                               int mask_size, int step_y, int step_x, float* out, float* cell_sums);
 
+/*
+ * Multi-GPU reduce of the bins (new; the reference is single GPU).  The bins are small integer counts in
+ * float32; summing them over the ranks as uint8 is exact whenever world_size * (largest entry) <= 255 and
+ * moves a quarter of the bytes over NVLink.  wgrt_bins_pack_u8 converts n device floats (n % 4 == 0) to
+ * uint8 and writes stats[0] = bit pattern of the largest entry (as float), stats[1] = 1 if any entry is
+ * not an integer in [0, 255]; wgrt_bins_unpack_u8 converts back.  Asynchronous on `stream`.  The decision
+ * and the NCCL call are the caller's (multi_gpu.reduce_bins).
+ */
+int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, void* stream);
+int wgrt_bins_unpack_u8(const uint8_t* dev_in, int64_t n, float* dev_bins, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

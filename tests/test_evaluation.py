@@ -122,3 +122,29 @@ def test_runner_main_prints_the_reference_report(capsys):
     out = capsys.readouterr().out
     for key in ("Number of rays traced : 72,000", "Efficiency (Red)", "Color dispersion", "FoV uniformity", "Eyebox uniformity"):
         assert key in out, out
+
+
+@pytest.mark.gpu
+def test_bins_pack_unpack_u8():
+    """wgrt_bins_pack_u8 / _unpack_u8 (the exact narrow all-reduce of multi_gpu.reduce_bins)."""
+    import ctypes as C
+    import torch
+    lib = EV._capi.load_library()
+    rs = np.random.default_rng(8)
+    for make, want_bad in ((lambda: rs.integers(0, 256, 4096 * 7).astype(np.float32), 0),
+                           (lambda: rs.integers(0, 9, 1024).astype(np.float32) + np.float32(0.5) * (np.arange(1024) == 77), 1),
+                           (lambda: np.where(np.arange(2048) == 5, 256.0, 1.0).astype(np.float32), 1),
+                           (lambda: np.where(np.arange(2048) == 9, -1.0, 2.0).astype(np.float32), 1)):
+        a = make()
+        t = torch.from_numpy(a).cuda()
+        q = torch.empty(a.size, dtype=torch.uint8, device="cuda"); st = torch.empty(2, dtype=torch.int32, device="cuda")
+        EV._capi.check(lib.wgrt_bins_pack_u8(C.c_void_p(t.data_ptr()), a.size, C.c_void_p(q.data_ptr()),
+                                             C.c_void_p(st.data_ptr()), None), lib)
+        torch.cuda.synchronize()
+        vmax = st[0:1].view(torch.float32).item()
+        assert int(st[1].item()) == want_bad
+        if not want_bad:
+            assert vmax == a.max() and np.array_equal(q.cpu().numpy(), a.astype(np.uint8))
+            back = torch.zeros_like(t)
+            EV._capi.check(lib.wgrt_bins_unpack_u8(C.c_void_p(q.data_ptr()), a.size, C.c_void_p(back.data_ptr()), None), lib)
+            assert torch.equal(back, t)

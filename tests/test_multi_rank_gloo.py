@@ -50,6 +50,37 @@ def test_partitioned_run_equals_single_process(world, tmp_path, oracle):
     assert EB1.sum() > 0
 
 
+def _reduce_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import multi_gpu
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rs = np.random.default_rng(100 + rank)
+    cases = {"counts": rs.integers(0, 40, size=(3, 4, 5, 8, 12)).astype(np.float32),        # narrow path (3 * 39 <= 255)
+             "large": rs.integers(0, 120, size=(2, 3, 3, 8, 12)).astype(np.float32),         # 3 * 119 > 255: float32 path
+             "fractional": rs.random((2, 2, 2, 8, 12)).astype(np.float32)}                   # not counts: float32 path
+    if rank == 1:
+        cases["counts"][0, 0, 0, 0, 0] = 85.0                                                # 3 * 85 = 255: still narrow
+    out = {}
+    for k, a in cases.items():
+        ref = torch.from_numpy(a.copy()); dist.all_reduce(ref)
+        got = a.copy(); multi_gpu.reduce_bins(got)
+        plain = a.copy(); multi_gpu.reduce_bins(plain, narrow=False)
+        out[k] = bool(np.array_equal(got, ref.numpy()) and np.array_equal(plain, ref.numpy()))
+    np.savez(os.path.join(out_dir, f"reduce{rank}.npz"), **out)
+    dist.destroy_process_group()
+
+
+def test_reduce_bins_narrow_path_is_exact(tmp_path):
+    """The uint8 all-reduce of the bins is used only when it is exact, and then gives the float32 result."""
+    world = 3
+    mp.spawn(_reduce_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        d = np.load(tmp_path / f"reduce{r}.npz")
+        assert all(bool(d[k]) for k in ("counts", "large", "fractional")), {k: bool(d[k]) for k in d.files}
+
+
 def test_cell_range_partition():
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200.multi_gpu import cell_range
     for n in (0, 1, 7, 22500):
