@@ -51,8 +51,8 @@ def reduce_bins(matrix_EB, group=None, narrow: bool = True):
     or a NumPy array (wrapped without copying).
 
     The bins are small integer counts stored in float32 (one deposit adds exactly 1.0,
-    GPU_ray_tracing_functions.py:1168).  With ``narrow`` the all-reduce moves them as uint8 whenever
-    that is EXACT -- every entry a non-negative integer and ``world_size * (largest entry over all
+    GPU_ray_tracing_functions.py:1168).  With ``narrow`` the all-reduce moves them as uint8 (four to an
+    int32 word) whenever that is EXACT -- every entry a non-negative integer and ``world_size * (largest entry over all
     ranks) <= 255``, so that no partial sum can wrap -- which is a quarter of the bytes over
     NVLink (864 MB -> 216 MB at the default size).  Anything else goes as float32, as before.  The
     result is bit-identical either way."""
@@ -81,7 +81,13 @@ def reduce_bins(matrix_EB, group=None, narrow: bool = True):
             stat = torch.stack((t.max().to(torch.float32), 1.0 - exact.to(torch.float32)))
         dist.all_reduce(stat, op=dist.ReduceOp.MAX, group=group)     # same decision on every rank
         if float(stat[1]) == 0.0 and float(stat[0]) * world <= 255.0:
-            dist.all_reduce(q, op=dist.ReduceOp.SUM, group=group)
+            # four counts per int32 word: byte sums stay <= 255, so no carry crosses a byte and the int32
+            # SUM is the uint8 SUM -- on the dtype NCCL's fast paths (NVLS, tree) are built for
+            packed = q.view(-1)
+            if packed.numel() % 4 == 0:
+                dist.all_reduce(packed.view(torch.int32), op=dist.ReduceOp.SUM, group=group)
+            else:
+                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
             if on_gpu:
                 _capi.check(lib.wgrt_bins_unpack_u8(C.c_void_p(q.data_ptr()), t.numel(), C.c_void_p(t.data_ptr()),
                                                     C.c_void_p(stream)), lib)
