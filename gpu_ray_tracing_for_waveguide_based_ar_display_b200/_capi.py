@@ -91,7 +91,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_trace_fullcolor_host.restype = C.c_int
     lib.wgrt_trace_fullcolor_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_void_p]
     lib.wgrt_bins_pack_u8.restype = C.c_int
-    lib.wgrt_bins_pack_u8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wgrt_bins_pack_u8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]
     lib.wgrt_bins_unpack_u8.restype = C.c_int
     lib.wgrt_bins_unpack_u8.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.wgrt_trace_evaluate_host.restype = C.c_int

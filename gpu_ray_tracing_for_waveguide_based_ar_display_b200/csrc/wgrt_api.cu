@@ -792,7 +792,7 @@ int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf,
   return WGRT_OK;
 }
 
-int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, void* stream) {
+int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, float limit, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!dev_bins || !dev_out || !dev_stats || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(dev_bins) & 15) ||
       (reinterpret_cast<uintptr_t>(dev_out) & 3))
@@ -800,7 +800,8 @@ int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32
   Workspace* w = nullptr;
   int rc = get_workspace(&w);
   if (rc != WGRT_OK) return rc;
-  CUDA_TRY(launch_bins_pack_u8(dev_bins, n, dev_out, dev_stats, w->num_sms, static_cast<cudaStream_t>(stream)));
+  if (!(limit >= 0.f && limit <= 255.f)) return fail(WGRT_ERR_INVALID, "bins_pack_u8: limit must be within [0, 255]");
+  CUDA_TRY(launch_bins_pack_u8(dev_bins, n, dev_out, dev_stats, limit, w->num_sms, static_cast<cudaStream_t>(stream)));
   return WGRT_OK;
 }
 

@@ -194,7 +194,8 @@ cudaError_t launch_debug_efield(const double* ete, const double* etm, const doub
 cudaError_t launch_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last, cudaStream_t s);
 cudaError_t launch_seed_rng(uint32_t* states, int64_t n, int64_t first_index, cudaStream_t s);
 cudaError_t launch_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflops);
-cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, int num_sms, cudaStream_t s);
+cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, float limit, int num_sms,
+                                cudaStream_t s);
 cudaError_t launch_bins_unpack_u8(const uint8_t* in, int64_t n, float* bins, int num_sms, cudaStream_t s);
 cudaError_t launch_pupil_sums(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
                               int mask, int step_y, int step_x, float* out, float* cell_sums, cudaStream_t s);

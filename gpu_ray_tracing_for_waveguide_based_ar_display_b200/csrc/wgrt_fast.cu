@@ -1117,7 +1117,7 @@ __global__ void __launch_bounds__(256) pupil_window_kernel(const float* __restri
 // Bin tensor <-> uint8 for the exact narrow all-reduce (multi_gpu.reduce_bins): one pass that converts,
 // and reports the largest entry and whether any entry is not an integer in [0, 255].
 __global__ void __launch_bounds__(256) bins_pack_u8_kernel(const float4* __restrict__ in, int64_t n4, uint32_t* __restrict__ out,
-                                                           unsigned* __restrict__ stats) {
+                                                           unsigned* __restrict__ stats, float limit) {
   float vmax = 0.f;
   bool bad = false;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(256) bins_pack_u8_kernel(const float4* __restr
     for (int k = 0; k < 4; ++k) {
       const float c = fminf(fmaxf(f[k], 0.f), 255.f);
       const uint32_t q = static_cast<uint32_t>(c);
-      bad |= !(static_cast<float>(q) == f[k]);        // negative, > 255, fractional or NaN
+      bad |= !(static_cast<float>(q) == f[k]) || c > limit;   // negative, > limit, fractional or NaN
       vmax = fmaxf(vmax, c);
       w |= q << (8 * k);
     }
@@ -1225,11 +1225,12 @@ cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const doub
   return cudaGetLastError();
 }
 
-cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, int num_sms, cudaStream_t s) {
+cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, float limit, int num_sms,
+                                cudaStream_t s) {
   cudaError_t err = cudaMemsetAsync(stats, 0, 2 * sizeof(unsigned), s);
   if (err != cudaSuccess || n == 0) return err;
   bins_pack_u8_kernel<<<num_sms * 8, 256, 0, s>>>(reinterpret_cast<const float4*>(bins), n / 4,
-                                                  reinterpret_cast<uint32_t*>(out), stats);
+                                                  reinterpret_cast<uint32_t*>(out), stats, limit);
   return cudaGetLastError();
 }
 

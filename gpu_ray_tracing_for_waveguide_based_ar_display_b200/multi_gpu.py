@@ -51,48 +51,46 @@ def reduce_bins(matrix_EB, group=None, narrow: bool = True):
     or a NumPy array (wrapped without copying).
 
     The bins are small integer counts stored in float32 (one deposit adds exactly 1.0,
-    GPU_ray_tracing_functions.py:1168).  With ``narrow`` the all-reduce moves them as uint8 (four to an
-    int32 word) whenever that is EXACT -- every entry a non-negative integer and ``world_size * (largest entry over all
-    ranks) <= 255``, so that no partial sum can wrap -- which is a quarter of the bytes over
-    NVLink (864 MB -> 216 MB at the default size).  Anything else goes as float32, as before.  The
-    result is bit-identical either way."""
+    GPU_ray_tracing_functions.py:1168).  With ``narrow`` they travel as uint8, four to an int32 word: if
+    every entry of every rank is an integer in [0, 255 // world_size], no byte sum can exceed 255, no
+    carry crosses a byte, and the int32 SUM all-reduce IS the sum of the counts -- a quarter of the bytes
+    over NVLink (864 MB -> 216 MB at the default size), bit-identical result.  A trailing word of the same
+    all-reduce carries every rank's "my entries do not qualify" flag; if it comes back non-zero the bins
+    (still untouched) are reduced as float32 instead.  ONE collective in the common case."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return matrix_EB
     t = torch.from_numpy(matrix_EB) if isinstance(matrix_EB, np.ndarray) else matrix_EB
     world = dist.get_world_size(group)
-    if narrow and t.dtype == torch.float32 and t.numel() > 0:
-        on_gpu = t.is_cuda and t.is_contiguous() and t.numel() % 4 == 0 and t.data_ptr() % 16 == 0
+    limit = 255 // world
+    if narrow and limit >= 1 and t.dtype == torch.float32 and t.numel() > 0 and t.numel() % 4 == 0 and t.is_contiguous():
+        n = t.numel()
+        words = torch.empty(n // 4 + 1, dtype=torch.int32, device=t.device)      # packed counts + the flag word
+        q = words[:-1].view(torch.uint8)
+        on_gpu = t.is_cuda and t.data_ptr() % 16 == 0
         if on_gpu:
-            # one fused pass of the engine: convert, largest entry, "all entries are integers in [0, 255]"
+            # one fused pass of the engine: convert and flag entries that are not integers in [0, limit]
             import ctypes as C
             from . import _capi
             lib = _capi.load_library()
-            q = torch.empty(t.numel(), dtype=torch.uint8, device=t.device)
             st = torch.empty(2, dtype=torch.int32, device=t.device)
             stream = torch.cuda.current_stream(t.device).cuda_stream
-            _capi.check(lib.wgrt_bins_pack_u8(C.c_void_p(t.data_ptr()), t.numel(), C.c_void_p(q.data_ptr()),
-                                              C.c_void_p(st.data_ptr()), C.c_void_p(stream)), lib)
-            stat = torch.stack((st[0:1].view(torch.float32)[0], st[1].to(torch.float32)))
+            _capi.check(lib.wgrt_bins_pack_u8(C.c_void_p(t.data_ptr()), n, C.c_void_p(q.data_ptr()),
+                                              C.c_void_p(st.data_ptr()), C.c_float(float(limit)), C.c_void_p(stream)), lib)
+            words[-1:] = st[1:2]
         else:
-            q = t.to(torch.uint8)                            # saturates / truncates: checked right below
-            exact = (q.to(torch.float32) == t).all()
-            stat = torch.stack((t.max().to(torch.float32), 1.0 - exact.to(torch.float32)))
-        dist.all_reduce(stat, op=dist.ReduceOp.MAX, group=group)     # same decision on every rank
-        if float(stat[1]) == 0.0 and float(stat[0]) * world <= 255.0:
-            # four counts per int32 word: byte sums stay <= 255, so no carry crosses a byte and the int32
-            # SUM is the uint8 SUM -- on the dtype NCCL's fast paths (NVLS, tree) are built for
-            packed = q.view(-1)
-            if packed.numel() % 4 == 0:
-                dist.all_reduce(packed.view(torch.int32), op=dist.ReduceOp.SUM, group=group)
-            else:
-                dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+            flat = t.reshape(-1)
+            clipped = flat.clamp(0, limit)
+            q.copy_(clipped.to(torch.uint8))
+            words[-1] = int(not bool((q.to(torch.float32) == flat).all()))
+        dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
+        if int(words[-1].item()) == 0:                       # every rank qualified: q holds the exact sums
             if on_gpu:
-                _capi.check(lib.wgrt_bins_unpack_u8(C.c_void_p(q.data_ptr()), t.numel(), C.c_void_p(t.data_ptr()),
+                _capi.check(lib.wgrt_bins_unpack_u8(C.c_void_p(q.data_ptr()), n, C.c_void_p(t.data_ptr()),
                                                     C.c_void_p(stream)), lib)
             else:
-                t.copy_(q.view(t.shape))
+                t.reshape(-1).copy_(q)
             return matrix_EB
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return matrix_EB

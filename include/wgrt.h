@@ -278,13 +278,15 @@ int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf
 
 /*
  * Multi-GPU reduce of the bins (new; the reference is single GPU).  The bins are small integer counts in
- * float32; summing them over the ranks as uint8 is exact whenever world_size * (largest entry) <= 255 and
- * moves a quarter of the bytes over NVLink.  wgrt_bins_pack_u8 converts n device floats (n % 4 == 0) to
- * uint8 and writes stats[0] = bit pattern of the largest entry (as float), stats[1] = 1 if any entry is
- * not an integer in [0, 255]; wgrt_bins_unpack_u8 converts back.  Asynchronous on `stream`.  The decision
- * and the NCCL call are the caller's (multi_gpu.reduce_bins).
+ * float32; summing them over the ranks as uint8 (four to an int32 word) is exact whenever every entry of
+ * every rank is an integer in [0, limit] with world_size * limit <= 255, and moves a quarter of the bytes
+ * over NVLink.  wgrt_bins_pack_u8 converts n device floats (n % 4 == 0) to uint8 and writes stats[0] = bit
+ * pattern of the largest entry (as float), stats[1] = 1 if any entry is not an integer in [0, limit];
+ * wgrt_bins_unpack_u8 converts back.  Asynchronous on `stream`.  The NCCL call and the fallback are the
+ * caller's (multi_gpu.reduce_bins carries the flag in a trailing word of the same all-reduce).
  */
-int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, void* stream);
+int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, float limit,
+                      void* stream);
 int wgrt_bins_unpack_u8(const uint8_t* dev_in, int64_t n, float* dev_bins, void* stream);
 
 #ifdef __cplusplus

@@ -139,7 +139,7 @@ def test_bins_pack_unpack_u8():
         t = torch.from_numpy(a).cuda()
         q = torch.empty(a.size, dtype=torch.uint8, device="cuda"); st = torch.empty(2, dtype=torch.int32, device="cuda")
         EV._capi.check(lib.wgrt_bins_pack_u8(C.c_void_p(t.data_ptr()), a.size, C.c_void_p(q.data_ptr()),
-                                             C.c_void_p(st.data_ptr()), None), lib)
+                                             C.c_void_p(st.data_ptr()), C.c_float(255.0), None), lib)
         torch.cuda.synchronize()
         vmax = st[0:1].view(torch.float32).item()
         assert int(st[1].item()) == want_bad
@@ -148,3 +148,6 @@ def test_bins_pack_unpack_u8():
             back = torch.zeros_like(t)
             EV._capi.check(lib.wgrt_bins_unpack_u8(C.c_void_p(q.data_ptr()), a.size, C.c_void_p(back.data_ptr()), None), lib)
             assert torch.equal(back, t)
+            EV._capi.check(lib.wgrt_bins_pack_u8(C.c_void_p(t.data_ptr()), a.size, C.c_void_p(q.data_ptr()),
+                                                 C.c_void_p(st.data_ptr()), C.c_float(31.0), None), lib)
+            assert int(st[1].item()) == int(a.max() > 31)      # entries above the limit are flagged
