@@ -66,8 +66,11 @@ def reduce_bins(matrix_EB, group=None, narrow: bool = True):
     limit = 255 // world
     if narrow and limit >= 1 and t.dtype == torch.float32 and t.numel() > 0 and t.numel() % 4 == 0 and t.is_contiguous():
         n = t.numel()
-        words = torch.empty(n // 4 + 1, dtype=torch.int32, device=t.device)      # packed counts + the flag word
-        q = words[:-1].view(torch.uint8)
+        # packed counts + the flag word, padded to a multiple of 4 KB (collectives like round sizes)
+        nw = (n // 4 + 1 + 1023) // 1024 * 1024
+        words = torch.empty(nw, dtype=torch.int32, device=t.device)
+        words[n // 4:].zero_()
+        q = words[:n // 4].view(torch.uint8)
         on_gpu = t.is_cuda and t.data_ptr() % 16 == 0
         if on_gpu:
             # one fused pass of the engine: convert and flag entries that are not integers in [0, limit]
