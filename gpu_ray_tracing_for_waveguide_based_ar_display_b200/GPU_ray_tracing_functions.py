@@ -101,13 +101,13 @@ def _describe(obj: Any, name: str) -> _Buf:
         strides = cai.get("strides")
         shape = tuple(cai["shape"])
         dtype = np.dtype(cai["typestr"])
-        if strides is not None:
-            expect, acc = [], dtype.itemsize
-            for s in reversed(shape):
-                expect.append(acc)
-                acc *= s
-            if tuple(strides) != tuple(reversed(expect)) and all(s > 1 for s in shape):
-                raise ValueError(f"{name}: device array must be C-contiguous")
+        if strides is not None and all(s > 0 for s in shape):
+            # dense C order; the stride of an axis of extent 1 is never used and may be anything
+            acc = dtype.itemsize
+            for extent, stride in zip(reversed(shape), reversed(tuple(strides))):
+                if extent > 1 and stride != acc:
+                    raise ValueError(f"{name}: device array must be C-contiguous")
+                acc *= extent
         return _Buf(int(cai["data"][0] or 0), shape, dtype, obj, False)
     if isinstance(obj, np.ndarray):
         if not obj.flags.c_contiguous:

@@ -20,7 +20,7 @@ WGRT_FLAG_BINS_ZERO = 0x4
 WGRT_FLAG_BINS_DEVICE = 0x8
 WGRT_NUM_COUNTERS = 16
 COUNTER_NAMES = ("rays", "bounces", "draws", "draw2", "draw3", "efield", "iters", "deposits",
-                 "poly_tests", "edge_visits", "straddle", "cross", "exact_fallback", "warp_steps", "warp_batches")
+                 "poly_tests", "edge_visits", "straddle", "cross", "exact_fallback", "warp_steps", "warp_batches", "near_tie")
 
 _f32p = C.c_void_p
 _f64p = C.c_void_p
@@ -63,6 +63,7 @@ EXPORTED_SYMBOLS = (
     "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host", "wgrt_trace_evaluate_host",
     "wgrt_counters_read", "wgrt_counters_reset",
     "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
+    "wgrt_debug_deposit_inside", "wgrt_debug_set_tie_tolerance",
     "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host", "wgrt_bins_pack_u8", "wgrt_bins_unpack_u8",
 )
 
@@ -107,6 +108,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_debug_efield.argtypes = [C.c_void_p] * 4 + [C.c_int64, C.c_void_p]
     lib.wgrt_debug_xorshift.restype = C.c_int
     lib.wgrt_debug_xorshift.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.wgrt_debug_deposit_inside.restype = C.c_int
+    lib.wgrt_debug_deposit_inside.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    lib.wgrt_debug_set_tie_tolerance.restype = C.c_int
+    lib.wgrt_debug_set_tie_tolerance.argtypes = [C.c_double]
     lib.wgrt_debug_fma_peak.restype = C.c_int
     lib.wgrt_debug_fma_peak.argtypes = [C.c_void_p, C.c_void_p]
     lib.wgrt_eval_pupil_sums.restype = C.c_int

@@ -19,7 +19,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # literal restatement that is compared with the CPU oracle.
 UNITS = {
     "wgrt_strict.cu": ["-fmad=false"],
-    "wgrt_fast.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WALK_THREADS", "WGRT_WALK_MIN_BLOCKS") if k in os.environ],
+    "wgrt_index.cu": [],
+    "wgrt_eval.cu": [],
     "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WARP_CTAS_PER_SM",) if k in os.environ],
     "wgrt_api.cu": [],
 }

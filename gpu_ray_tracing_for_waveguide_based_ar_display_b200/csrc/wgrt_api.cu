@@ -63,7 +63,16 @@ struct Workspace {
   DeviceBuf small;   // RegionDyn[NUM_REGIONS] | AtlasDyn @ 256 | tile counters @ 512 | hash state @ 768 | counters @ 1024 | Region[NUM_REGIONS] @ 1280
   bool index_stale = true;  // the index buffers were (re)allocated or used by a debug call
   DeviceBuf jones[3];   // per-warp Jones-matrix scratch of the warp walk, one per launch slot
+  DeviceBuf redo[3];    // near-tie redo list of the warp walk, one per launch slot
   DeviceBuf arena;   // staging for the host entry points
+  // Launches of one device share this workspace (tile counter, Jones scratch, region index): every
+  // enqueue waits for the previous one when it goes to another stream (see order_after_last_use)
+  cudaEvent_t last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool has_last = false;
+  // device polygon-offset arrays already validated: (pointer, entries, vertex count)
+  struct SeenOffsets { const void* ptr; int64_t n, nv; };
+  std::vector<SeenOffsets> seen_offsets;
   bool pipe_ready = false;                         // streams of the host entry's H2D / walk / D2H pipeline
   cudaStream_t s_in = nullptr, s_run[2] = {nullptr, nullptr}, s_out = nullptr;
   RegionDyn* dyn() { return static_cast<RegionDyn*>(small.ptr); }
@@ -84,7 +93,12 @@ struct Workspace {
     small.release();
     atlas.release();
     for (auto& j : jones) j.release();
+    for (auto& j : redo) j.release();
     arena.release();
+    if (last_use) cudaEventDestroy(last_use);
+    last_use = nullptr;
+    has_last = false;
+    seen_offsets.clear();
     if (pipe_ready) {
       cudaStreamDestroy(s_in); cudaStreamDestroy(s_run[0]); cudaStreamDestroy(s_run[1]); cudaStreamDestroy(s_out);
       pipe_ready = false;
@@ -228,6 +242,49 @@ int build_region_index(Workspace& w, const wgrt_problem_t& p, cudaStream_t strea
   return WGRT_OK;
 }
 
+// The workspace is shared by every launch of the device.  Work enqueued on `stream` that touches it must
+// run after the previous enqueue's work when that went to a different stream (same-stream work is
+// ordered already).  Launches of one device therefore execute in enqueue order, whatever their streams.
+int order_after_last_use(Workspace& w, cudaStream_t stream) {
+  if (w.has_last && w.last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, w.last_use, 0));
+  return WGRT_OK;
+}
+int record_last_use(Workspace& w, cudaStream_t stream) {
+  if (!w.last_use) CUDA_TRY(cudaEventCreateWithFlags(&w.last_use, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(w.last_use, stream));
+  w.last_stream = stream;
+  w.has_last = true;
+  return WGRT_OK;
+}
+
+int check_offsets(const int64_t* off, int64_t np, int64_t nv, const char* name) {
+  if (off[0] != 0 || off[np] > nv) return fail(WGRT_ERR_INVALID, "%s: must start at 0 and end within the vertex array", name);
+  for (int64_t k = 0; k < np; ++k)
+    if (off[k + 1] < off[k]) return fail(WGRT_ERR_INVALID, "%s: must be non-decreasing", name);
+  return WGRT_OK;
+}
+
+// Device path: the polygon offsets index the vertex arrays inside the kernels, so malformed offsets would
+// read out of bounds.  Each (pointer, size) pair is copied to the host and checked the first time it is
+// seen on a device (at most 251 entries; one small synchronous copy on the caller's stream).
+int validate_device_offsets(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream) {
+  for (int s = 0; s < 2; ++s) {
+    const int64_t* off = s ? p.OC_offset : p.FC_offset;
+    const int64_t np = s ? p.n_OC : p.n_FC, nv = s ? p.OC_n : p.FC_n;
+    bool seen = false;
+    for (auto& e : w.seen_offsets) seen = seen || (e.ptr == off && e.n == np && e.nv == nv);
+    if (seen) continue;
+    int64_t host[256];
+    CUDA_TRY(cudaMemcpyAsync(host, off, sizeof(int64_t) * (np + 1), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    int rc = check_offsets(host, np, nv, s ? "OC_offset" : "FC_offset");
+    if (rc != WGRT_OK) return rc;
+    if (w.seen_offsets.size() >= 64) w.seen_offsets.clear();
+    w.seen_offsets.push_back({off, np, nv});
+  }
+  return WGRT_OK;
+}
+
 // One launch of the walk.  `slot` selects the tile-counter pair (launches that may run concurrently
 // need different slots); `build_index = false` when the caller built the region index already.
 int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream, int slot = 0, bool build_index = true) {
@@ -244,19 +301,11 @@ int trace_device(Workspace& w, const wgrt_problem_t& p, cudaStream_t stream, int
     CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
     w.index_stale = false;
   }
-  // the production walk is the warp-per-cell kernel (wgrt_walk.cu); WGRT_WALK=cta selects the
-  // earlier CTA-per-cell kernel (wgrt_fast.cu), kept for A/B measurements
-  static int use_cta = -1;
-  if (use_cta < 0) {
-    const char* e = getenv("WGRT_WALK");
-    use_cta = (e && strcmp(e, "cta") == 0) ? 1 : 0;
-  }
-  if (use_cta) CUDA_TRY(launch_walk_fast(p, rs, w.work(slot), w.counters(), w.num_sms, stream));
-  else {
-    // (a reallocation frees the old scratch with cudaFree, which waits for work still using it)
-    CUDA_TRY(w.jones[slot].reserve(walk_warp_scratch_bytes(p, w.num_sms)));
-    CUDA_TRY(launch_walk_warp(p, rs, w.work(slot), w.counters(), w.num_sms, static_cast<double*>(w.jones[slot].ptr), stream));
-  }
+  // (a reallocation frees the old scratch with cudaFree, which waits for work still using it)
+  CUDA_TRY(w.jones[slot].reserve(walk_warp_scratch_bytes(p, w.num_sms)));
+  CUDA_TRY(w.redo[slot].reserve(sizeof(RedoList)));
+  CUDA_TRY(launch_walk_warp(p, rs, w.work(slot), w.counters(), w.num_sms, static_cast<double*>(w.jones[slot].ptr),
+                            static_cast<RedoList*>(w.redo[slot].ptr), stream));
   return WGRT_OK;
 }
 
@@ -309,7 +358,15 @@ int wgrt_trace_fullcolor(const wgrt_problem_t* p, void* stream) {
   Workspace* w = nullptr;
   rc = get_workspace(&w);
   if (rc != WGRT_OK) return rc;
-  return trace_device(*w, *p, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->num_rays == 0) return WGRT_OK;
+  rc = validate_device_offsets(*w, *p, st);
+  if (rc != WGRT_OK) return rc;
+  rc = order_after_last_use(*w, st);
+  if (rc != WGRT_OK) return rc;
+  rc = trace_device(*w, *p, st);
+  if (rc != WGRT_OK) return rc;
+  return record_last_use(*w, st);
 }
 
 }  // extern "C" (the host entry below needs helpers from an unnamed namespace)
@@ -395,13 +452,10 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
   int rc = validate(hp, ev == nullptr);
   if (rc != WGRT_OK) return rc;
   if (num_iter < 0) return fail(WGRT_ERR_INVALID, "num_iter < 0");
-  for (int s = 0; s < 2; ++s) {
-    const int64_t* off = s ? hp->OC_offset : hp->FC_offset;
-    const int64_t np = s ? hp->n_OC : hp->n_FC, nv = s ? hp->OC_n : hp->FC_n;
-    if (off[0] != 0 || off[np] > nv) return fail(WGRT_ERR_INVALID, "polygon offsets out of range");
-    for (int64_t k = 0; k < np; ++k)
-      if (off[k + 1] < off[k]) return fail(WGRT_ERR_INVALID, "polygon offsets must be non-decreasing");
-  }
+  rc = check_offsets(hp->FC_offset, hp->n_FC, hp->FC_n, "FC_offset");
+  if (rc != WGRT_OK) return rc;
+  rc = check_offsets(hp->OC_offset, hp->n_OC, hp->OC_n, "OC_offset");
+  if (rc != WGRT_OK) return rc;
   Workspace* w = nullptr;
   rc = get_workspace(&w);
   if (rc != WGRT_OK) return rc;
@@ -545,6 +599,11 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
   } sync_guard{s_in, s_run2[0], s_run2[1], s_out};
 
   const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+  // an asynchronous wgrt_trace_fullcolor launch may still be using the workspace (region index)
+  rc = order_after_last_use(*w, s_in);
+  if (rc != WGRT_OK) return rc;
+  rc = order_after_last_use(*w, s_run2[0]);
+  if (rc != WGRT_OK) return rc;
   CUDA_TRY(cudaEventRecord(span[0], s_in));
   for (auto& it : items)
     if (it.upfront && it.bytes && it.src) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, H2D, s_in));
@@ -766,6 +825,38 @@ int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last
     CUDA_TRY(cudaMemcpy(states, d_s, (size_t)n * 4, cudaMemcpyDeviceToHost));
     if (out_last) CUDA_TRY(cudaMemcpy(out_last, d_u, (size_t)n * 8, cudaMemcpyDeviceToHost));
   }
+  return WGRT_OK;
+}
+
+int wgrt_debug_set_tie_tolerance(double tol) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (tol != tol) return fail(WGRT_ERR_INVALID, "tolerance is NaN");
+  set_tie_tolerance(tol);
+  return WGRT_OK;
+}
+
+int wgrt_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n, int32_t* out, int mode) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!rect || !px || !py || !out || n < 0 || (mode != 0 && mode != 1)) return fail(WGRT_ERR_INVALID, "bad arguments");
+  Workspace* w = nullptr;
+  int rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  const size_t pb = (size_t)n * 8;
+  CUDA_TRY(cudaDeviceSynchronize());   // the arena may still be in use by an asynchronous launch
+  CUDA_TRY(w->arena.reserve(padded(64) + 2 * padded(pb) + padded((size_t)n * 4)));
+  Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+  double* d_r = static_cast<double*>(ar.take(64));
+  double* d_x = static_cast<double*>(ar.take(pb));
+  double* d_y = static_cast<double*>(ar.take(pb));
+  int32_t* d_o = static_cast<int32_t*>(ar.take((size_t)n * 4));
+  CUDA_TRY(cudaMemcpy(d_r, rect, 64, cudaMemcpyHostToDevice));
+  if (n) {
+    CUDA_TRY(cudaMemcpy(d_x, px, pb, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_y, py, pb, cudaMemcpyHostToDevice));
+  }
+  CUDA_TRY(launch_debug_deposit_inside(d_r, d_x, d_y, n, d_o, mode == 0 ? 1 : 0, nullptr));
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (n) CUDA_TRY(cudaMemcpy(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return WGRT_OK;
 }
 

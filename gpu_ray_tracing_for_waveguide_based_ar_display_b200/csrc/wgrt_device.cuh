@@ -50,6 +50,23 @@ struct Counts {
   }
 };
 
+// Rays the fast walk refuses to decide (a draw within TIE_TOL of a threshold, wgrt_walk.cu): their
+// launch-relative indices, re-walked literally by walk_redo_kernel (wgrt_strict.cu) after the walk.
+constexpr unsigned REDO_CAP = 1u << 16;
+struct RedoList {
+  unsigned count;        // pushes attempted in this launch (may exceed REDO_CAP)
+  unsigned pad_[3];
+  long long idx[REDO_CAP];
+};
+// false when the list is full: the caller then keeps its own decision (parity falls back to
+// "a few ulp from the threshold" for that ray; needs > 65536 near ties in ONE launch)
+__device__ __forceinline__ bool redo_push(RedoList* r, long long ray) {
+  const unsigned slot = atomicAdd(&r->count, 1u);
+  if (slot >= REDO_CAP) return false;
+  r->idx[slot] = ray;
+  return true;
+}
+
 // GRTF:52-61
 template <bool COUNT>
 __device__ __forceinline__ bool on_segment_literal(double px, double py, double x1, double y1, double x2,
@@ -180,11 +197,14 @@ struct RegionSet {
 
 cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* counters, cudaStream_t s);
 cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s);
-cudaError_t launch_walk_fast(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
-                             unsigned long long* counters, int num_sms, cudaStream_t s);
+void set_tie_tolerance(double tol);
+cudaError_t launch_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n, int32_t* out,
+                                        int literal, cudaStream_t s);
 size_t walk_warp_scratch_bytes(const wgrt_problem_t& p, int num_sms);
 cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
-                             unsigned long long* counters, int num_sms, double* jones_scratch, cudaStream_t s);
+                             unsigned long long* counters, int num_sms, double* jones_scratch, RedoList* redo,
+                             cudaStream_t s);
+cudaError_t launch_walk_redo(const wgrt_problem_t& p, const RedoList* redo, unsigned long long* counters, cudaStream_t s);
 cudaError_t launch_debug_locate_literal(const double* verts, const int64_t* off, int64_t npoly, const double* px,
                                         const double* py, int64_t n, int32_t* out, cudaStream_t s);
 cudaError_t launch_debug_locate_grid(const RegionSet& rs, int region, const double* px, const double* py, int64_t n,

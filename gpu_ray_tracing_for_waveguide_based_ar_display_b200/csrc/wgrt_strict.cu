@@ -56,6 +56,8 @@ __device__ void walk_one_ray(const wgrt_problem_t& p, int64_t idx, Counts* cn) {
     dl = static_cast<double>(p.delta_phase[idx]);
   }
   if (m < 0 || m >= p.X || n < 0 || n >= p.Y || lm < 0 || lm >= p.L) return;  // outside every table
+  if (p.runner_points == 0 &&
+      !(isfinite(p.m[idx]) && isfinite(p.n[idx]) && (!p.lmd_num || isfinite(p.lmd_num[idx])))) return;
   uint32_t rng = p.rng_states[idx];
   double ener = 1.0;
   const double threshold = p.threshold;  // GRTF:859 (0) or GRTF:444 (1e-15)
@@ -254,6 +256,27 @@ __global__ void __launch_bounds__(256) walk_strict_kernel(const __grid_constant_
   if (COUNT) cn.flush(counters);
 }
 
+// The rays the fast walk left undecided (near ties, see wgrt_walk.cu): walked from their start with the
+// literal expressions.  Their RNG states and bins are untouched by the fast walk, so the result is what
+// a strict launch gives for them.  Counted into WGRT_CNT_NEAR_TIE by every launch.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) walk_redo_kernel(const __grid_constant__ wgrt_problem_t p,
+                                                        const RedoList* __restrict__ redo,
+                                                        unsigned long long* counters) {
+  const unsigned n = min(redo->count, REDO_CAP);
+  Counts cn;
+  if (COUNT) cn.clear();
+  for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+    const int64_t idx = redo->idx[j];
+    if (idx >= 0 && idx < p.num_rays) walk_one_ray<COUNT>(p, idx, &cn);
+  }
+  if (COUNT) {
+    cn.c[WGRT_CNT_RAYS] = 0;   // the fast walk counted the ray when it loaded it
+    cn.flush(counters);
+  }
+  if (threadIdx.x == 0 && n) atomicAdd(counters + WGRT_CNT_NEAR_TIE, static_cast<unsigned long long>(n));
+}
+
 __global__ void locate_literal_kernel(const double* verts, const int64_t* off, int64_t npoly, const double* px,
                                       const double* py, int64_t n, int32_t* out) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -309,6 +332,12 @@ cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* coun
     walk_strict_kernel<true><<<blocks_for(p.num_rays, threads), threads, 0, s>>>(p, counters);
   else
     walk_strict_kernel<false><<<blocks_for(p.num_rays, threads), threads, 0, s>>>(p, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_walk_redo(const wgrt_problem_t& p, const RedoList* redo, unsigned long long* counters, cudaStream_t s) {
+  if (p.flags & WGRT_FLAG_COUNTERS) walk_redo_kernel<true><<<1, 128, 0, s>>>(p, redo, counters);
+  else walk_redo_kernel<false><<<1, 128, 0, s>>>(p, redo, counters);
   return cudaGetLastError();
 }
 

@@ -25,9 +25,14 @@
 //    E_field_cal's cos / sin / hypot / atan2 / wrap (GRTF:136-150) and the per-event normalisation
 //    (GRTF:876-877 ff.) disappear: efficiencies are v^H M v * s with M = J^H J precomputed per cell
 //    and order, TIR phases are complex multiplies by per-cell phasors.  Algebraically the same map;
-//    numerically a few ulp apart, i.e. a decision `u <= efficiency` can flip only when u lands within
-//    ~1e-15 of the threshold (expected ~1e-6 flips per 450 M-ray job).  Tests demand bit equality
-//    with the reference kernel on up to 450 M ray launches and get it.
+//    numerically a few ulp apart, i.e. a decision `u <= efficiency` could flip only when u lands within
+//    ~1e-15 of a threshold.  Parity is nevertheless BY CONSTRUCTION: a ray whose draw lands within
+//    TIE_TOL = 1e-10 of any threshold it is compared with (five orders of magnitude more than the
+//    two evaluations can differ) is not decided here at all -- the lane drops it untouched (RNG state
+//    not written, nothing deposited: a deposit ends a ray) onto the launch's redo list, and
+//    walk_redo_kernel (wgrt_strict.cu) walks it from its start with the reference's literal
+//    expressions right after this kernel.  Expected: ~0.3 such rays per 112.5 M-ray launch; their
+//    number is reported (WGRT_CNT_NEAR_TIE).
 //  * Everything state dependent is table driven from shared memory (per-cell event rows, sinfo).
 #include <climits>
 
@@ -49,6 +54,9 @@ constexpr int R_INVCOS = 4;        // 1 / cos(theta_new)
 constexpr int R_META = 5;          // bit field, see below
 constexpr int JROW = 8;            // doubles per Jones row in the scratch
 constexpr int ST_DEAD = -1, ST_PEND_FWD = 6, ST_PEND_BACK = 7;
+// |u - cumulative efficiency| below this: the ray is re-walked literally (see the file header)
+constexpr double TIE_TOL_DEFAULT = 1e-10;
+double g_tie_tol = TIE_TOL_DEFAULT;   // wgrt_debug_set_tie_tolerance (tests widen it to exercise the redo path)
 // Resident single-warp CTAs per SM the kernel is compiled for.  Measured on C2: 32 (64 registers, a few
 // spills) 11.14 ms, 28 (72 registers, no spills) 10.8 ms, 24 (80 registers) 11.1 ms.
 #ifndef WGRT_WARP_CTAS_PER_SM
@@ -173,6 +181,17 @@ __device__ __forceinline__ const double* lut_slice(const wgrt_problem_t& p, int 
   }
 }
 
+// The eyebox rectangle of a FoV cell is (xmin,ymax),(xmin,ymin),(xmax,ymin),(xmax,ymax)
+// (couplers_coor.py:514-526).  When the four vertices are exactly that, points clearly inside /
+// outside it need no edge arithmetic (see deposit_inside).
+__device__ __forceinline__ void eyebox_box(const double* __restrict__ r, CellConst& cc) {
+  const double x0 = r[0], y0 = r[1], x1 = r[2], y1 = r[3], x2 = r[4], y2 = r[5], x3 = r[6], y3 = r[7];
+  const bool ok = x0 == x1 && x2 == x3 && y1 == y2 && y0 == y3 && x0 < x2 && y1 < y0 && isfinite(x0) &&
+                  isfinite(x2) && isfinite(y0) && isfinite(y1);
+  cc.box[0] = x0; cc.box[1] = x2; cc.box[2] = y1; cc.box[3] = y0;
+  cc.box_ok = ok ? 1 : 0;
+}
+
 // Event table and per-cell constants of cell (lm, m, n); the 32 lanes of the warp share the rows.
 __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m, int64_t n, double* tab,
                                   double* __restrict__ jones, CellConst& cc, int rows, int lane) {
@@ -260,15 +279,7 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     cc.sinfo[6] = 0;
     cc.sinfo[7] = 0;
   } else if (t == 26) {
-    // The eyebox rectangle of a FoV cell is (xmin,ymax),(xmin,ymin),(xmax,ymin),(xmax,ymax)
-    // (couplers_coor.py:514-526).  When the four vertices are exactly that, points clearly inside /
-    // outside it need no edge arithmetic (see deposit_inside).
-    const double* r = p.eff_reg_FOV + 8 * (m * p.Y + n);
-    const double x0 = r[0], y0 = r[1], x1 = r[2], y1 = r[3], x2 = r[4], y2 = r[5], x3 = r[6], y3 = r[7];
-    const bool ok = x0 == x1 && x2 == x3 && y1 == y2 && y0 == y3 && x0 < x2 && y1 < y0 && isfinite(x0) &&
-                    isfinite(x2) && isfinite(y0) && isfinite(y1);
-    cc.box[0] = x0; cc.box[1] = x2; cc.box[2] = y1; cc.box[3] = y0;
-    cc.box_ok = ok ? 1 : 0;
+    eyebox_box(p.eff_reg_FOV + 8 * (m * p.Y + n), cc);
   }
 }
 
@@ -305,6 +316,21 @@ __device__ __forceinline__ bool deposit_inside(const CellConst& cc, double x, do
   return inside_or_on_edge_literal<COUNT>(x, y, cc.rect, 0, 4, cn);
 }
 
+// unit hook (wgrt_debug_deposit_inside): the walk's eyebox test on arbitrary points / rectangles
+__global__ void deposit_inside_kernel(const double* __restrict__ rect, const double* __restrict__ px,
+                                      const double* __restrict__ py, int64_t n, int32_t* __restrict__ out, int literal) {
+  __shared__ CellConst cc;
+  if (threadIdx.x < 8) cc.rect[threadIdx.x] = rect[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) eyebox_box(rect, cc);
+  __syncthreads();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = literal ? inside_or_on_edge_literal<false>(px[i], py[i], cc.rect, 0, 4, nullptr)
+                   : deposit_inside<false>(cc, px[i], py[i], nullptr);
+  if (!literal && cc.box_ok) out[i] |= 2;   // bit 1: the shortcut was armed for this rectangle
+}
+
 struct Ray {
   double x, y;      // position
   cplx te, tm;      // Jones vector, not normalised
@@ -322,7 +348,8 @@ template <bool COUNT, bool IMPLICIT>
 __global__ void __launch_bounds__(32, WGRT_WARP_CTAS_PER_SM)
 walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
                  int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
-                 unsigned long long* counters, double* __restrict__ jones_scratch) {
+                 unsigned long long* counters, double* __restrict__ jones_scratch, RedoList* __restrict__ redo,
+                 const double TIE_TOL) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   WarpShared& sh = *reinterpret_cast<WarpShared*>(smem_raw);
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
@@ -371,7 +398,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         run_limit = t_end;   // cut on the fly where the key changes
       }
       const int64_t m = static_cast<int64_t>(km), n = static_cast<int64_t>(kn), lm = static_cast<int64_t>(kl);
-      const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
+      // (a non-finite key converts to an arbitrary integer; such rays are left untouched)
+      const bool valid = isfinite(km) && isfinite(kn) && isfinite(kl) && m >= 0 && m < p.X && n >= 0 && n < p.Y &&
+                         lm >= 0 && lm < p.L;
       __syncwarp();
       if (valid) build_cell_tables(p, lm, m, n, tab, jones, sh.cc, rows, lane);
       __syncwarp();
@@ -402,7 +431,11 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
               fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
             } else {
-              same = ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl);
+              // the run key is compared by bit pattern: a NaN key still equals itself, so the ray at
+              // `cursor` always belongs to its own run and the cursor always advances
+              same = __float_as_uint(ld_stream(p.m + i)) == __float_as_uint(km) &&
+                     __float_as_uint(ld_stream(p.n + i)) == __float_as_uint(kn) &&
+                     (!has_l || __float_as_uint(ld_stream(p.lmd_num + i)) == __float_as_uint(kl));
               fx = ld_stream(p.x + i); fy = ld_stream(p.y + i);
               fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i); fdl = ld_stream(p.delta_phase + i);
             }
@@ -439,7 +472,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double g = cc.inv_cos_in;
             const double e1 = (tab[R_Q] * t2 + tab[R_Q + 1] * m2 + (tab[R_Q + 2] * zre + tab[R_Q + 3] * zim)) * g;
             const double e2 = (tab[ROW + R_Q] * t2 + tab[ROW + R_Q + 1] * m2 + (tab[ROW + R_Q + 2] * zre + tab[ROW + R_Q + 3] * zim)) * g;
-            if (u <= e1) { k = 0; esel = e1; }                 // GRTF:871: no energy gate here
+            if ((fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
+              // near tie: left untouched for the literal re-walk
+            } else if (u <= e1) { k = 0; esel = e1; }          // GRTF:871: no energy gate here
             else if (u <= e1 + e2) { k = 1; esel = e2; }       // GRTF:887
             else st_stream(p.rng_states + i, frng);            // GRTF:903-904: absorbed
           }
@@ -526,6 +561,13 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const bool ok3 = three && u <= e12 + e3v && r.ener * e3v > threshold;
             k = ok1 ? 0 : ok2 ? 1 : ok3 ? 2 : -1;
             esel = ok1 ? e1 : ok2 ? e2 : e3v;
+            bool tie = fabs(u - e1) < TIE_TOL || fabs(u - e12) < TIE_TOL || (three && fabs(u - (e12 + e3v)) < TIE_TOL);
+            if (threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
+              const double rt = 1e-9 * threshold;
+              tie = tie || fabs(r.ener * e1 - threshold) < rt || fabs(r.ener * e2 - threshold) < rt ||
+                    (three && fabs(r.ener * e3v - threshold) < rt);
+            }
+            if (tie && redo_push(redo, t_begin + r.idx)) k = -2;   // dropped untouched, re-walked literally
           } else {
             r.iter = 0;   // a popped survivor: row0 IS the chosen in-coupling row, ener already holds its efficiency
             k = 0;
@@ -537,6 +579,10 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         if (at_event) {
           if (k < 0) {
             lost = true;   // absorbed
+            if (k == -2) {   // near tie: not even the RNG state is written
+              r.state = ST_DEAD;
+              lost = false;
+            }
           } else {
             const double* row = tab + (r.row0 + k) * ROW;
             const int meta = static_cast<int>(__double_as_longlong(row[R_META]));
@@ -646,10 +692,11 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
 // tile size: a tile should hold whole runs.  One block measures the first run.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) pick_tile_warp_kernel(const __grid_constant__ wgrt_problem_t p, int* tile_size,
-                                                              int* work_counter, int tile_cap) {
+                                                              int* work_counter, int tile_cap, RedoList* redo) {
   __shared__ int s_run;
   if (threadIdx.x == 0) {
     *work_counter = 0;
+    redo->count = 0u;
     s_run = INT_MAX;
   }
   if (p.tile_hint) {
@@ -695,13 +742,23 @@ __global__ void __launch_bounds__(1024) pick_tile_warp_kernel(const __grid_const
 
 }  // namespace
 
+cudaError_t launch_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n, int32_t* out,
+                                        int literal, cudaStream_t s) {
+  if (n == 0) return cudaSuccess;
+  deposit_inside_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(rect, px, py, n, out, literal);
+  return cudaGetLastError();
+}
+
+void set_tie_tolerance(double tol) { g_tie_tol = tol >= 0.0 ? tol : TIE_TOL_DEFAULT; }
+
 size_t walk_warp_scratch_bytes(const wgrt_problem_t& p, int num_sms) {
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   return static_cast<size_t>(num_sms) * 32 * rows * JROW * sizeof(double);   // at most 32 single-warp CTAs per SM
 }
 
 cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
-                             unsigned long long* counters, int num_sms, double* jones_scratch, cudaStream_t s) {
+                             unsigned long long* counters, int num_sms, double* jones_scratch, RedoList* redo,
+                             cudaStream_t s) {
   if (p.num_rays == 0) return cudaSuccess;
   int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
@@ -730,9 +787,11 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const int64_t resident = static_cast<int64_t>(num_sms) * per_sm;
   const int grid = static_cast<int>(resident < min_tiles ? resident : (min_tiles > 1 ? min_tiles : 1));
   const int64_t tcap = p.num_rays / (4 * resident);
-  pick_tile_warp_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter, static_cast<int>(tcap > (1 << 20) ? (1 << 20) : tcap));
-  kern<<<grid, 32, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch);
-  return cudaGetLastError();
+  pick_tile_warp_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter, static_cast<int>(tcap > (1 << 20) ? (1 << 20) : tcap), redo);
+  kern<<<grid, 32, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch, redo, g_tie_tol);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  return launch_walk_redo(p, redo, counters, s);   // the near-tie rays, literally (usually none)
 }
 
 }  // namespace wgrt

@@ -34,8 +34,14 @@ LUT_NAMES = ("lut_ic1", "lut_ic2", "lut_ic3", "lut_fc1", "lut_fc2", "lut_oc1", "
 RAY_FIELDS = ("x", "y", "gap_x", "gap_y", "pol", "azi", "m", "n", "lmd_num", "te", "tm", "delta_phase")
 
 
-def _fill_lut(shape_prefix, P, theta, phi, diag_targets, rng, cross=0.02, floor=0.01):
-    """One LUT. ``diag_targets[(g0, p)]`` = |diagonal Jones| array broadcastable to shape_prefix."""
+def _fill_lut(shape_prefix, P, theta, phi, diag_targets, rng, cross=0.02, floor=0.01, cross_range=None):
+    """One LUT. ``diag_targets[(g0, p)]`` = |diagonal Jones| array broadcastable to shape_prefix.
+    ``cross_range=(lo, hi)``: cross-polarisation amplitudes uniform in [lo, hi] x the diagonal one
+    (strong polarisation mixing) instead of ``cross`` x U(0.5, 1.5); same random stream either way."""
+    def xpol(amp, u):
+        if cross_range is None:
+            return cross * amp * u
+        return (cross_range[0] + (cross_range[1] - cross_range[0]) * (u - 0.5)) * amp
     C = 2 + 8 * P
     mag = np.full(shape_prefix + (C,), floor)
     mag *= rng.uniform(0.5, 1.5, size=mag.shape)
@@ -47,8 +53,8 @@ def _fill_lut(shape_prefix, P, theta, phi, diag_targets, rng, cross=0.02, floor=
         c_mm = 2 + (g0 + 5) * P + p
         mag[..., c_tt] = amp * rng.uniform(0.95, 1.05, size=shape_prefix)
         mag[..., c_mm] = 0.93 * amp * rng.uniform(0.95, 1.05, size=shape_prefix)
-        mag[..., c_x1] = cross * amp * rng.uniform(0.5, 1.5, size=shape_prefix)
-        mag[..., c_x2] = cross * amp * rng.uniform(0.5, 1.5, size=shape_prefix)
+        mag[..., c_x1] = xpol(amp, rng.uniform(0.5, 1.5, size=shape_prefix))
+        mag[..., c_x2] = xpol(amp, rng.uniform(0.5, 1.5, size=shape_prefix))
     phase = rng.uniform(-np.pi, np.pi, size=mag.shape)
     lut = (mag * np.exp(1j * phase)).astype(np.complex128)
     lut[..., 0] = np.broadcast_to(theta, shape_prefix)
@@ -67,7 +73,12 @@ def make_luts(angles: Dict[str, np.ndarray], n_g: float, n_fc: int, n_oc: int, s
              fc_zero=0.86, fc_turn=0.08, oc_zero=0.80, oc_cross=0.03, outcouple=0.12)
     if eff:
         e.update(eff)
+    # eff["cross_pol"] = (lo, hi): strong polarisation mixing in every Jones quartet (see _fill_lut)
+    xr = tuple(e["cross_pol"]) if e.get("cross_pol") is not None else None
     rng = np.random.default_rng(seed)
+
+    def fill(*a):   # every table of this call shares the mixing option
+        return _fill_lut(*a, cross_range=xr)
     th_in, th_ic, th_ic2 = angles["th_in_ic"], angles["th_out_ic"], angles["th_out_ic2"]
     th_fc, th_oc = angles["th_out_fc"], angles["th_out_oc"]
     c_in, c_ic, c_ic2, c_fc, c_oc = (np.cos(a) for a in (th_in, th_ic, th_ic2, th_fc, th_oc))
@@ -84,32 +95,32 @@ def make_luts(angles: Dict[str, np.ndarray], n_g: float, n_fc: int, n_oc: int, s
 
     luts = {}
     # in-coupling from air: eff = |J E|^2 * cos(th_new) / cos(th_in) * n_g     (GRTF:868-869)
-    luts["lut_ic1"] = _fill_lut(base, 5, th_in, angles["phi_in_ic"], {
+    luts["lut_ic1"] = fill(base, 5, th_in, angles["phi_in_ic"], {
         (2, 1): amp(e["incouple"] * mod, c_ic / c_in * n_g),
         (2, 3): amp(e["incouple_m1"] * mod, c_ic2 / c_in * n_g)}, rng)
     # inside the in-coupler, +1 direction: eff = |J E|^2 * cos(th_new)/cos(th_cur)   (GRTF:917-918)
-    luts["lut_ic2"] = _fill_lut(base, 5, th_ic, angles["phi_out_ic"], {
+    luts["lut_ic2"] = fill(base, 5, th_ic, angles["phi_out_ic"], {
         (0, 2): amp(e["ic_zero"], 1.0),
         (0, 4): amp(e["ic_cross"], c_ic2 / c_ic)}, rng)
-    luts["lut_ic3"] = _fill_lut(base, 5, th_ic2, angles["phi_out_ic2"], {
+    luts["lut_ic3"] = fill(base, 5, th_ic2, angles["phi_out_ic2"], {
         (0, 0): amp(e["ic_cross"], c_ic / c_ic2),
         (0, 2): amp(e["ic_zero"], 1.0)}, rng)
     # fold coupler: slices further from the in-coupler turn a little more light
     sl_fc = (1.0 + 0.5 * np.arange(n_fc) / max(n_fc - 1, 1))[:, None, None, None]
     fbase = (n_fc,) + base
-    luts["lut_fc1"] = _fill_lut(fbase, 3, th_ic, angles["phi_out_ic"], {
+    luts["lut_fc1"] = fill(fbase, 3, th_ic, angles["phi_out_ic"], {
         (0, 1): amp(e["fc_zero"], 1.0),
         (0, 0): amp(e["fc_turn"] * sl_fc * mod, c_fc / c_ic)}, rng)
-    luts["lut_fc2"] = _fill_lut(fbase, 3, th_fc, angles["phi_out_fc"], {
+    luts["lut_fc2"] = fill(fbase, 3, th_fc, angles["phi_out_fc"], {
         (0, 2): amp(e["fc_turn"] * sl_fc, c_ic / c_fc),
         (0, 1): amp(e["fc_zero"], 1.0)}, rng)
     sl_oc = (1.0 + 0.8 * np.arange(n_oc) / max(n_oc - 1, 1))[:, None, None, None]
     obase = (n_oc,) + base
-    luts["lut_oc1"] = _fill_lut(obase, 5, th_fc, angles["phi_out_fc"], {
+    luts["lut_oc1"] = fill(obase, 5, th_fc, angles["phi_out_fc"], {
         (0, 2): amp(e["oc_zero"], 1.0),
         (0, 0): amp(e["oc_cross"], c_oc / c_fc),
         (2, 1): amp(e["outcouple"] * sl_oc * mod, c_in / c_fc / n_g)}, rng)
-    luts["lut_oc2"] = _fill_lut(obase, 5, th_oc, angles["phi_out_oc"], {
+    luts["lut_oc2"] = fill(obase, 5, th_oc, angles["phi_out_oc"], {
         (0, 4): amp(e["oc_cross"], c_fc / c_oc),
         (0, 2): amp(e["oc_zero"], 1.0),
         (2, 3): amp(e["outcouple"] * sl_oc * mod, c_in / c_oc / n_g)}, rng)
@@ -157,7 +168,7 @@ class RaySet:
 
 def build_ray_set(points: np.ndarray, num_FOV_x: int, num_FOV_y: int, n_lmd: int,
                   num_rays_per_FoV: int, lmd_subset: Optional[Sequence[int]] = None,
-                  cells: Optional[np.ndarray] = None) -> RaySet:
+                  cells: Optional[np.ndarray] = None, ray_pol: Optional[str] = None, pol_seed: int = 0) -> RaySet:
     """Ray arrays in the runner's order (RUN:82-115).
 
     ``points``: [num_rays_per_FoV//2, 2] start points.  ``lmd_subset`` restricts the wavelength
@@ -185,8 +196,18 @@ def build_ray_set(points: np.ndarray, num_FOV_x: int, num_FOV_y: int, n_lmd: int
     te_block = np.concatenate((np.ones(half, f32), np.zeros(half, f32)))
     te = np.tile(te_block, K)
     tm = np.tile(1.0 - te_block, K).astype(f32)
+    dl = zeros.copy()
+    if ray_pol == "mixed":
+        # general input polarisation (the kernel's signature allows it; the runner only uses TE / TM with
+        # delta_phase = 0): elliptical states, amplitudes and phase difference per ray
+        prng = np.random.default_rng(pol_seed)
+        te = prng.uniform(0.2, 1.0, N).astype(f32)
+        tm = prng.uniform(0.2, 1.0, N).astype(f32)
+        dl = prng.uniform(-3.0, 3.0, N).astype(f32)
+    elif ray_pol is not None:
+        raise ValueError("ray_pol must be None or 'mixed'")
     return RaySet(x, y, zeros.copy(), zeros.copy(), zeros.copy(), zeros.copy(), m, n, lm_arr,
-                  te, tm, zeros.copy(), initial_rng_states(N))
+                  te, tm, dl, initial_rng_states(N))
 
 
 @dataclass
@@ -215,7 +236,8 @@ class Scene:
 
 def make_scene(num_FOV_x: int, num_FOV_y: int, num_rays_per_FoV: int, eb=(80, 120), seed: int = 0,
                lmd_subset: Optional[Sequence[int]] = None, design: Optional[WaveguideDesign] = None,
-               eff: Optional[Dict[str, float]] = None, build_rays: bool = True) -> Scene:
+               eff: Optional[Dict[str, float]] = None, build_rays: bool = True,
+               ray_pol: Optional[str] = None) -> Scene:
     out = couplers_coor_full_color(num_FOV_x, num_FOV_y, design=design)
     (IC, FC, FC_offset, OC, OC_offset, eff_reg1, eff_reg2, eff_reg_FOV, eff_reg_FOV_range,
      lut_TIR, lut_gap, _fres, _Lic, _pic, _Lfc, _pfc, _Loc, _poc, n_g, lmd,
@@ -235,7 +257,8 @@ def make_scene(num_FOV_x: int, num_FOV_y: int, num_rays_per_FoV: int, eb=(80, 12
     L = len(lmd)
     if build_rays:
         pts = points_in_disc(IC, num_rays_per_FoV // 2, seed + 1)
-        rays = build_ray_set(pts, num_FOV_x, num_FOV_y, L, num_rays_per_FoV, lmd_subset)
+        rays = build_ray_set(pts, num_FOV_x, num_FOV_y, L, num_rays_per_FoV, lmd_subset, ray_pol=ray_pol,
+                             pol_seed=seed + 2)
     else:
         rays = None
     return Scene(geom, float(n_g), luts, rays, (L, num_FOV_y, num_FOV_x, eb[0], eb[1]),

@@ -56,6 +56,8 @@ enum {
   WGRT_CNT_EXACT_FALLBACK, /* region queries that left the cell grid for the exact edge scan */
   WGRT_CNT_WARP_STEPS,   /* fast walk: loop iterations executed per WARP (iters / this = live lanes) */
   WGRT_CNT_WARP_BATCHES, /* fast walk: 32-ray in-coupling batches */
+  WGRT_CNT_NEAR_TIE,     /* fast walk, counted by EVERY launch (flag or not): rays whose draw came within 1e-10
+                          * of a decision threshold and were therefore re-walked with the literal expressions */
   WGRT_NUM_COUNTERS = 16
 };
 
@@ -247,6 +249,20 @@ int wgrt_debug_efield(const double* ete, const double* etm, const double* delta,
 /* get_uniform_random_number (GPU_ray_tracing_functions.py:25-34): advance each state `draws`
  * times; out_last[i] = last uniform of stream i. */
 int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last);
+
+/* is_inside_or_on_edge_4d on one eyebox rectangle (GPU_ray_tracing_functions.py:73-108; rect = the 4 x 2
+ * vertices of eff_reg_FOV[m, n]): out[i] bit 0 = point i is inside or on an edge.  mode 0 = the literal
+ * two-pass test, mode 1 = the walk's production test (accept / reject shortcut for points clearly inside /
+ * outside an exactly axis-aligned rectangle, literal otherwise); with mode 1, bit 1 of out[i] tells that
+ * the shortcut was armed for this rectangle. */
+int wgrt_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n_points,
+                              int32_t* out, int mode);
+
+/* Near-tie tolerance of the fast walk (default 1e-10; negative restores it): a ray whose uniform draw
+ * lands within `tol` of a threshold it is compared with is re-walked with the reference's literal
+ * expressions instead of being decided by the reformulated arithmetic.  Tests widen it (e.g. 0.05) to
+ * push a large share of the rays through that path; results must not change.  Process-wide. */
+int wgrt_debug_set_tie_tolerance(double tol);
 
 /*
  * Roofline denominators measured on the current device: achieved FP64 FMA rate of a pure

@@ -71,6 +71,18 @@ SCENES = {
                       design=dict(t=0.3, num_FC=15, fov_x_deg=24.0),
                       eff=dict(incouple=0.9, incouple_m1=0.08, ic_zero=0.9, ic_cross=0.05, fc_zero=0.6, fc_turn=0.3,
                                oc_zero=0.85, oc_cross=0.06, outcouple=0.05)),
+    # strong polarisation mixing: cross-polarisation amplitudes 0.3-0.7 of the diagonal ones with random
+    # phases in every Jones quartet, order efficiencies summing near 1 -- the cancellation in the
+    # off-diagonal terms of J^H J that real RCWA tables produce
+    "walk_mix": dict(num_FOV_x=3, num_FOV_y=3, num_rays_per_FoV=300, seed=43, lmd_subset=None, num_iter=1,
+                     eff=dict(incouple=0.6, incouple_m1=0.25, ic_zero=0.55, ic_cross=0.3, fc_zero=0.5, fc_turn=0.33,
+                              oc_zero=0.55, oc_cross=0.25, outcouple=0.08, cross_pol=(0.3, 0.7))),
+    # general input polarisation: elliptical states (te, tm in [0.2, 1], delta_phase in [-3, 3]) -- the
+    # delta_phase != 0 entry of E_field_cal (GRTF:136-138) that the runner's TE / TM rays never take
+    "walk_pol": dict(num_FOV_x=3, num_FOV_y=3, num_rays_per_FoV=300, seed=47, lmd_subset=None, num_iter=1,
+                     ray_pol="mixed",
+                     eff=dict(incouple=0.8, incouple_m1=0.1, ic_zero=0.85, ic_cross=0.08, fc_zero=0.7, fc_turn=0.25,
+                              oc_zero=0.8, oc_cross=0.08, outcouple=0.08, cross_pol=(0.1, 0.3))),
 }
 
 
@@ -80,7 +92,7 @@ def scene_from_recipe(r):
     design = WaveguideDesign(**r["design"]) if r.get("design") else None
     return make_scene(r["num_FOV_x"], r["num_FOV_y"], r["num_rays_per_FoV"], seed=r["seed"],
                       lmd_subset=r.get("lmd_subset"), eff=r.get("eff"), eb=tuple(r.get("eb", (80, 120))),
-                      design=design)
+                      design=design, ray_pol=r.get("ray_pol"))
 
 
 def input_digest(scene) -> str:
@@ -108,8 +120,18 @@ def _run_chunk(job):
     rng = sub.rng_states.copy()
     threads = 32
     blocks = (sub.num_rays + threads - 1) // threads
+    args = list(scene.kernel_args(EB, rng))
+    if recipe.get("ray_pol"):
+        # Simulator promotion trap: in the simulator `python_complex * np.float32` is
+        # complex64, so E_field_cal's `phase * Etm_abs` (GRTF:138) would lose precision for amplitudes
+        # other than 0 / 1 -- the JIT-compiled kernel converts float32 -> float64 first and loses nothing.
+        # Feeding the SAME values as float64 arrays makes the simulator compute what the compiled kernel
+        # computes (the reference file itself is untouched; the reference's own PTX then confirms this
+        # fixture on the GPU with real float32 arrays, tests/test_gpu_reference_kernel.py).
+        for k in range(12):
+            args[k] = args[k].astype(np.float64)
     for _ in range(num_iter):
-        GRTF.process_rays_kernel_pro_fullColor[blocks, threads](*scene.kernel_args(EB, rng))
+        GRTF.process_rays_kernel_pro_fullColor[blocks, threads](*args)
         assert np.all(rng != 0)
     nz = np.flatnonzero(EB)
     return lo, hi, rng, nz, EB.ravel()[nz]
@@ -200,6 +222,34 @@ def make_units(procs: int):
                     break
         loc[nm + "_verts"] = verts; loc[nm + "_off"] = np.asarray(off, dtype=np.int64)
         loc[nm + "_pts"] = pts; loc[nm + "_hit"] = res
+    # is_inside_or_on_edge_4d on per-FoV eyebox rectangles, GRTF:73-108: the design's rectangles, a rotated
+    # one and one in another vertex order; points at and around the 1e-9 band of every side and corner
+    eff_reg_FOV = out[7]
+    r0 = np.asarray(eff_reg_FOV[2, 2], dtype=np.float64)
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    ctr = r0.mean(0)
+    rects = [np.asarray(eff_reg_FOV[0, 0]), np.asarray(eff_reg_FOV[4, 3]),
+             (r0 - ctr) @ np.array([[c, -s_], [s_, c]]).T + ctr, r0[[1, 2, 3, 0]],
+             np.array([[0.0, 1.0], [0.0, 0.0], [1.0, 0.0], [1.0, 1.0]])]
+    offs = np.array([0.0, 5e-13, -5e-13, 5e-12, -5e-12, 5e-10, -5e-10, 2e-9, -2e-9, 1e-6, -1e-6])
+    rect_pts, rect_hit = [], []
+    for rect in rects:
+        pts = []
+        for i in range(4):
+            a, b = rect[i - 1], rect[i]
+            d = b - a
+            nrm = np.array([-d[1], d[0]]) / np.hypot(*d)
+            for t in (0.0, 1.0, -1e-3, 1.001, 0.5, 0.137, 0.9):
+                for o in offs:
+                    pts.append(a + t * d + o * nrm)
+            for o in offs:
+                pts.append(b + o * np.array([1.0, 1.0])); pts.append(b + o * np.array([1.0, -1.0]))
+        lo, hi = rect.min(0), rect.max(0)
+        pts = np.concatenate((np.array(pts), rs.uniform(lo - 0.3 * (hi - lo), hi + 0.3 * (hi - lo), size=(200, 2))))
+        fov = np.ascontiguousarray(rect.reshape(1, 1, 4, 2))
+        rect_pts.append(pts)
+        rect_hit.append(np.array([bool(GRTF.is_inside_or_on_edge_4d(float(q[0]), float(q[1]), fov, 0, 0)) for q in pts]))
+    loc["rect_verts"] = np.array(rects); loc["rect_pts"] = np.array(rect_pts); loc["rect_hit"] = np.array(rect_hit)
     path = os.path.join(GOLDEN_DIR, "units.npz")
     np.savez_compressed(path, xs_in=states, xs_out=st, xs_last=last, ef_ete=ete, ef_etm=etm,
                         ef_delta=delta, ef_jones=jones, ef_out=ef, **loc)

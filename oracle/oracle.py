@@ -39,6 +39,8 @@ def lib() -> C.CDLL:
         L = C.CDLL(_LIB)
         L.wgrt_oracle_trace.restype = C.c_int
         L.wgrt_oracle_trace.argtypes = [C.POINTER(WgrtProblem), C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        L.wgrt_oracle_trace_events.restype = C.c_int64
+        L.wgrt_oracle_trace_events.argtypes = [C.POINTER(WgrtProblem), C.c_int64, C.c_void_p, C.c_int64]
         L.wgrt_oracle_locate.restype = C.c_int
         L.wgrt_oracle_locate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p]
@@ -68,6 +70,26 @@ def trace(*args, first: int = 0, count: Optional[int] = None, num_threads: int =
     if counters:
         return {k: int(cnt[i]) for i, k in enumerate(COUNTER_NAMES)}
     return None
+
+
+EVENT_FIELDS = ("state", "u", "e1", "e12", "e123", "x", "y", "ener")
+
+
+def trace_events(*args, idx: int, cap: int = 4096, single_lambda: bool = False, threshold: float = 0.0,
+                 ray_index_base: int = 0) -> np.ndarray:
+    """Walk ray ``idx`` alone and return its decisions as an [n_events, 8] array (EVENT_FIELDS): every draw
+    ``u`` with the cumulative efficiencies it was compared with (state -1 = in-coupling from air; e123 is
+    NaN for two-order events).  Mutates that ray's RNG state and the bins like a one-ray launch."""
+    if single_lambda:
+        args = tuple(args[:8]) + (None,) + tuple(args[8:])
+    prob, keep = pack_problem(args, host=True, single_lambda=single_lambda, threshold=threshold,
+                              ray_index_base=ray_index_base)
+    ev = np.zeros((cap, 8), dtype=np.float64)
+    n = lib().wgrt_oracle_trace_events(C.byref(prob), int(idx), ev.ctypes.data, cap)
+    del keep
+    if n < 0:
+        raise RuntimeError(f"oracle error {n}")
+    return ev[:min(n, cap)]
 
 
 def locate(verts, offsets, px, py):

@@ -46,6 +46,26 @@ typedef struct {
   uint64_t c[WGRT_NUM_COUNTERS];
 } counters_t;
 
+/* Per-decision trace of ONE ray (wgrt_oracle_trace_events, used by tools/triage_mismatch.py): every
+ * draw with the thresholds it is compared with.  8 doubles per event:
+ * state (-1 = in-coupling from air), u, e1, e1+e2, e1+e2+e3 (NaN for two-order events), x, y, ener. */
+typedef struct {
+  double* out;
+  int64_t cap, n;
+} event_trace_t;
+static __thread event_trace_t* g_trace = NULL;
+#define TRACE_EVENT(st, e3v)                                                                   \
+  do {                                                                                         \
+    if (g_trace) {                                                                             \
+      if (g_trace->n < g_trace->cap) {                                                         \
+        double* t_ = g_trace->out + 8 * g_trace->n;                                            \
+        t_[0] = (double)(st); t_[1] = u; t_[2] = e1; t_[3] = e1 + e2; t_[4] = (e3v);           \
+        t_[5] = x; t_[6] = y; t_[7] = ener;                                                    \
+      }                                                                                        \
+      g_trace->n++;                                                                            \
+    }                                                                                          \
+  } while (0)
+
 /* GRTF:25-34 */
 static inline double draw_uniform_at(uint32_t* rng_states, int64_t index, int64_t index_base, counters_t* cn) {
   uint32_t s = rng_states[index];
@@ -270,6 +290,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
   e2 = (o2.te * o2.te + o2.tm * o2.tm) * c_ic3 / c_ic1 * p->n_g;
   u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
   cn->c[WGRT_CNT_DRAW2]++;
+  TRACE_EVENT(-1, NAN);
 #define TAKE(o, e, tir, gx, gy, costh)                 \
   do {                                                 \
     norm = sqrt((o).te * (o).te + (o).tm * (o).tm);    \
@@ -312,6 +333,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
       e2 = (o2.te * o2.te + o2.tm * o2.tm) * c_ic3 / cos_theta;
       u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
       cn->c[WGRT_CNT_DRAW2]++;
+      TRACE_EVENT(state, NAN);
       if (u <= e1) {
         TAKE(o1, e1, 0, 0, 1, c_ic2);
         ener *= e1;
@@ -343,6 +365,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
         double ener1 = ener * e1, ener2 = ener * e2;
         u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
         cn->c[WGRT_CNT_DRAW2]++;
+        TRACE_EVENT(state, NAN);
         if (u <= e1 && ener1 > threshold) {
           TAKE(o1, e1, 0, 0, 1, c_fc1);
           ener = ener1 * 1.0;
@@ -392,6 +415,7 @@ static void walk_ray(const wgrt_problem_t* p, int64_t idx, counters_t* cn) {
         double ener1 = ener * e1, ener2 = ener * e2, ener3 = ener * e3;
         u = draw_uniform_at(p->rng_states, idx, p->ray_index_base, cn);
         cn->c[WGRT_CNT_DRAW3]++;
+        TRACE_EVENT(state, e1 + e2 + e3);
         if (u <= e1 && ener1 > threshold) {
           TAKE(o1, e1, 1, 2, 3, c_oc1);
           ener = ener1 * 1.0;
@@ -488,6 +512,24 @@ int wgrt_oracle_trace(const wgrt_problem_t* p, int64_t first, int64_t count, uin
       for (int k = 0; k < WGRT_NUM_COUNTERS; ++k) counters[k] += ws[t].local.c[k];
   free(ws); free(th);
   return bad ? WGRT_ERR_INVALID : WGRT_OK;
+}
+
+/* Walk ray `idx` of a HOST problem alone and record its decisions (see event_trace_t).  Mutates the
+ * ray's RNG state and the bins like a launch over that one ray.  Returns the number of events
+ * (which may exceed `cap`; only the first `cap` are stored) or a negative error code. */
+int64_t wgrt_oracle_trace_events(const wgrt_problem_t* p, int64_t idx, double* events, int64_t cap) {
+  int rc = check_problem(p);
+  if (rc != WGRT_OK) return rc;
+  if (idx < 0 || idx >= p->num_rays || !events || cap < 0) return WGRT_ERR_INVALID;
+  int64_t m = (int64_t)p->m[idx], n = (int64_t)p->n[idx], lm = p->lmd_num ? (int64_t)p->lmd_num[idx] : 0;
+  if (m < 0 || m >= p->X || n < 0 || n >= p->Y || lm < 0 || lm >= p->L) return WGRT_ERR_INVALID;
+  counters_t cn;
+  memset(&cn, 0, sizeof cn);
+  event_trace_t tr = {events, cap, 0};
+  g_trace = &tr;
+  walk_ray(p, idx, &cn);
+  g_trace = NULL;
+  return tr.n;
 }
 
 /* ---- unit-level entry points (same contracts as the wgrt_debug_* functions) --------------- */

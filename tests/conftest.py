@@ -28,7 +28,7 @@ def load_golden_walk(name):
         design = WaveguideDesign(**recipe["design"])
     scene = si.make_scene(recipe["num_FOV_x"], recipe["num_FOV_y"], recipe["num_rays_per_FoV"],
                           seed=recipe["seed"], lmd_subset=recipe.get("lmd_subset"), eff=recipe.get("eff"),
-                          eb=tuple(recipe.get("eb", (80, 120))), design=design)
+                          eb=tuple(recipe.get("eb", (80, 120))), design=design, ray_pol=recipe.get("ray_pol"))
     return scene, g
 
 

@@ -61,7 +61,7 @@ def assert_same(a, b, what):
 def test_reference_kernel_reproduces_simulator_golden():
     """The PTX really is the reference: it reproduces the fixtures its CPU simulator produced."""
     from conftest import golden_bins, load_golden_walk
-    for name in ("walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin"):
+    for name in ("walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin", "walk_mix", "walk_pol"):
         scene, g = load_golden_walk(name)
         got = run_reference(scene, int(g["num_iter"]))
         assert_same(got, (golden_bins(g), g["rng_states"]), name)
@@ -72,9 +72,19 @@ def test_reference_kernel_reproduces_simulator_golden():
     dict(nx=5, ny=5, rays=64, seed=101, lmd=[1], it=4),             # BASELINE config 1
     dict(nx=20, ny=15, rays=5000, seed=201, lmd=None, it=2),        # 4.5 M rays, runner-sized cells
     dict(nx=41, ny=41, rays=1000, seed=202, lmd=None, it=1),        # BASELINE config 3 grid, 5 M rays
+    # strong polarisation mixing (cross-pol 0.3-0.7 of the diagonal Jones entries, random phases, order
+    # efficiencies summing near 1): 1.44 M rays x 2 launches
+    dict(nx=12, ny=10, rays=4000, seed=205, lmd=None, it=2,
+         eff=dict(incouple=0.6, incouple_m1=0.25, ic_zero=0.55, ic_cross=0.3, fc_zero=0.5, fc_turn=0.33,
+                  oc_zero=0.55, oc_cross=0.25, outcouple=0.08, cross_pol=(0.3, 0.7))),
+    # general (elliptical) input polarisation, delta_phase != 0
+    dict(nx=12, ny=10, rays=4000, seed=206, lmd=None, it=1, ray_pol="mixed",
+         eff=dict(incouple=0.8, incouple_m1=0.1, ic_zero=0.85, ic_cross=0.08, fc_zero=0.7, fc_turn=0.25,
+                  oc_zero=0.8, oc_cross=0.08, outcouple=0.08, cross_pol=(0.1, 0.3))),
 ])
 def test_engine_equals_reference_kernel(cfg):
-    scene = si.make_scene(cfg["nx"], cfg["ny"], cfg["rays"], seed=cfg["seed"], lmd_subset=cfg["lmd"])
+    scene = si.make_scene(cfg["nx"], cfg["ny"], cfg["rays"], seed=cfg["seed"], lmd_subset=cfg["lmd"],
+                          eff=cfg.get("eff"), ray_pol=cfg.get("ray_pol"))
     want = run_reference(scene, cfg["it"])
     assert want[0].sum() > 0
     assert_same(run_engine(KERNEL, scene, cfg["it"]), want, "fast vs reference kernel")

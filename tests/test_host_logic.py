@@ -217,3 +217,26 @@ def test_no_cpu_fallback(small_scene):
     with pytest.raises(Exception):
         GRTF.process_rays_kernel_pro_fullColor[1, 256](*small_scene.kernel_args(EB))
     assert EB.sum() == 0
+
+
+def test_strided_device_views_are_rejected():
+    """the C-contiguity check of __cuda_array_interface__ buffers must ignore only the strides of
+    axes of extent 1 -- a strided view with a singleton axis is still strided."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.GPU_ray_tracing_functions import _describe
+
+    class Fake:
+        def __init__(self, shape, strides, typestr="<f4"):
+            self.__cuda_array_interface__ = {"data": (4096, False), "shape": shape, "typestr": typestr,
+                                             "strides": strides, "version": 3}
+
+    _describe(Fake((1, 5, 4), (80, 16, 4)), "ok")              # dense
+    _describe(Fake((1, 5, 4), (12345, 16, 4)), "ok")           # singleton axis: its stride is irrelevant
+    _describe(Fake((3, 1, 4), (16, 999, 4)), "ok")
+    _describe(Fake((0, 4), (1, 1)), "ok")                      # empty
+    _describe(Fake((5, 4), None), "ok")
+    for shape, strides in (((1, 5, 4), (160, 32, 8)),          # L = 1 table, every other element
+                           ((3, 1, 4), (32, 32, 8)),
+                           ((5, 4), (4, 20)),                  # transposed
+                           ((2, 3, 4), (96, 16, 4))):          # padded rows
+        with pytest.raises(ValueError):
+            _describe(Fake(shape, strides), "bad")

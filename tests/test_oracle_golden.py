@@ -7,7 +7,7 @@ import pytest
 
 from conftest import GOLDEN, golden_bins, input_digest, load_golden_walk
 
-WALKS = ["walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin"]
+WALKS = ["walk_small", "walk_c1", "walk_mid", "walk_deep", "walk_fine", "walk_thin", "walk_mix", "walk_pol"]
 
 
 @pytest.mark.parametrize("name", WALKS)
@@ -71,6 +71,32 @@ def test_polygon_unit(ring, oracle):
     hit = oracle.locate(g[ring + "_verts"], g[ring + "_off"], pts[:, 0], pts[:, 1])
     assert np.array_equal(hit, g[ring + "_hit"])
     assert (hit >= 0).any() and (hit < 0).any()
+
+
+def test_eyebox_rectangle_unit(oracle):
+    """is_inside_or_on_edge_4d (GRTF:100-108) evaluated by the reference on eyebox rectangles (the design's, a
+    rotated one, another vertex order, the unit square) at and around the 1e-9 band of every side / corner."""
+    g = np.load(os.path.join(GOLDEN, "units.npz"))
+    for k in range(len(g["rect_verts"])):
+        pts = g["rect_pts"][k]
+        hit = oracle.locate(g["rect_verts"][k], np.array([0, 4]), pts[:, 0], pts[:, 1]) >= 0
+        assert np.array_equal(hit, g["rect_hit"][k]), k
+        assert hit.any() and not hit.all()
+
+
+def test_event_trace_is_consistent_with_the_walk(oracle, small_scene):
+    """oracle.trace_events (used by tools/triage_mismatch.py): one row per draw, and replaying a ray alone
+    leaves the RNG state the launch leaves."""
+    EB = small_scene.new_matrix_EB(); rng = small_scene.rays.rng_states.copy()
+    c = oracle.trace(*small_scene.kernel_args(EB, rng), counters=True)
+    draws = 0
+    rng1 = small_scene.rays.rng_states.copy()
+    for i in range(0, small_scene.rays.num_rays, 7):
+        ev = oracle.trace_events(*small_scene.kernel_args(small_scene.new_matrix_EB(), rng1), idx=i)
+        assert rng1[i] == rng[i] and len(ev) >= 1 and ev[0, 0] == -1
+        assert np.all((ev[:, 1] > 0) & (ev[:, 1] < 1)) and np.all(ev[:, 3] >= ev[:, 2])
+        draws += len(ev)
+    assert 0 < draws <= c["draws"]
 
 
 def test_counters_consistent(oracle, small_scene):
