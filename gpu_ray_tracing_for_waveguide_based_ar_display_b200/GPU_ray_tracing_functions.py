@@ -287,6 +287,33 @@ def pack_problem(args: Sequence[Any], host: bool, flags: int = 0, tile_hint: int
     return p, [b.owner for b in bufs if b is not None]
 
 
+_LUT_ARGS = range(23, 30)          # lut_ic1 .. lut_oc2
+_warned_c64 = False
+
+
+def _as_complex128(a: Any, name: str) -> Any:
+    """The engine reads the RCWA tables as complex128.  A complex64 table (the dtype of the reference's
+    ``.npy`` files is unknown: they are not reachable) is converted -- host arrays with NumPy, device
+    buffers on the device -- instead of being rejected where Numba would have compiled a kernel for it.
+    Note that the reference itself would then evaluate parts of ``E_field_cal`` in single precision;
+    the engine computes in double on the widened values."""
+    global _warned_c64
+    cai = getattr(a, "__cuda_array_interface__", None)
+    dt = np.dtype(cai["typestr"]) if cai is not None else getattr(a, "dtype", None)
+    if dt != np.dtype(np.complex64):
+        return a
+    if not _warned_c64:
+        import warnings
+        warnings.warn(f"{name}: complex64 look-up table converted to complex128 for the launch", RuntimeWarning,
+                      stacklevel=3)
+        _warned_c64 = True
+    if cai is None:
+        return np.ascontiguousarray(a, dtype=np.complex128)
+    import torch
+    t = torch.as_tensor(a, device="cuda").to(torch.complex128).contiguous()
+    return _TorchAlias(torch.view_as_real(t), tuple(cai["shape"]), np.complex128)
+
+
 def _stream_handle(stream: Any) -> int:
     if stream is None or stream == 0:
         return 0
@@ -357,6 +384,8 @@ class RayWalkKernel:
         if len(args) != len(_ARG_NAMES):
             raise TypeError(f"process_rays_kernel_pro_fullColor takes {len(_ARG_NAMES)} positional "
                             f"arguments ({len(args)} given)")
+        args = tuple(_as_complex128(a, _ARG_NAMES[i]) if i in _LUT_ARGS and a is not None else a
+                     for i, a in enumerate(args))
         staged = []        # (host ndarray, device tensor, copy_back)
         dev_args = list(args)
         any_host = False

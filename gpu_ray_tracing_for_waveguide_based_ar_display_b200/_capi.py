@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwgrt.so")
+CHECKED_LIB_PATH = os.path.join(_HERE, "libwgrt_checked.so")   # -DWGRT_CHECKED build: bounds assertions in the walk
 
 WGRT_OK = 0
 WGRT_FLAG_STRICT = 0x1
@@ -55,6 +56,11 @@ class WgrtError(RuntimeError):
     pass
 
 
+class WgrtInvalidArgument(WgrtError, ValueError):
+    """WGRT_ERR_INVALID: an argument the library rejected (also a ``ValueError``, which is what the Python
+    layer raises for the checks it can do itself)."""
+
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/wgrt.h declares
@@ -63,7 +69,7 @@ EXPORTED_SYMBOLS = (
     "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host", "wgrt_trace_evaluate_host",
     "wgrt_counters_read", "wgrt_counters_reset",
     "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
-    "wgrt_debug_deposit_inside", "wgrt_debug_set_tie_tolerance",
+    "wgrt_debug_deposit_inside", "wgrt_debug_set_tie_tolerance", "wgrt_debug_check_failures",
     "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host", "wgrt_bins_pack_u8", "wgrt_bins_unpack_u8",
 )
 
@@ -110,6 +116,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_debug_xorshift.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     lib.wgrt_debug_deposit_inside.restype = C.c_int
     lib.wgrt_debug_deposit_inside.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    lib.wgrt_debug_check_failures.restype = C.c_int
+    lib.wgrt_debug_check_failures.argtypes = [C.c_void_p, C.c_int]
     lib.wgrt_debug_set_tie_tolerance.restype = C.c_int
     lib.wgrt_debug_set_tie_tolerance.argtypes = [C.c_double]
     lib.wgrt_debug_fma_peak.restype = C.c_int
@@ -129,7 +137,8 @@ def check(rc: int, lib: Optional[C.CDLL] = None) -> None:
     if rc != WGRT_OK:
         lib = lib or load_library()
         msg = lib.wgrt_last_error()
-        raise WgrtError(f"libwgrt error {rc}: {msg.decode() if msg else '?'}")
+        cls = WgrtInvalidArgument if rc == -1 else WgrtError
+        raise cls(f"libwgrt error {rc}: {msg.decode() if msg else '?'}")
 
 
 def np_ptr(a: np.ndarray) -> int:

@@ -12,6 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libwgrt.so")
+OUT_CHECKED = os.path.join(PKG, "libwgrt_checked.so")
 OBJ_DIR = os.path.join(HERE, "build")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -49,28 +50,34 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> str:
+    """``checked=True`` builds libwgrt_checked.so: the same sources with -DWGRT_CHECKED (bounds assertions
+    in the production walk, see wgrt_device.cuh), used by tests/test_gpu_checked_build.py."""
+    obj_dir = os.path.join(OBJ_DIR, "checked") if checked else OBJ_DIR
+    out = OUT_CHECKED if checked else OUT
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
     for src, extra in UNITS.items():
         s = os.path.join(HERE, src)
-        o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, *ARCH, *COMMON, *_host_compiler_args(), *extra, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *COMMON, *_host_compiler_args(), *extra, *(["-DWGRT_CHECKED"] if checked else []),
+                   "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
-    if force or _stale(OUT, objs):
-        cmd = [nvcc, *ARCH, "-shared", *_host_compiler_args(), "-o", OUT, *objs, "-lcudart"]
+    if force or _stale(out, objs):
+        cmd = [nvcc, *ARCH, "-shared", *_host_compiler_args(), "-o", out, *objs, "-lcudart"]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose=False, checked=True))

@@ -828,6 +828,18 @@ int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last
   return WGRT_OK;
 }
 
+int wgrt_debug_check_failures(uint64_t* out, int reset) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out) return fail(WGRT_ERR_INVALID, "bad arguments");
+  CUDA_TRY(cudaDeviceSynchronize());
+  unsigned long long v = 0;
+  cudaError_t e = walk_check_failures(&v, reset != 0);
+  if (e == cudaErrorNotSupported) return fail(WGRT_ERR_UNSUPPORTED, "not a checked build (libwgrt_checked.so)");
+  CUDA_TRY(e);
+  *out = v;
+  return WGRT_OK;
+}
+
 int wgrt_debug_set_tie_tolerance(double tol) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (tol != tol) return fail(WGRT_ERR_INVALID, "tolerance is NaN");

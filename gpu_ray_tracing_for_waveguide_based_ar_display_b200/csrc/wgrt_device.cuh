@@ -10,6 +10,21 @@
 
 #include "../../include/wgrt.h"
 
+// Checked build (libwgrt_checked.so, -DWGRT_CHECKED): every index the production walk forms into shared
+// memory, the Jones scratch, the atlas, the region grids and the ray / bin arrays is asserted to be in
+// range; violations are counted (wgrt_debug_check_failures) instead of corrupting memory.  This stands in
+// for compute-sanitizer's memcheck, which the GPU pool does not allow.  In the normal build the macro
+// vanishes.
+#if defined(WGRT_CHECKED) && defined(WGRT_CHECK_TU)
+static __device__ unsigned long long wgrt_check_fail_count;
+#define WGRT_CHECK(cond)                                              \
+  do {                                                                \
+    if (!(cond)) atomicAdd(&wgrt_check_fail_count, 1ull);             \
+  } while (0)
+#else
+#define WGRT_CHECK(cond) ((void)0)
+#endif
+
 namespace wgrt {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
@@ -154,6 +169,7 @@ __device__ __forceinline__ void deposit_bin(const wgrt_problem_t& p, int64_t lm,
   const int64_t iy = static_cast<int64_t>(floor((y - ymin) / dy));
   const int64_t flat = (((lm * p.Y + n) * p.X + m) * p.EBy + iy) * p.EBx + ix;
   const int64_t total = p.L * p.Y * p.X * p.EBy * p.EBx;
+  WGRT_CHECK(ix >= 0 && ix <= p.EBx && iy >= 0 && iy <= p.EBy);   // == only for a point exactly on the max edge
   if (flat >= 0 && flat < total) atomicAdd(p.matrix_EB + flat, 1.0f);
 }
 
@@ -198,6 +214,7 @@ struct RegionSet {
 cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* counters, cudaStream_t s);
 cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s);
 void set_tie_tolerance(double tol);
+cudaError_t walk_check_failures(unsigned long long* out, bool reset);   // cudaErrorNotSupported unless WGRT_CHECKED
 cudaError_t launch_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n, int32_t* out,
                                         int literal, cudaStream_t s);
 size_t walk_warp_scratch_bytes(const wgrt_problem_t& p, int num_sms);

@@ -73,6 +73,7 @@ __device__ __forceinline__ bool ring_test_masked(double px, double py, const dou
       const int i = (w << 5) + __ffs(bits) - 1;
       bits &= bits - 1;
       const int j = (i == s) ? e - 1 : i - 1;
+      WGRT_CHECK(i >= s && i < e && j >= s && j < e);
       const double2 vi = __ldg(reinterpret_cast<const double2*>(verts) + i);
       const double2 vj = __ldg(reinterpret_cast<const double2*>(verts) + j);
       // GRTF:68 calls point_on_segment(px, py, poly, start + j, start + i)
@@ -94,8 +95,10 @@ __host__ __device__ __forceinline__ uint32_t pack_detail(int first, int stop, in
 template <bool COUNT>
 __device__ __noinline__ int region_locate_exact(const Region& r, double x, double y, int cell, int iy, Counts* cn) {
   if (COUNT) cn->c[WGRT_CNT_EXACT_FALLBACK]++;
+  WGRT_CHECK(cell >= 0 && cell < r.n * r.n && iy >= 0 && iy < r.n);
   const uint32_t d = __ldg(r.detail + cell);
   const int first = d & 0xff, stop = (d >> 8) & 0xff, dflt = (d >> 16) & 0xff;
+  WGRT_CHECK(first <= stop && stop <= r.npoly && (dflt == 255 || dflt < r.npoly));
   const uint32_t* mask = r.rowmask + static_cast<size_t>(iy) * r.words;
   for (int k = first; k < stop; ++k) {
     const int s = ring_begin(r.offsets, r.nverts, k), e = ring_begin(r.offsets, r.nverts, k + 1);
@@ -115,6 +118,7 @@ __device__ __forceinline__ int region_locate(const Region& r, double x, double y
   const double lim = static_cast<double>(r.n);
   if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return -1;
   const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
+  WGRT_CHECK(ix >= 0 && ix < r.n && iy >= 0 && iy < r.n && (iy >> r.shift) < r.nc && (ix >> r.shift) < r.nc);
   uint8_t code = __ldg(r.coarse + (iy >> r.shift) * r.nc + (ix >> r.shift));
   if (code == CELL_AMBIG) {  // MIXED coarse cell: ask the fine level
     const int cell = iy * r.n + ix;
@@ -182,10 +186,12 @@ __device__ __forceinline__ uint32_t atlas_lookup(const Atlas& a, double x, doubl
   const double fx = (x - a.x0) * a.inv_dx, fy = (y - a.y0) * a.inv_dy;
   const double lim = static_cast<double>(ATLAS_N);
   if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return ATLAS_OUTSIDE;   // also NaN
+  WGRT_CHECK(static_cast<int>(fx) >= 0 && static_cast<int>(fx) < ATLAS_N && static_cast<int>(fy) >= 0 && static_cast<int>(fy) < ATLAS_N);
   uint32_t word = __ldg(a.words + static_cast<int>(fy) * ATLAS_N + static_cast<int>(fx));
   if (word & ATLAS_ANY_MIXED) {
     const double sub = static_cast<double>(1 << ATLAS_SUB_SHIFT);
     const int ix = min(static_cast<int>(fx * sub), ATLAS_N2 - 1), iy = min(static_cast<int>(fy * sub), ATLAS_N2 - 1);
+    WGRT_CHECK(ix >= 0 && iy >= 0 && (ix >> ATLAS_SUB_SHIFT) == static_cast<int>(fx) && (iy >> ATLAS_SUB_SHIFT) == static_cast<int>(fy));
     word = __ldg(a.words2 + static_cast<size_t>(iy) * ATLAS_N2 + ix);
   }
   return word;

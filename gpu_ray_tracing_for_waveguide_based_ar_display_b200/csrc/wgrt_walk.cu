@@ -36,6 +36,7 @@
 //  * Everything state dependent is table driven from shared memory (per-cell event rows, sinfo).
 #include <climits>
 
+#define WGRT_CHECK_TU 1   // this translation unit carries the bounds assertions of the checked build
 #include "wgrt_region.cuh"
 
 namespace wgrt {
@@ -481,6 +482,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           const unsigned surv = __ballot_sync(FULL_MASK, k >= 0);
           if (k >= 0) {
             const int slot = qn + __popc(surv & lt_mask);
+            WGRT_CHECK(slot >= 0 && slot < QUEUE_CAP && i >= t_begin && i < t_end);
             sh.q.idx[slot] = static_cast<uint32_t>(i - t_begin) | (static_cast<uint32_t>(k) << 31);
             sh.q.rng[slot] = frng;
             sh.q.esel[slot] = esel;
@@ -497,6 +499,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           const int rank = __popc(dead & lt_mask);
           if (r.state == ST_DEAD && rank < take) {
             const int slot = qn - 1 - rank;
+            WGRT_CHECK(slot >= 0 && slot < QUEUE_CAP);
             const uint32_t e = sh.q.idx[slot];
             r.idx = static_cast<int>(e & 0x7fffffffu);
             r.rng = sh.q.rng[slot];
@@ -534,6 +537,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         double esel = 1.0;
         if (at_event) {
           if (r.iter >= 0) {
+            WGRT_CHECK(r.row0 >= 0 && r.row0 + 1 < rows && t_begin + r.idx < t_end);
             const double* e = tab + r.row0 * ROW;
             const int meta0 = static_cast<int>(__double_as_longlong(e[R_META]));
             const bool three = (meta0 & META_THREE) != 0;
@@ -549,6 +553,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double zre = r.te.re * r.tm.re + r.te.im * r.tm.im;   // conj(te) * tm
             const double zim = r.te.re * r.tm.im - r.te.im * r.tm.re;
             const double g = r.s * r.inv_cos;
+            WGRT_CHECK(!three || r.row0 + 2 < rows);
             const double* e3 = three ? e + 2 * ROW : e;                 // two-order events: never selected
             const double e1 = (e[R_Q] * t2 + e[R_Q + 1] * m2 + (e[R_Q + 2] * zre + e[R_Q + 3] * zim)) * g;
             const double e2 = (e[ROW + R_Q] * t2 + e[ROW + R_Q + 1] * m2 + (e[ROW + R_Q + 2] * zre + e[ROW + R_Q + 3] * zim)) * g;
@@ -584,6 +589,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               lost = false;
             }
           } else {
+            WGRT_CHECK(r.row0 >= 0 && r.row0 + k < rows && k <= 2);
             const double* row = tab + (r.row0 + k) * ROW;
             const int meta = static_cast<int>(__double_as_longlong(row[R_META]));
             const int post = (meta >> 7) & 3;
@@ -630,6 +636,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           }
           r.row0 = -1;
           if (lost) {
+            WGRT_CHECK(r.idx >= 0 && t_begin + r.idx < t_end);
             st_stream(p.rng_states + t_begin + r.idx, r.rng);
             r.state = ST_DEAD;
             lost = false;
@@ -652,6 +659,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             if (COUNT) cn.c[WGRT_CNT_ITERS]++;
             lost = ++r.iter > 100000 || !in_r1;
           }
+          WGRT_CHECK(st >= 0 && st < 6);
           int sinfo = cc.sinfo[st];
           int region = sinfo & SI_REGION_MASK;
           int code = region == REG_FC ? fc : region == REG_OC ? oc : 0;
@@ -666,6 +674,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           if (!lost) {
             if (code != CELL_NONE) {
               r.row0 = ((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code;
+              WGRT_CHECK(r.row0 >= 2 && r.row0 + 1 < rows);
             } else if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) {
               lost = true;                       // GRTF:1244-1246
             } else {
@@ -747,6 +756,20 @@ cudaError_t launch_debug_deposit_inside(const double* rect, const double* px, co
   if (n == 0) return cudaSuccess;
   deposit_inside_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(rect, px, py, n, out, literal);
   return cudaGetLastError();
+}
+
+cudaError_t walk_check_failures(unsigned long long* out, bool reset) {
+#if defined(WGRT_CHECKED)
+  cudaError_t e = cudaMemcpyFromSymbol(out, wgrt_check_fail_count, sizeof(unsigned long long));
+  if (e == cudaSuccess && reset) {
+    const unsigned long long zero = 0;
+    e = cudaMemcpyToSymbol(wgrt_check_fail_count, &zero, sizeof zero);
+  }
+  return e;
+#else
+  (void)out; (void)reset;
+  return cudaErrorNotSupported;
+#endif
 }
 
 void set_tie_tolerance(double tol) { g_tie_tol = tol >= 0.0 ? tol : TIE_TOL_DEFAULT; }

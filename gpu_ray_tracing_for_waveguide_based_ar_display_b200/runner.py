@@ -15,7 +15,7 @@ from typing import Dict, Optional, Tuple
 import numpy as np
 
 from . import _capi
-from .GPU_ray_tracing_functions import pack_problem
+from .GPU_ray_tracing_functions import _as_complex128, pack_problem
 
 __all__ = ["trace_full_color", "trace_and_evaluate"]
 
@@ -44,6 +44,7 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
     Returns the bin tensor (host).
     """
     lib = _capi.load_library()
+    luts = {k: _as_complex128(v, k) for k, v in luts.items()}
     P = num_rays_per_FoV // 2
     if points.shape != (P, 2) or 2 * P != num_rays_per_FoV:
         raise ValueError("points must be [num_rays_per_FoV/2, 2]")
@@ -94,6 +95,7 @@ def trace_and_evaluate(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: flo
     """
     from . import AR_system_evaluation_functions as EV
     lib = _capi.load_library()
+    luts = {k: _as_complex128(v, k) for k, v in luts.items()}
     P = num_rays_per_FoV // 2
     if points.shape != (P, 2) or 2 * P != num_rays_per_FoV:
         raise ValueError("points must be [num_rays_per_FoV/2, 2]")

@@ -258,6 +258,12 @@ int wgrt_debug_xorshift(uint32_t* states, int64_t n, int draws, double* out_last
 int wgrt_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n_points,
                               int32_t* out, int mode);
 
+/* Checked build only (libwgrt_checked.so, compiled with -DWGRT_CHECKED; WGRT_ERR_UNSUPPORTED otherwise):
+ * number of violated bounds assertions in the production walk since the last reset -- every index it forms
+ * into shared memory, the Jones scratch, the atlas / region grids and the ray arrays is asserted there.
+ * Synchronises the device.  (Stand-in for compute-sanitizer memcheck, which the GPU pool does not allow.) */
+int wgrt_debug_check_failures(uint64_t* out, int reset);
+
 /* Near-tie tolerance of the fast walk (default 1e-10; negative restores it): a ray whose uniform draw
  * lands within `tol` of a threshold it is compared with is re-walked with the reference's literal
  * expressions instead of being decided by the reformulated arithmetic.  Tests widen it (e.g. 0.05) to
