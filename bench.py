@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the partitioned config-3 sub-record")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded baseline sample")
     return ap.parse_args()
 
@@ -230,27 +231,27 @@ def reference_arm(args, nx, ny, rpc, eb):
 
 
 # ------------------------------------------------------------------------------------------------
-def partitioned_arm(args, nx, ny, rpc, eb):
+def partitioned_record(args, nx, ny, rpc, eb, world, rank, local_rank, workload, sample_clocks=True):
     """Strong scaling on BASELINE.json configs[2]: the job's FoV-wavelength cells are split into contiguous
-    ranges (multi_gpu.cell_range), every rank walks its range device resident with the runner layout and
-    the GLOBAL RNG seeds (RUN:158) for K launches, then one NCCL all-reduce sums the bins.  Rank 0 checks
-    the reduced bins against the same job walked on its GPU alone: they must be bit-equal."""
+    ranges (multi_gpu.cell_range) and every rank walks its range with the runner layout and the GLOBAL RNG
+    seeds (RUN:158).  A cell's deposits land in its own tile of matrix_EB, so the ranks' outputs are disjoint:
+    NO collective is needed -- `value` times K launches of every rank's range, device
+    resident; `e2e` is multi_gpu.trace_partitioned from pinned host memory to pinned host memory (each rank
+    uploads only its table columns, downloads only its matrix_EB columns).  Outside the timed regions the
+    ranks' bins are summed onto rank 0 and compared with the same job walked on rank 0's GPU alone: they
+    must be bit-equal.  Returns the record (rank 0) or None."""
+    import contextlib
     import torch
     import torch.distributed as dist
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, multi_gpu, synthetic_inputs as si
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    _capi.load_library()
     scene = si.make_scene(nx, ny, 2, eb=eb, seed=2024)             # tables; the rays are implicit
     pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2025)
     L = scene.eb_shape[0]
     n_cells = nx * ny * L
     c0, c1 = multi_gpu.cell_range(n_cells, world, rank)
     stream = torch.cuda.current_stream()
+    steps, warm = args.steps, max(args.warmup, 3)
 
     def to_dev(a):
         v = a.view(np.float64) if a.dtype == np.complex128 else a
@@ -280,56 +281,130 @@ def partitioned_arm(args, nx, ny, rpc, eb):
 
     launch, a, rng, ebt = job(c0, c1 - c0)
     rng0 = rng._t.clone()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warm):
         launch(*a)
-    if world > 1:
-        multi_gpu.reduce_bins(ebt._t)                             # NCCL warm-up
     torch.cuda.synchronize()
     rng._t.copy_(rng0); ebt._t.zero_()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
+    # the clock sampler (rank 0 only) starts BEFORE the barrier: its start-up must not skew the ranks
+    with (ClockSampler(local_rank) if (rank == 0 and sample_clocks) else contextlib.nullcontext()) as clocks:
+        barrier()
         ev0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             launch(*a)
-        if world > 1:
-            multi_gpu.reduce_bins(ebt._t)
         ev1.record(stream)
         barrier()
-    t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
+    mine_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([mine_ms], device="cuda", dtype=torch.float64)
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        per_rank = [t.clone()]
     ms = float(t.item())
     # bounces of the timed launches: replay with counters
     claunch, ca, crng, cebt = job(c0, c1 - c0, counters=True)
     _capi.reset_counters()
-    for _ in range(args.steps):
+    for _ in range(steps):
         claunch(*ca)
     cnt = _capi.read_counters()
-    bt = torch.tensor([cnt["bounces"], cnt["rays"]], device="cuda", dtype=torch.float64)
+    bt = torch.tensor([cnt["bounces"], cnt["rays"], cnt["near_tie"]], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(bt)
-    del crng, cebt
-    same = None
+    del crng, cebt, claunch, ca
+
+    # ---- end to end: pinned host -> pinned host through multi_gpu.trace_partitioned, no collective -----
+    pin_keep, geom_p, luts_p = [], {}, {}
+    for src, dst in ((scene.geom, geom_p), (scene.luts, luts_p)):
+        for k, v in src.items():
+            tpin, view = pinned_like(v)
+            pin_keep.append(tpin); dst[k] = view
+    tpin, eb_view = pinned_like(scene.new_matrix_EB())
+    pin_keep.append(tpin)
+    m0 = m1 = 0
+    for _ in range(2):
+        _, (m0, m1) = multi_gpu.trace_partitioned(pts, geom_p, scene.n_g, luts_p, rpc, world, rank, num_iter=1,
+                                                  eb=eb, matrix_EB=eb_view)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        multi_gpu.trace_partitioned(pts, geom_p, scene.n_g, luts_p, rpc, world, rank, num_iter=1, eb=eb,
+                                    matrix_EB=eb_view)
+    tw = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    wall = float(tw.item())
+    cols = m1 - m0
+    frac_cols = cols / nx
+    h2d = sum(v.nbytes for k, v in list(geom_p.items()) + list(luts_p.items())
+              if k.startswith("lut_") or k.startswith("eff_reg_FOV")) * frac_cols + pts.shape[0] * 8
+    d2h = eb_view.nbytes * frac_cols
+    # one launch of this rank's range from the same seeds on the device == the columns that came back
+    l1, a1, r1, e1 = job(c0, c1 - c0)
+    l1(*a1)
+    torch.cuda.synchronize()
+    own = e1._t.cpu().numpy().reshape(scene.eb_shape)
+    e2e_same = bool(np.array_equal(own[:, :, m0:m1], eb_view[:, :, m0:m1]))
+    io = torch.tensor([h2d, d2h, 1.0 if e2e_same else 0.0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(io)
+    del l1, a1, r1, e1, own, pin_keep, geom_p, luts_p, eb_view
+
+    # ---- correctness, outside the timed regions: sum of the ranks' (disjoint) bins == the 1-GPU job ----
+    total = ebt._t.clone()
+    if world > 1:
+        dist.reduce(total, dst=0)
+    rec = None
     if rank == 0:
         flaunch, fa, frng, febt = job(0, n_cells)
-        for _ in range(args.steps):
+        for _ in range(steps):
             flaunch(*fa)
         torch.cuda.synchronize()
-        same = bool(torch.equal(febt._t, ebt._t))
-        line = {"metric": METRIC, "value": float(bt[0].item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / max(args.steps, 1),
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "num_FOV_x": nx, "num_FOV_y": ny, "wavelengths": L,
-                           "rays_per_FoV": rpc, "rays_per_launch_all_gpus": n_cells * rpc, "eyebox_bins": list(eb),
-                           "partition": f"contiguous FoV-wavelength cell ranges, {n_cells} cells over {world} ranks, "
-                                        "global RNG seeds, one NCCL all-reduce of the bins inside the timed region",
-                           "l2_policy": "runner layout: per-launch inputs are the RNG states (2 GB over all ranks) > L2"},
-                "rays_per_s": float(bt[1].item()) / (ms * 1e-3), "full_colour_wall_ms": ms,
-                "deposits": float(ebt._t.sum(dtype=torch.float64).item()),
-                "reduced_bins_bit_equal_to_single_gpu_job": same,
-                "gpu_launches": args.steps * 9, "clocks": clocks.summary()}
-        print(json.dumps(line), flush=True)
+        same = bool(torch.equal(febt._t, total))
+        bounces_per_launch = float(bt[0].item()) / max(steps, 1)
+        rec = {"metric": METRIC, "value": float(bt[0].item()) / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+               "steps": steps, "warmup": warm, "ms_per_step": ms / max(steps, 1),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": workload, "num_FOV_x": nx, "num_FOV_y": ny, "wavelengths": L,
+                          "rays_per_FoV": rpc, "rays_per_launch_all_gpus": n_cells * rpc, "eyebox_bins": list(eb),
+                          "partition": f"contiguous FoV-wavelength cell ranges, {n_cells} cells over {world} ranks, global RNG "
+                                       "seeds; the ranks' bins are disjoint: no collective (each rank keeps / downloads "
+                                       "the FoV-x columns of its cells)",
+                          "l2_policy": "runner layout: per-launch inputs are the RNG states (2 GB over all ranks) > L2"},
+               "rays_per_s": float(bt[1].item()) / (ms * 1e-3), "full_colour_wall_ms": ms,
+               "per_rank_walk_ms_per_step": [float(x.item()) / max(steps, 1) for x in per_rank],
+               "collective_ms": 0.0, "near_tie_rays": int(bt[2].item()),
+               "deposits": float(total.sum(dtype=torch.float64).item()),
+               "summed_bins_bit_equal_to_single_gpu_job": same,
+               "e2e": {"value": bounces_per_launch * steps / wall, "unit": UNIT, "ms_per_step": wall / max(steps, 1) * 1e3,
+                       "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+                       "api": "multi_gpu.trace_partitioned -> wgrt_trace_fullcolor_host (runner layout, WGRT_FLAG_BINS_COLUMNS): "
+                              "per rank H2D of its table columns, walk of its cell range, D2H of its matrix_EB columns; "
+                              "one launch per call, pinned host buffers, no collective",
+                       "columns_bit_equal_to_device_launch": bool(io[2].item() == world)},
+               "gpu_launches": steps * 10}
+        if clocks is not None:
+            rec["clocks"] = clocks.summary()
+    del total
+    torch.cuda.empty_cache()
+    return rec
+
+
+def partitioned_arm(args, nx, ny, rpc, eb):
+    """--workload c3_...: the partitioned arm alone, printed as the run's JSON line."""
+    import torch
+    import torch.distributed as dist
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _capi.load_library()
+    rec = partitioned_record(args, nx, ny, rpc, eb, world, rank, local_rank, args.workload)
+    if rank == 0:
+        print(json.dumps(rec), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -383,34 +458,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    import contextlib
+    reducer = multi_gpu.BinReducer(eb_t.numel(), eb_t.device) if world > 1 else None
     for _ in range(max(args.warmup, 3)):
         launch(*dev_args)
     if world > 1:
-        multi_gpu.reduce_bins(eb_t)  # NCCL warm-up at the timed message size (first use sets up its channels)
+        for _ in range(3):   # NCCL warm-up at the timed message size (the first uses set up channels and pick the algorithm)
+            reducer.reduce_scatter(eb_t)
     torch.cuda.synchronize()
     eb_t.zero_()
     rng_saved = rng_t.clone()
 
-    # ---- timed region: K launches (+ one NCCL all-reduce of the bins when N > 1) -----------------
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 2)]
-    barrier()
-    with ClockSampler(local_rank) as clocks:
+    # ---- timed region: K launches (+ ONE reduce-scatter of the bins when N > 1) -------------------
+    # CUDA events on the launch stream; the clock sampler runs on rank 0 only and starts BEFORE the barrier,
+    # so that its start-up (~0.1 s of nvidia-smi) cannot skew the ranks against each other -- in round 1 every
+    # rank started its own sampler between the barrier and its first launch, and the skew (6 ms at N = 2,
+    # 52 ms at N = 8) was charged to the collective that waits for the slowest rank.
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 3)]
+    part = None
+    with (ClockSampler(local_rank) if rank == 0 else contextlib.nullcontext()) as clocks:
+        barrier()
         ev[0].record(stream)
         for k in range(args.steps):
             launch(*dev_args)
             ev[k + 1].record(stream)
         if world > 1:
-            multi_gpu.reduce_bins(eb_t)     # one NCCL all-reduce, as uint8 when that is exact (multi_gpu.py)
+            part = reducer.reduce_scatter(eb_t)   # as uint8 when that is exact (multi_gpu.BinReducer); no host sync
         ev[args.steps + 1].record(stream)
         barrier()
     rng_final = rng_t.clone()
     total_ms = ev[0].elapsed_time(ev[args.steps + 1])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    collective_ms = ev[args.steps].elapsed_time(ev[args.steps + 1]) if world > 1 else 0.0
+    t = torch.tensor([total_ms, sum(step_ms), collective_ms], device="cuda", dtype=torch.float64)
+    per_rank = [torch.zeros_like(t) for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    deposits_total = float(eb_t.sum(dtype=torch.float64).item())
+        dist.all_gather(per_rank, t)
+    else:
+        per_rank = [t]
+    total_ms_max = max(float(x[0].item()) for x in per_rank)
+    narrow_exact = None
+    if world > 1:
+        narrow_exact = reducer.narrow_ok()
+        if not narrow_exact:                      # some count exceeded 255 // world: the float32 form (untimed here)
+            part = reducer.reduce_scatter(eb_t, wide=True)
+        dsum = part.sum(dtype=torch.float64).reshape(1)
+        dist.all_reduce(dsum)
+        deposits_total = float(dsum.item())
+    else:
+        deposits_total = float(eb_t.sum(dtype=torch.float64).item())
 
     # ---- exact event counts of the timed launches: replay them with device counters -------------
     rng_t.copy_(rng_saved)
@@ -437,15 +533,24 @@ def main():
         "config": {"workload": args.workload, "num_FOV_x": nx, "num_FOV_y": ny, "wavelengths": 3,
                    "rays_per_FoV": rpc, "rays_per_launch_per_gpu": N, "eyebox_bins": list(eb),
                    "l2_policy": "inputs (4.1 GB of ray state per launch) exceed the 126 MB L2; no flush needed",
-                   "partition": "replicated design, rank-specific RNG streams, one NCCL all-reduce of the bins (as uint8 when exact)"
-                   if world > 1 else "single GPU"},
+                   "partition": "replicated design, rank-specific RNG streams, one NCCL reduce-scatter of the bins (as uint8 "
+                                "when exact): every rank ends with 1/N of the summed tensor" if world > 1 else "single GPU"},
         "rays_per_s": rays_all / (total_ms_max * 1e-3),
         "full_colour_wall_ms": total_ms_max,
         "bounces_per_ray": bounces_all / max(rays_all, 1),
         "deposits": deposits_total,
         "step_ms_rank0": step_ms,
-        "gpu_launches": args.steps * 9,   # per launch: geometry hash, 6 region-index / atlas kernels (no-ops when unchanged), tile pick, walk
-        "clocks": clocks.summary(),
+        "per_rank_ms": {"walk_total": [float(x[1].item()) for x in per_rank],
+                        "collective": [float(x[2].item()) for x in per_rank],
+                        "timed_region": [float(x[0].item()) for x in per_rank]},
+        "collective_ms": max(float(x[2].item()) for x in per_rank),
+        "collective": None if world == 1 else
+        ("one NCCL reduce-scatter of the bins as uint8 (exact: every count <= 255 // N), 216 MB per rank in"
+         if narrow_exact else "narrow form not exact for these counts: float32 reduce-scatter needed (untimed re-run)"),
+        # per launch: geometry hash, 6 region-index / atlas kernels (no-ops when unchanged), tile pick, walk, near-tie redo
+        "gpu_launches": args.steps * 10 + (3 if world > 1 else 0),
+        "near_tie_rays": cnt["near_tie"],
+        "clocks": clocks.summary() if clocks is not None else None,
     }
 
     if rank == 0:
@@ -488,6 +593,8 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers -----------------------------------
     if not args.no_e2e and world > 1:
+        del dev_args, count_args
+        torch.cuda.empty_cache()
         line["e2e"] = e2e_multi_gpu(args, scene, rpc, N, world, rank, stream)
     if not args.no_e2e and world == 1:
         from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner
@@ -651,6 +758,14 @@ def main():
         line["e2e_dropin"]["deposits_match_device_run"] = bool(world > 1 or e2e_deposits == deposits_total)
         del prob, keep, e2e_args, pinned
 
+    # ---- BASELINE configs[2], partitioned over the ranks (strong scaling), as a sub-record ----------
+    if not args.no_partitioned:
+        wl = "c3_dense_fov_41x41x3x10000"
+        torch.cuda.empty_cache()
+        rec = partitioned_record(args, *WORKLOADS[wl], world, rank, local_rank, wl, sample_clocks=False)
+        if rank == 0:
+            line["partitioned_c3"] = rec
+
     # ---- CPU baseline (rank 0, N = 1 only) --------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
@@ -663,102 +778,77 @@ def main():
         line["cpu_baseline"] = {"value": c1["bounces"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": desc, "seconds": dt, "rays_per_s": c1["rays"] / dt}
 
+    if rank == 0 and world == 1:
+        line["reference_cudasim"] = reference_cudasim_record()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def reference_cudasim_record():
+    """BASELINE.json: "the reference's only CPU path (its Numba kernels under NUMBA_ENABLE_CUDASIM on the box's
+    host cores, core count stated)".  The reference is Python source and does not travel to the GPU box, so
+    this is the rate measured where it exists -- the build container, when oracle/make_golden.py ran the
+    unmodified reference kernel under the simulator to produce tests/golden/walk_c1.npz (BASELINE
+    configs[0]: 532 nm, 5 x 5 FoV cells, 64 rays per cell) -- stored in the fixture with its process count."""
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "walk_c1.npz"))
+        rays = int(g["rng_states"].shape[0]) * int(g["num_iter"])
+        secs, procs = float(g["sim_seconds"]), int(g["sim_procs"])
+        return {"rays_per_s": rays / secs, "seconds": secs, "rays": rays, "processes": procs,
+                "config": "BASELINE configs[0]: single wavelength 532 nm, 5x5 FoV grid, 64 rays per FoV, x2 launches",
+                "kind": "reference (GPU_ray_tracing_functions.py unmodified, NUMBA_ENABLE_CUDASIM=1, ray-chunked over "
+                        "processes); measured in the build container at fixture generation, not on this box"}
+    except (OSError, KeyError) as e:
+        return {"unavailable": str(e)}
+
+
 def e2e_multi_gpu(args, scene, rpc, N, world, rank, stream):
-    """End to end on N GPUs, the way a multi-GPU job runs (north_star: "one NCCL reduce of the bin tensors
-    over NVLink at the end").  Every step, from pinned host memory to pinned host memory:
-      1. the job's inputs enter the node ONCE: each rank uploads 1/N of every RCWA / geometry table over its
-         own PCIe link and an NCCL all-gather over NVLink completes the tables on every GPU (N ranks
-         uploading the same 360 MB through one host were measured host bound: 27.7 ms per step at N = 8);
-      2. each rank seeds its own RNG streams on the device (RUN:158 with a rank offset) and walks the full
-         C2 ray set through the reference-shaped kernel object (runner layout) into a device bin tensor;
-      3. ONE NCCL reduce-scatter sums the bins over the ranks and each rank downloads its 1/N slice of
-         the reduced tensor (N x 864 MB of bins through the host: 57 ms per step at N = 4)."""
+    """End to end on N GPUs, the way a replicated multi-GPU job runs (multi_gpu.ReplicatedJob; north_star:
+    "one NCCL reduce of the bin tensors over NVLink at the end").  Every step, from pinned host memory to
+    pinned host memory: each rank uploads 1/N of every table over its own PCIe link + NCCL all-gather;
+    device-side seeding of rank-specific streams; one launch of the full C2 ray set through the
+    reference-shaped kernel object (runner layout); ONE reduce-scatter of the bins; D2H of the rank's 1/N
+    slice of the sum.  (N ranks each pushing full tables and full bin tensors through one host were measured
+    host-bound in round 1: 57 ms per step at N = 4.)"""
     import torch
     import torch.distributed as dist
     from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
-    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, synthetic_inputs as si
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi, multi_gpu, synthetic_inputs as si
     pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 2024 + 1)
-    tables = dict(scene.geom); tables.update(scene.luts)
-    tables["px"] = pts[:, 0].astype(np.float32); tables["py"] = pts[:, 1].astype(np.float32)
-    host, dev, alias, sharded = {}, {}, {}, {}
-    h2d = 0
-    for k, a in tables.items():
-        tpin, _ = pinned_like(a)
-        host[k] = tpin.view(-1)
-        dev[k] = torch.empty_like(host[k], device="cuda")
-        alias[k] = GRTF._TorchAlias(dev[k], a.shape, a.dtype)
-        sharded[k] = host[k].numel() % world == 0 and a.nbytes >= (1 << 20)
-        h2d += a.nbytes // world if sharded[k] else a.nbytes
-    shape = scene.eb_shape
-    numel = int(np.prod(shape))
-    assert numel % world == 0
-    eb_dev = torch.zeros(numel, dtype=torch.float32, device="cuda")
-    eb_alias = GRTF._TorchAlias(eb_dev, shape, np.float32)
-    rng_dev = torch.empty(N, dtype=torch.int32, device="cuda")
-    rng_alias = GRTF._TorchAlias(rng_dev, (N,), np.uint32)
-    part_dev = torch.empty(numel // world, dtype=torch.float32, device="cuda")
-    part_host = torch.empty(numel // world, dtype=torch.float32).pin_memory()
-    golden = int(np.int64(0x9E3779B9) - (1 << 32))                      # the multiplier as a wrapping int32
-    kern = GRTF.process_rays_kernel_pro_fullColor.configured(ray_index_base=rank * N).runner_layout(rpc // 2, N)
-
-    def launch_args():
-        g = alias
-        return [g["px"], g["py"]] + [None] * 10 + [rng_alias, g["IC"], g["FC"], g["FC_offset"], g["OC"], g["OC_offset"],
-                scene.n_g, g["eff_reg1"], g["eff_reg2"], g["eff_reg_FOV"], g["eff_reg_FOV_range"], g["lut_ic1"], g["lut_ic2"],
-                g["lut_ic3"], g["lut_fc1"], g["lut_fc2"], g["lut_oc1"], g["lut_oc2"], g["lut_TIR"], g["lut_gap"], eb_alias]
-
-    def step():
-        for k in host:
-            if sharded[k]:
-                n = host[k].numel() // world
-                dev[k][rank * n:(rank + 1) * n].copy_(host[k][rank * n:(rank + 1) * n], non_blocking=True)
-                dist.all_gather_into_tensor(dev[k], dev[k][rank * n:(rank + 1) * n])
-            else:
-                dev[k].copy_(host[k], non_blocking=True)
-        torch.arange(rank * N + 1, rank * N + N + 1, dtype=torch.int32, device="cuda", out=rng_dev)
-        rng_dev.mul_(golden)                                             # RUN:158, wrapping 32-bit product
-        eb_dev.zero_()
-        kern[1, 256, stream](*launch_args())
-        dist.reduce_scatter_tensor(part_dev, eb_dev)
-        part_host.copy_(part_dev, non_blocking=True)
-        torch.cuda.synchronize()
-
+    job = multi_gpu.ReplicatedJob(pts, scene.geom, scene.n_g, scene.luts, rpc, eb=scene.eb_shape[3:])
     for _ in range(2):
-        step()
+        job.step(1)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        part, (lo, hi) = job.step(1)
     tw = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     wall = float(tw.item())
     # check: the same job walked from explicitly seeded host states, counters on, then summed over the ranks
     d_rng = torch.from_numpy(si.initial_rng_states(N, offset=rank * N).view(np.int32)).cuda()
-    seeds_ok = bool(torch.equal(torch.arange(rank * N + 1, rank * N + N + 1, dtype=torch.int32, device="cuda").mul_(golden), d_rng))
+    numel = int(np.prod(scene.eb_shape))
     chk = torch.zeros(numel, dtype=torch.float32, device="cuda")
-    a = launch_args()
-    a[12] = GRTF._TorchAlias(d_rng, (N,), np.uint32)
-    a[32] = GRTF._TorchAlias(chk, shape, np.float32)
     _capi.reset_counters()
-    kern.configured(counters=True)[1, 256, stream](*a)
+    kern = job.kernel.configured(counters=True)
+    kern[1, 256, stream](*job.launch_args(GRTF._TorchAlias(d_rng, (N,), np.uint32),
+                                          GRTF._TorchAlias(chk, scene.eb_shape, np.float32)))
     c1 = _capi.read_counters()
     dist.all_reduce(chk)
-    n = numel // world
-    same = seeds_ok and bool(torch.equal(chk[rank * n:(rank + 1) * n].cpu(), part_host))
+    same = bool(torch.equal(chk[lo:hi].cpu(), torch.from_numpy(part)))
     tv = torch.tensor([float(c1["bounces"]), 1.0 if same else 0.0], device="cuda", dtype=torch.float64)
     dist.all_reduce(tv)
-    return {"value": float(tv[0].item()) * args.steps / wall, "unit": UNIT, "ms_per_step": wall / max(args.steps, 1) * 1e3,
-            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(numel * 4),
-            "api": "per rank: H2D of 1/N of every table + NCCL all-gather, device-side seeding, "
-                   "GRTF.process_rays_kernel_pro_fullColor (runner layout) into device bins, one NCCL reduce-scatter, "
-                   "D2H of the rank's 1/N slice of the reduced bins",
-            "reduced_slices_bit_equal_to_device_run": bool(tv[1].item() == world)}
+    out = {"value": float(tv[0].item()) * args.steps / wall, "unit": UNIT, "ms_per_step": wall / max(args.steps, 1) * 1e3,
+           "h2d_bytes_per_step": int(job.h2d_bytes) * world, "d2h_bytes_per_step": int(numel * 4),
+           "api": "multi_gpu.ReplicatedJob.step: per rank H2D of 1/N of every table + NCCL all-gather, device-side seeding, "
+                  "GRTF.process_rays_kernel_pro_fullColor (runner layout) into device bins, one NCCL reduce-scatter "
+                  "(uint8 when exact), D2H of the rank's 1/N slice of the summed bins",
+           "reduced_slices_bit_equal_to_device_run": bool(tv[1].item() == world)}
+    del job, chk, d_rng
+    torch.cuda.empty_cache()
+    return out
 
 
 def reference_gpu_leg(args, dev_args, host_args, rng_saved, rng_final, eb_engine, N, stream, value, bounces_all):

@@ -19,6 +19,7 @@ WGRT_FLAG_STRICT = 0x1
 WGRT_FLAG_COUNTERS = 0x2
 WGRT_FLAG_BINS_ZERO = 0x4
 WGRT_FLAG_BINS_DEVICE = 0x8
+WGRT_FLAG_BINS_COLUMNS = 0x10
 WGRT_NUM_COUNTERS = 16
 COUNTER_NAMES = ("rays", "bounces", "draws", "draw2", "draw3", "efield", "iters", "deposits",
                  "poly_tests", "edge_visits", "straddle", "cross", "exact_fallback", "warp_steps", "warp_batches", "near_tie")
@@ -67,7 +68,7 @@ _lib: Optional[C.CDLL] = None
 EXPORTED_SYMBOLS = (
     "wgrt_version", "wgrt_problem_size", "wgrt_last_error", "wgrt_device_count", "wgrt_release",
     "wgrt_trace_fullcolor", "wgrt_trace_fullcolor_host", "wgrt_trace_evaluate_host",
-    "wgrt_counters_read", "wgrt_counters_reset",
+    "wgrt_seed_rng", "wgrt_counters_read", "wgrt_counters_reset",
     "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
     "wgrt_debug_deposit_inside", "wgrt_debug_set_tie_tolerance", "wgrt_debug_check_failures",
     "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host", "wgrt_bins_pack_u8", "wgrt_bins_unpack_u8",
@@ -104,6 +105,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_trace_evaluate_host.restype = C.c_int
     lib.wgrt_trace_evaluate_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wgrt_seed_rng.restype = C.c_int
+    lib.wgrt_seed_rng.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
     lib.wgrt_counters_read.restype = C.c_int
     lib.wgrt_counters_read.argtypes = [C.c_void_p, C.c_int]
     lib.wgrt_counters_reset.restype = C.c_int

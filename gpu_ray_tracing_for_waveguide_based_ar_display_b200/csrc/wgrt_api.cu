@@ -478,7 +478,9 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
   struct Item { const void* src; void** dst; size_t bytes; bool upfront; };
   wgrt_problem_t dp = *hp;
   dp.gap_x = dp.gap_y = dp.pol = dp.azi = nullptr;  // never read by the walk
-  dp.flags &= ~(WGRT_FLAG_BINS_ZERO | WGRT_FLAG_BINS_DEVICE);
+  dp.flags &= ~(WGRT_FLAG_BINS_ZERO | WGRT_FLAG_BINS_DEVICE | WGRT_FLAG_BINS_COLUMNS);
+  const bool columns_only = (hp->flags & WGRT_FLAG_BINS_COLUMNS) != 0;
+  if (columns_only && !runner) return fail(WGRT_ERR_INVALID, "WGRT_FLAG_BINS_COLUMNS needs the runner layout");
   const size_t ray_b = N * 4, pts_b = static_cast<size_t>(hp->runner_points) * 4;
   const size_t ic_b = fov * hp->C_ic * 16, fc_b = fov * hp->C_fc * 16, oc_b = fov * hp->C_oc * 16;  // per wavelength (and slice)
   if (runner) dp.m = dp.n = dp.lmd_num = dp.te = dp.tm = dp.delta_phase = nullptr;
@@ -548,8 +550,9 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
       c.rays = b > a ? (b - a) * rpc : 0;
       // matrix_EB columns outside the cell range travel with the first / last chunk: the whole
       // tensor is uploaded (unless declared zero) and downloaded, as by a single full copy
-      c.out_m0 = k == 0 ? 0 : c.in_m0;
-      c.out_m1 = k == K - 1 ? static_cast<int64_t>(X) : c.in_m1;
+      // (WGRT_FLAG_BINS_COLUMNS: only the columns the cell range touches move at all)
+      c.out_m0 = (k == 0 && !columns_only) ? 0 : c.in_m0;
+      c.out_m1 = (k == K - 1 && !columns_only) ? static_cast<int64_t>(X) : c.in_m1;
       chunks.push_back(c);
     }
   } else {
@@ -607,7 +610,13 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
   CUDA_TRY(cudaEventRecord(span[0], s_in));
   for (auto& it : items)
     if (it.upfront && it.bytes && it.src) CUDA_TRY(cudaMemcpyAsync(*it.dst, it.src, it.bytes, H2D, s_in));
-  if (zero_bins) CUDA_TRY(cudaMemsetAsync(dp.matrix_EB, 0, eb_b, s_in));
+  if (zero_bins && columns_only && !chunks.empty() && eb_b) {
+    const size_t m0 = static_cast<size_t>(chunks.front().out_m0), m1 = static_cast<size_t>(chunks.back().out_m1);
+    if (m1 > m0)
+      CUDA_TRY(cudaMemset2DAsync((char*)dp.matrix_EB + m0 * tile_b, X * tile_b, 0, (m1 - m0) * tile_b, L * Y, s_in));
+  } else if (zero_bins) {
+    CUDA_TRY(cudaMemsetAsync(dp.matrix_EB, 0, eb_b, s_in));
+  }
   // the region index is built once, on walk stream 0, as soon as the polygons are up
   CUDA_TRY(cudaEventRecord(span[6], s_in));
   CUDA_TRY(cudaStreamWaitEvent(s_run2[0], span[6], 0));
@@ -717,6 +726,13 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
 }  // namespace
 
 extern "C" {
+
+int wgrt_seed_rng(uint32_t* dev_states, int64_t n, int64_t first_index, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (n < 0 || (n > 0 && !dev_states)) return fail(WGRT_ERR_INVALID, "bad arguments");
+  CUDA_TRY(launch_seed_rng(dev_states, n, first_index, static_cast<cudaStream_t>(stream)));
+  return WGRT_OK;
+}
 
 int wgrt_counters_read(uint64_t* out, int n) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -39,6 +39,12 @@ extern "C" {
                                    * caller's device tensor and nothing is downloaded -- for callers
                                    * that reduce the bins over several GPUs before reading them */
 
+#define WGRT_FLAG_BINS_COLUMNS 0x10u /* host entry, runner layout only: move only the FoV-x columns of matrix_EB
+                                    * that the launch's cell range touches (instead of the whole tensor); the
+                                    * rest of the caller's host array is neither read nor written.  For
+                                    * multi-GPU jobs partitioned by cell range: every rank passes a full-shape
+                                    * host array and gets its own columns back (multi_gpu.trace_partitioned) */
+
 /* ---- event counters (uint64 each) ------------------------------------------------------ */
 enum {
   WGRT_CNT_RAYS = 0,     /* rays launched                                                   */
@@ -225,6 +231,12 @@ int wgrt_trace_fullcolor_host(const wgrt_problem_t* host_problem, int num_iter, 
  */
 int wgrt_trace_evaluate_host(const wgrt_problem_t* host_problem, int num_iter, int mask_size, int step_y,
                              int step_x, float* perceive, float* cell_sums, float* timings_ms);
+
+/*
+ * The runner's RNG seeding rule on the device (gpu_ray_tracing_pro_fullColor.py:158):
+ * dev_states[i] = 0x9E3779B9 * (first_index + i + 1) mod 2^32, i in [0, n).  Asynchronous on `stream`.
+ */
+int wgrt_seed_rng(uint32_t* dev_states, int64_t n, int64_t first_index, void* stream);
 
 /* Counters accumulated by launches that carried WGRT_FLAG_COUNTERS (device-wide, since reset). */
 int wgrt_counters_read(uint64_t* out, int n);

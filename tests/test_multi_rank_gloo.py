@@ -68,6 +68,23 @@ def _reduce_worker(rank, world, port, out_dir):
         got = a.copy(); multi_gpu.reduce_bins(got)
         plain = a.copy(); multi_gpu.reduce_bins(plain, narrow=False)
         out[k] = bool(np.array_equal(got, ref.numpy()) and np.array_equal(plain, ref.numpy()))
+    # BinReducer: persistent buffers, reduce-scatter form, flag reduced with the data (no host sync on the path)
+    for k, a in cases.items():
+        ref = torch.from_numpy(a.copy()); dist.all_reduce(ref)
+        red = multi_gpu.BinReducer(a.size, "cpu")
+        t = torch.from_numpy(a.copy())
+        keep = t.clone()
+        part = red.reduce_scatter(t)
+        narrow = red.narrow_ok()
+        lo, hi = red.slice_of()
+        ok = torch.equal(t, keep) and narrow == (k == "counts")          # the bins are never modified
+        if narrow:
+            ok = ok and torch.equal(part, ref.reshape(-1)[lo:hi])
+        part = red.reduce_scatter_checked(t).clone()
+        ok = ok and torch.equal(part, ref.reshape(-1)[lo:hi])
+        spans = [red.slice_of(r) for r in range(world)]
+        ok = ok and spans[0][0] == 0 and spans[-1][1] == a.size and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        out["reducer_" + k] = bool(ok)
     np.savez(os.path.join(out_dir, f"reduce{rank}.npz"), **out)
     dist.destroy_process_group()
 
@@ -78,7 +95,7 @@ def test_reduce_bins_narrow_path_is_exact(tmp_path):
     mp.spawn(_reduce_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         d = np.load(tmp_path / f"reduce{r}.npz")
-        assert all(bool(d[k]) for k in ("counts", "large", "fractional")), {k: bool(d[k]) for k in d.files}
+        assert all(bool(d[k]) for k in d.files) and len(d.files) == 6, {k: bool(d[k]) for k in d.files}
 
 
 def test_cell_range_partition():
@@ -104,3 +121,29 @@ def test_shard_rays_seeds_match_global_layout():
             for f in si.RAY_FIELDS:
                 assert np.array_equal(getattr(rays, f), getattr(full, f)[a:b]), f
             assert np.array_equal(rays.rng_states, full.rng_states[a:b])
+
+
+def test_column_ranges_and_merge():
+    """Partitioned jobs need no collective: every rank returns the FoV-x columns its cells touch; shared
+    boundary columns add up (disjoint cells)."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.multi_gpu import cell_range, column_range, merge_columns
+    L, X, Y = 3, 41, 41
+    n = L * X * Y
+    rs = np.random.default_rng(3)
+    # bins of the whole job: cell (m, n, l) owns tile [l, n, m]
+    full = rs.integers(0, 5, size=(L, Y, X, 2, 3)).astype(np.float32)
+    for world in (1, 2, 5, 8):
+        total = np.zeros_like(full)
+        covered = np.zeros(X, dtype=int)
+        for r in range(world):
+            c0, c1 = cell_range(n, world, r)
+            m0, m1 = column_range(c0, c1, Y, L)
+            assert 0 <= m0 < m1 <= X and m0 == c0 // (Y * L) and (m1 - 1) == (c1 - 1) // (Y * L)
+            covered[m0:m1] += 1
+            part = np.zeros_like(full)                       # what the rank's walk produces: its own cells only
+            cells = np.arange(c0, c1)
+            mm, nn, ll = cells // (Y * L), (cells // L) % Y, cells % L
+            part[ll, nn, mm] = full[ll, nn, mm]
+            merge_columns(total, part, (m0, m1))
+        assert np.array_equal(total, full) and covered.min() >= 1 and covered.max() <= 2
+    assert column_range(5, 5, Y, L) == (0, 0)
