@@ -689,34 +689,40 @@ def main():
             "d2h_bytes_per_call": int(d2h_r + seeds.nbytes),
             "stream_spans_ms_per_call_rank0": {"h2d": tms_j[0], "trace": tms_j[1], "d2h": tms_j[2]},
             "bins_and_rng_bit_equal_to_device_launches": samej}
-        # (2b) e2e_eval -- "full-colour eval wall time": the runner from its inputs to the evaluation's
-        # reductions (RUN:59-198 up to AR_system_evaluation_functions.py:109 and RUN:186) in one call, K
-        # launches, the bin tensor never leaving the device; then the reference's remaining host
-        # arithmetic (evaluation(), a few ms of NumPy on [3, 75, 100, 7, 8] arrays), timed separately
+        # (2b) e2e_eval -- "full-colour eval wall time": the runner from its inputs to its evaluation results
+        # (RUN:59-198) in one call: K launches, the pupil-mask sums and per-cell totals (EVAL:68-109, RUN:186) AND the
+        # rest of evaluation() (EVAL:110-160: display model, Lab / CIEDE2000, luminance statistics) on the device; the
+        # bin tensor never leaves it and 8 doubles per eye position + the per-cell totals come back.  The host only
+        # averages those over the 56 eye positions (`host_evaluation_ms`).  For comparison the same call with the
+        # round-1 host-finished evaluation (NumPy on the downloaded pupil sums) is timed too.
         from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import AR_system_evaluation_functions as EV
-        runner.trace_and_evaluate(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1, full_evaluation=False)
+        runner.trace_and_evaluate(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=1)
         tms_e = []
         barrier()
         t0 = time.perf_counter()
-        res = runner.trace_and_evaluate(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=args.steps, timings=tms_e,
-                                        full_evaluation=False)
+        res = runner.trace_and_evaluate(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=args.steps, timings=tms_e)
         wall_e = wall_max(time.perf_counter() - t0)
         t0 = time.perf_counter()
-        d_e, u_fov, u_eb, _img = EV.evaluation(np.broadcast_to(np.float32(0), eb_view.shape),
-                                               matrix_eye_perceive=res["matrix_eye_perceive"])
+        EV.finish_metrics(res["eval_metrics"], ny * nx, *(((eb[0] - 30) // 8 + 1), ((eb[1] - 30) // 12 + 1)))
         host_eval_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        res_h = runner.trace_and_evaluate(pts, geom_p, scene.n_g, luts_p, rpc, num_iter=args.steps, host_evaluation=True)
+        wall_h = time.perf_counter() - t0
         cells_ref = eb_view.reshape(eb_view.shape[0], eb_view.shape[1], eb_view.shape[2], -1).sum(axis=-1, dtype=np.float64)
+        rel = max(abs(res[k] - res_h[k]) / max(abs(res_h[k]), 1e-300) for k in ("delta_e", "U_fov", "U_EB"))
         line["e2e_eval"] = {
             "value": all_sum(cj["bounces"]) / wall_e, "unit": UNIT, "wall_ms_per_call": wall_e * 1e3,
             "launches_per_call": args.steps, "h2d_bytes_per_call": int(h2d_r),
-            "d2h_bytes_per_call": int(res["matrix_eye_perceive"].nbytes + res["cell_sums"].nbytes),
+            "d2h_bytes_per_call": int(res["eval_metrics"].nbytes + res["cell_sums"].nbytes),
             "stream_spans_ms_per_call_rank0": {"h2d": tms_e[0], "trace": tms_e[1], "d2h_and_reductions": tms_e[2]},
             "host_evaluation_ms": host_eval_s * 1e3,
-            "maps": {"efficiency_per_colour": [float(v) for v in res["efficiency"]], "U_fov": float(u_fov),
-                     "U_EB": float(u_eb), "delta_e_2000": float(d_e)},
+            "maps": {"efficiency_per_colour": [float(v) for v in res["efficiency"]], "U_fov": float(res["U_fov"]),
+                     "U_EB": float(res["U_EB"]), "delta_e_2000": float(res["delta_e"])},
+            "host_finished_variant": {"wall_ms_per_call": wall_h * 1e3, "max_rel_diff_of_maps": rel,
+                                      "note": "round-1 path: pupil sums downloaded, evaluation() finished in NumPy"},
             "cell_sums_equal_to_downloaded_bins": bool(np.array_equal(res["cell_sums"].astype(np.float64), cells_ref)),
-            "api": "runner.trace_and_evaluate -> wgrt_trace_evaluate_host: K launches + pupil-mask sums + per-cell "
-                   "totals on the device, bins never downloaded"}
+            "api": "runner.trace_and_evaluate -> wgrt_trace_evaluate_metrics_host: K launches + pupil-mask sums + per-cell "
+                   "totals + evaluation() lines 110-160 on the device, bins never downloaded"}
         del d_geom, d_luts, d_rng, d_eb, rargs, pin_keep, geom_p, luts_p, eb_view, seeds
         torch.cuda.empty_cache()
 

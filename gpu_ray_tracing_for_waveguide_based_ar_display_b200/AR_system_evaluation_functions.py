@@ -22,8 +22,8 @@ import numpy as np
 
 from . import _capi
 
-__all__ = ["evaluation", "pupil_sums", "efficiency_per_colour", "linearize_srgb", "apply_srgb_gamma",
-           "normalize_brightness_without_changing_color"]
+__all__ = ["evaluation", "evaluation_device", "eval_params", "finish_metrics", "pupil_sums", "efficiency_per_colour",
+           "linearize_srgb", "apply_srgb_gamma", "normalize_brightness_without_changing_color"]
 
 # reference lines 47-57
 M = np.array([[1.67430115, -0.76582385, -0.06172232],
@@ -124,6 +124,59 @@ def _delta_e_2000(lab1, lab2):
     Sc, Sh = 1 + 0.045 * Cpm, 1 + 0.015 * Cpm * T
     Rt = -np.sin(np.radians(2 * dth)) * Rc
     return np.sqrt((dLp / Sl) ** 2 + (dCp / Sc) ** 2 + (dHp / Sh) ** 2 + Rt * (dCp / Sc) * (dHp / Sh))
+
+
+def _lab_white():
+    x_w, y_w = _WHITE_XY
+    return np.array([x_w / y_w, 1.0, (1 - x_w - y_w) / y_w]) * 100.0
+
+
+def eval_params(scale: float) -> "_capi.WgrtEvalParams":
+    """The colour constants of ``evaluation()`` (reference lines 47-63, 112-116) as the device kernel takes
+    them (``wgrt_eval_params_t``); ``scale`` multiplies the raw pupil sums (1 / (num_rays_per_FoV * num_iter),
+    RUN:197)."""
+    prm = _capi.WgrtEvalParams()
+    prm.scale = float(scale)
+    white = _lab_white()
+    w_rgb = np.linalg.inv(M) @ linearize_srgb(np.ones(3))
+    lab_d65 = _xyz_to_lab(_XYZ_D65_SPD / _XYZ_D65_SPD[1] * 100.0, white)
+    for dst, src in ((prm.white_rgb, w_rgb), (prm.M, M.ravel()), (prm.M_xyz, M_XYZ.ravel()), (prm.white_xyz, white),
+                     (prm.lab_d65, lab_d65)):
+        for i, v in enumerate(src):
+            dst[i] = float(v)
+    return prm
+
+
+def finish_metrics(metrics: np.ndarray, n_pix: int, n_epy: int, n_epx: int):
+    """``(delta_e, U_fov, U_EB)`` from the per-eye-position reductions of ``wgrt_eval_metrics`` (reference
+    lines 148-160: the averages over eye positions)."""
+    m = np.asarray(metrics, dtype=np.float64).reshape(n_epy * n_epx, _capi.WGRT_EVAL_NUM)
+    n_ep = n_epy * n_epx
+    delta_e = float(np.sum(m[:, 0] / n_pix) / n_ep)
+    has_zero = m[:, 4] > 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(has_zero, 0.0, m[:, 1] / m[:, 2])
+    U_fov = float(np.sum(ratio) / n_ep)
+    u_eb = np.where(has_zero, 0.0, m[:, 3] / n_pix)
+    U_EB = 0 if np.max(u_eb) == 0 else float(np.min(u_eb) / np.max(u_eb))
+    return delta_e, U_fov, U_EB
+
+
+def evaluation_device(matrix_eye_perceive_raw: np.ndarray, scale: float, return_image: bool = True):
+    """``evaluation()`` lines 110-160 on the GPU (``wgrt_eval_metrics``) from RAW pupil sums
+    [3, Yf, Xf, n_epy, n_epx] and the normalisation ``scale``.  Returns ``delta_e, U_fov, U_EB, output_image``
+    (``output_image`` None unless requested)."""
+    lib = _capi.load_library()
+    p = np.ascontiguousarray(matrix_eye_perceive_raw, dtype=np.float32)
+    if p.ndim != 5 or p.shape[0] != 3:
+        raise ValueError("matrix_eye_perceive must be [3, FoV_y, FoV_x, n_epy, n_epx]")
+    _, Yf, Xf, n_epy, n_epx = p.shape
+    metrics = np.zeros((n_epy * n_epx, _capi.WGRT_EVAL_NUM), dtype=np.float64)
+    image = np.zeros((Yf, Xf, 3, n_epy, n_epx), dtype=np.float32) if return_image else None
+    prm = eval_params(scale)
+    _capi.check(lib.wgrt_eval_metrics_host(p.ctypes.data, Yf, Xf, n_epy, n_epx, C.byref(prm), metrics.ctypes.data,
+                                           image.ctypes.data if return_image else None), lib)
+    return (*finish_metrics(metrics, Yf * Xf, n_epy, n_epx), image)
 
 
 def evaluation(matrix_EB, matrix_eye_perceive: Optional[np.ndarray] = None):

@@ -11,7 +11,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwgrt.so")
+LIB_PATH = os.environ.get("WGRT_LIB") or os.path.join(_HERE, "libwgrt.so")   # WGRT_LIB: an experiment build
 CHECKED_LIB_PATH = os.path.join(_HERE, "libwgrt_checked.so")   # -DWGRT_CHECKED build: bounds assertions in the walk
 
 WGRT_OK = 0
@@ -53,6 +53,37 @@ class WgrtProblem(C.Structure):
     ]
 
 
+WGRT_EVAL_NUM = 8
+EVAL_FIELDS = ("sum_de", "y_min", "y_max", "y_sum", "y_zeros", "v_max")
+
+
+class WgrtEvalParams(C.Structure):
+    """Mirror of ``wgrt_eval_params_t`` (include/wgrt.h)."""
+    _fields_ = [("scale", C.c_double), ("white_rgb", C.c_double * 3), ("M", C.c_double * 9),
+                ("M_xyz", C.c_double * 9), ("white_xyz", C.c_double * 3), ("lab_d65", C.c_double * 3)]
+
+
+class WgrtLegacyProblem(C.Structure):
+    """Mirror of ``wgrt_legacy_problem_t`` (include/wgrt.h): the legacy energy-splitting tracer."""
+    _fields_ = [
+        ("vectors", C.c_void_p), ("capacity", C.c_int64), ("useful_count_in", C.c_int64),
+        ("total_ray_counter", C.c_void_p), ("max_steps", C.c_int64),
+        ("IC", C.c_void_p), ("IC_n", C.c_int64),
+        ("FC", C.c_void_p), ("FC_n", C.c_int64), ("FC_offset", C.c_void_p), ("n_FC", C.c_int64),
+        ("OC", C.c_void_p), ("OC_n", C.c_int64), ("OC_offset", C.c_void_p), ("n_OC", C.c_int64),
+        ("eff_reg1", C.c_void_p), ("eff_reg1_n", C.c_int64), ("eff_reg2", C.c_void_p), ("eff_reg2_n", C.c_int64),
+        ("eff_reg_FOV", C.c_void_p), ("eff_reg_FOV_range", C.c_void_p),
+        ("lut_ic1", C.c_void_p), ("lut_ic2", C.c_void_p), ("lut_fc1", C.c_void_p), ("lut_fc2", C.c_void_p),
+        ("lut_oc", C.c_void_p),
+        ("C_ic", C.c_int32), ("C_fc", C.c_int32), ("C_oc", C.c_int32), ("reserved0", C.c_int32),
+        ("lut_TIR", C.c_void_p), ("lut_gap", C.c_void_p), ("X", C.c_int64), ("Y", C.c_int64),
+        ("matrix_EB", C.c_void_p), ("EBy", C.c_int64), ("EBx", C.c_int64),
+    ]
+
+
+LEGACY_COLS = 13
+
+
 class WgrtError(RuntimeError):
     pass
 
@@ -71,7 +102,9 @@ EXPORTED_SYMBOLS = (
     "wgrt_seed_rng", "wgrt_counters_read", "wgrt_counters_reset",
     "wgrt_debug_locate", "wgrt_debug_efield", "wgrt_debug_xorshift", "wgrt_debug_fma_peak",
     "wgrt_debug_deposit_inside", "wgrt_debug_set_tie_tolerance", "wgrt_debug_check_failures",
-    "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host", "wgrt_bins_pack_u8", "wgrt_bins_unpack_u8",
+    "wgrt_eval_pupil_sums", "wgrt_eval_pupil_sums_host", "wgrt_eval_metrics", "wgrt_eval_metrics_host",
+    "wgrt_trace_evaluate_metrics_host",
+    "wgrt_legacy_problem_size", "wgrt_legacy_step", "wgrt_legacy_pack_active", "wgrt_legacy_trace_host", "wgrt_bins_pack_u8", "wgrt_bins_unpack_u8",
 )
 
 
@@ -131,6 +164,25 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.wgrt_eval_pupil_sums_host.restype = C.c_int
     lib.wgrt_eval_pupil_sums_host.argtypes = [C.c_void_p] + [C.c_int64] * 5 + [C.c_int] * 3 + \
         [C.c_void_p, C.c_void_p]
+    lib.wgrt_eval_metrics.restype = C.c_int
+    lib.wgrt_eval_metrics.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(WgrtEvalParams),
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.wgrt_eval_metrics_host.restype = C.c_int
+    lib.wgrt_eval_metrics_host.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(WgrtEvalParams),
+                                           C.c_void_p, C.c_void_p]
+    lib.wgrt_trace_evaluate_metrics_host.restype = C.c_int
+    lib.wgrt_trace_evaluate_metrics_host.argtypes = [C.POINTER(WgrtProblem), C.c_int, C.c_int, C.c_int, C.c_int,
+                                                     C.POINTER(WgrtEvalParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p]
+    lib.wgrt_legacy_problem_size.restype = C.c_int
+    if lib.wgrt_legacy_problem_size() != C.sizeof(WgrtLegacyProblem):
+        raise WgrtError("wgrt_legacy_problem_t layout mismatch between _capi.py and libwgrt.so")
+    lib.wgrt_legacy_step.restype = C.c_int
+    lib.wgrt_legacy_step.argtypes = [C.POINTER(WgrtLegacyProblem), C.c_void_p]
+    lib.wgrt_legacy_pack_active.restype = C.c_int
+    lib.wgrt_legacy_pack_active.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.wgrt_legacy_trace_host.restype = C.c_int
+    lib.wgrt_legacy_trace_host.argtypes = [C.POINTER(WgrtLegacyProblem), C.c_int, C.c_void_p]
     if path is None:
         _lib = lib
     return lib

@@ -20,9 +20,11 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 # literal restatement that is compared with the CPU oracle.
 UNITS = {
     "wgrt_strict.cu": ["-fmad=false"],
+    "wgrt_legacy.cu": ["-fmad=false"],
     "wgrt_index.cu": [],
     "wgrt_eval.cu": [],
-    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WARP_CTAS_PER_SM",) if k in os.environ],
+    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WARP_CTAS_PER_SM", "WGRT_STREAM_CTAS_PER_SM", "WGRT_STAGE_BLOCK",
+                                                        "WGRT_STAGE_BLOCKS", "WGRT_VARIANT") if k in os.environ],
     "wgrt_api.cu": [],
 }
 HEADERS = ["wgrt_device.cuh", "wgrt_region.cuh", os.path.join("..", "..", "include", "wgrt.h")]
@@ -55,6 +57,10 @@ def build(force: bool = False, verbose: bool = False, checked: bool = False) -> 
     in the production walk, see wgrt_device.cuh), used by tests/test_gpu_checked_build.py."""
     obj_dir = os.path.join(OBJ_DIR, "checked") if checked else OBJ_DIR
     out = OUT_CHECKED if checked else OUT
+    if os.environ.get("WGRT_BUILD_TAG"):     # experiment builds: libwgrt_<tag>.so next to the product library
+        tag = os.environ["WGRT_BUILD_TAG"]
+        obj_dir = os.path.join(OBJ_DIR, "exp_" + tag)
+        out = os.path.join(PKG, f"libwgrt_{tag}.so")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     hdrs = [os.path.join(HERE, h) for h in HEADERS] + [os.path.abspath(__file__)]

@@ -419,6 +419,9 @@ struct EvalSpec {
   int mask_size, step_y, step_x;
   float* perceive;    // host [L, Y, X, n_epy, n_epx] or NULL
   float* cell_sums;   // host [L, Y, X] or NULL
+  const wgrt_eval_params_t* params = nullptr;   // not NULL: finish evaluation() on the device (wgrt_eval_metrics)
+  double* metrics = nullptr;                    // host [n_ep, WGRT_EVAL_NUM]
+  float* image = nullptr;                       // host [Y, X, 3, n_epy, n_epx] or NULL
 };
 
 struct HostChunk {
@@ -443,6 +446,18 @@ extern "C" int wgrt_trace_evaluate_host(const wgrt_problem_t* hp, int num_iter, 
   if (mask_size <= 0 || step_y <= 0 || step_x <= 0) return fail(WGRT_ERR_INVALID, "bad pupil mask / steps");
   if (mask_size > 220) return fail(WGRT_ERR_UNSUPPORTED, "pupil mask wider than 220 bins");
   const EvalSpec ev{mask_size, step_y, step_x, perceive, cell_sums};
+  return trace_host_impl(hp, num_iter, timings_ms, &ev);
+}
+
+extern "C" int wgrt_trace_evaluate_metrics_host(const wgrt_problem_t* hp, int num_iter, int mask_size, int step_y,
+                                                int step_x, const wgrt_eval_params_t* params, double* metrics,
+                                                float* cell_sums, float* perceive, float* image, float* timings_ms) {
+  if (mask_size <= 0 || step_y <= 0 || step_x <= 0) return fail(WGRT_ERR_INVALID, "bad pupil mask / steps");
+  if (mask_size > 220) return fail(WGRT_ERR_UNSUPPORTED, "pupil mask wider than 220 bins");
+  if (!params || !metrics) return fail(WGRT_ERR_INVALID, "null pointer: params / metrics");
+  if (hp && hp->L != 3) return fail(WGRT_ERR_UNSUPPORTED, "the colour evaluation needs exactly 3 wavelengths");
+  EvalSpec ev{mask_size, step_y, step_x, perceive, cell_sums};
+  ev.params = params; ev.metrics = metrics; ev.image = image;
   return trace_host_impl(hp, num_iter, timings_ms, &ev);
 }
 
@@ -513,14 +528,21 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
       {bins_on_device ? nullptr : hp->matrix_EB, (void**)&dp.matrix_EB, bins_on_device ? 0 : eb_b, !zero_bins && !runner},
   };
   items.insert(items.end(), shared_items.begin(), shared_items.end());
-  float *d_perceive = nullptr, *d_cells = nullptr;
-  size_t perceive_b = 0;
+  float *d_perceive = nullptr, *d_cells = nullptr, *d_image = nullptr;
+  double* d_metrics = nullptr;
+  size_t perceive_b = 0, metrics_b = 0, image_b = 0, n_epy = 0, n_epx = 0;
   if (ev) {
-    const size_t n_epy = hp->EBy >= ev->mask_size ? static_cast<size_t>((hp->EBy - ev->mask_size) / ev->step_y + 1) : 0;
-    const size_t n_epx = hp->EBx >= ev->mask_size ? static_cast<size_t>((hp->EBx - ev->mask_size) / ev->step_x + 1) : 0;
+    n_epy = hp->EBy >= ev->mask_size ? static_cast<size_t>((hp->EBy - ev->mask_size) / ev->step_y + 1) : 0;
+    n_epx = hp->EBx >= ev->mask_size ? static_cast<size_t>((hp->EBx - ev->mask_size) / ev->step_x + 1) : 0;
     perceive_b = cells * n_epy * n_epx * 4;
     items.push_back({nullptr, (void**)&d_perceive, perceive_b, false});
     items.push_back({nullptr, (void**)&d_cells, cells * 4, false});
+    if (ev->params) {
+      metrics_b = n_epy * n_epx * WGRT_EVAL_NUM * sizeof(double);
+      image_b = ev->image ? fov * 3 * n_epy * n_epx * 4 : 0;
+      items.push_back({nullptr, (void**)&d_metrics, metrics_b, false});
+      items.push_back({nullptr, (void**)&d_image, image_b, false});
+    }
   }
   size_t total = 0;
   for (auto& it : items) total += padded(it.bytes);
@@ -707,6 +729,12 @@ int trace_host_impl(const wgrt_problem_t* hp, int num_iter, float* timings_ms, c
     // the D2H stream has waited for every chunk's walk: reduce the finished bins where they are
     CUDA_TRY(launch_pupil_sums(dp.matrix_EB, hp->L, hp->Y, hp->X, hp->EBy, hp->EBx, ev->mask_size, ev->step_y, ev->step_x,
                                d_perceive, d_cells, s_out));
+    if (ev->params && metrics_b) {
+      CUDA_TRY(launch_eval_metrics(d_perceive, hp->Y, hp->X, static_cast<int>(n_epy), static_cast<int>(n_epx), *ev->params,
+                                   d_metrics, image_b ? d_image : nullptr, s_out));
+      CUDA_TRY(cudaMemcpyAsync(ev->metrics, d_metrics, metrics_b, D2H, s_out));
+      if (image_b) CUDA_TRY(cudaMemcpyAsync(ev->image, d_image, image_b, D2H, s_out));
+    }
     if (ev->perceive && perceive_b) CUDA_TRY(cudaMemcpyAsync(ev->perceive, d_perceive, perceive_b, D2H, s_out));
     if (ev->cell_sums) CUDA_TRY(cudaMemcpyAsync(ev->cell_sums, d_cells, cells * 4, D2H, s_out));
   }
@@ -911,6 +939,44 @@ int wgrt_eval_pupil_sums(const float* dev_EB, int64_t L, int64_t Yf, int64_t Xf,
   return WGRT_OK;
 }
 
+int wgrt_eval_metrics(const float* dev_perceive, int64_t Yf, int64_t Xf, int n_epy, int n_epx,
+                      const wgrt_eval_params_t* params, double* dev_metrics, float* dev_image, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!dev_perceive || !params || !dev_metrics || Yf < 0 || Xf < 0 || n_epy < 0 || n_epx < 0)
+    return fail(WGRT_ERR_INVALID, "bad arguments");
+  CUDA_TRY(launch_eval_metrics(dev_perceive, Yf, Xf, n_epy, n_epx, *params, dev_metrics, dev_image,
+                               static_cast<cudaStream_t>(stream)));
+  return WGRT_OK;
+}
+
+int wgrt_eval_metrics_host(const float* perceive, int64_t Yf, int64_t Xf, int n_epy, int n_epx,
+                           const wgrt_eval_params_t* params, double* metrics, float* image) {
+  if (!perceive || !params || !metrics || Yf < 0 || Xf < 0 || n_epy < 0 || n_epx < 0) return fail(WGRT_ERR_INVALID, "bad arguments");
+  const size_t n_ep = static_cast<size_t>(n_epy) * n_epx, pix = static_cast<size_t>(Yf * Xf);
+  const size_t pb = 3 * pix * n_ep * 4, mb = n_ep * WGRT_EVAL_NUM * sizeof(double), ib = image ? pix * 3 * n_ep * 4 : 0;
+  float *d_p, *d_i;
+  double* d_m;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    Workspace* w = nullptr;
+    int rc = get_workspace(&w);
+    if (rc != WGRT_OK) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(w->arena.reserve(padded(pb) + padded(mb) + padded(ib)));
+    Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+    d_p = static_cast<float*>(ar.take(pb));
+    d_m = static_cast<double*>(ar.take(mb));
+    d_i = ib ? static_cast<float*>(ar.take(ib)) : nullptr;
+    if (pb) CUDA_TRY(cudaMemcpy(d_p, perceive, pb, cudaMemcpyHostToDevice));
+  }
+  int rc = wgrt_eval_metrics(d_p, Yf, Xf, n_epy, n_epx, params, d_m, d_i, nullptr);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (mb) CUDA_TRY(cudaMemcpy(metrics, d_m, mb, cudaMemcpyDeviceToHost));
+  if (ib) CUDA_TRY(cudaMemcpy(image, d_i, ib, cudaMemcpyDeviceToHost));
+  return WGRT_OK;
+}
+
 int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, float limit, void* stream) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (!dev_bins || !dev_out || !dev_stats || n < 0 || (n & 3) || (reinterpret_cast<uintptr_t>(dev_bins) & 15) ||
@@ -968,3 +1034,174 @@ int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf
 }
 
 }  // extern "C"
+
+// ---- legacy deterministic energy-splitting tracer (row f4) ---------------------------------------------
+namespace {
+
+int validate_legacy(const wgrt_legacy_problem_t* p) {
+  if (!p) return fail(WGRT_ERR_INVALID, "null problem");
+  if (p->capacity < 0 || p->useful_count_in < 0 || p->useful_count_in > p->capacity)
+    return fail(WGRT_ERR_INVALID, "useful_count_in must be within [0, capacity]");
+  if (p->max_steps < 0) return fail(WGRT_ERR_INVALID, "max_steps < 0");
+  if (p->X <= 0 || p->Y <= 0 || p->EBx <= 0 || p->EBy <= 0) return fail(WGRT_ERR_INVALID, "X, Y, EBy, EBx must be positive");
+  if (p->n_FC < 0 || p->n_OC < 0 || p->n_FC > 250 || p->n_OC > 250) return fail(WGRT_ERR_INVALID, "n_FC / n_OC must be within [0, 250]");
+  if (p->C_ic < 24 || p->C_fc < 20 || p->C_oc < 26)
+    return fail(WGRT_ERR_INVALID, "LUT channel counts too small (need C_ic>=24, C_fc>=20, C_oc>=26)");
+  if (p->IC_n < 0 || p->FC_n < 0 || p->OC_n < 0 || p->eff_reg1_n < 0 || p->eff_reg2_n < 0) return fail(WGRT_ERR_INVALID, "negative vertex count");
+#define NEED(f) \
+  if (!p->f) return fail(WGRT_ERR_INVALID, "null pointer: " #f)
+  NEED(total_ray_counter); NEED(IC); NEED(FC); NEED(FC_offset); NEED(OC); NEED(OC_offset); NEED(eff_reg1); NEED(eff_reg2);
+  NEED(eff_reg_FOV); NEED(eff_reg_FOV_range); NEED(lut_ic1); NEED(lut_ic2); NEED(lut_fc1); NEED(lut_fc2); NEED(lut_oc);
+  NEED(lut_TIR); NEED(lut_gap); NEED(matrix_EB);
+  if (p->capacity > 0) NEED(vectors);
+#undef NEED
+  return WGRT_OK;
+}
+
+// the region index works on the polygons alone: present them as a (ray-less) full-colour problem
+wgrt_problem_t polygons_of(const wgrt_legacy_problem_t& lp) {
+  wgrt_problem_t p{};
+  p.IC = lp.IC; p.IC_n = lp.IC_n;
+  p.FC = lp.FC; p.FC_n = lp.FC_n; p.FC_offset = lp.FC_offset; p.n_FC = lp.n_FC;
+  p.OC = lp.OC; p.OC_n = lp.OC_n; p.OC_offset = lp.OC_offset; p.n_OC = lp.n_OC;
+  p.eff_reg1 = lp.eff_reg1; p.eff_reg1_n = lp.eff_reg1_n;
+  p.eff_reg2 = lp.eff_reg2; p.eff_reg2_n = lp.eff_reg2_n;
+  return p;
+}
+
+int legacy_step_device(Workspace& w, const wgrt_legacy_problem_t& lp, bool soa, cudaStream_t stream, bool build_index) {
+  const wgrt_problem_t poly = polygons_of(lp);
+  RegionSet rs;
+  int rc = region_set_of(w, poly, rs);
+  if (rc != WGRT_OK) return rc;
+  if (build_index) {
+    CUDA_TRY(launch_region_build(rs, w.index_stale, stream));
+    w.index_stale = false;
+  }
+  // dropped-children counter: the spare counter slot behind the event counters
+  CUDA_TRY(launch_legacy_step(lp, rs, soa, w.counters() + WGRT_NUM_COUNTERS, stream));
+  return WGRT_OK;
+}
+
+}  // namespace
+
+extern "C" int wgrt_legacy_problem_size(void) { return static_cast<int>(sizeof(wgrt_legacy_problem_t)); }
+
+extern "C" int wgrt_legacy_step(const wgrt_legacy_problem_t* p, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = validate_legacy(p);
+  if (rc != WGRT_OK) return rc;
+  Workspace* w = nullptr;
+  rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  if (p->useful_count_in == 0) return WGRT_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const wgrt_problem_t poly = polygons_of(*p);
+  rc = validate_device_offsets(*w, poly, st);
+  if (rc != WGRT_OK) return rc;
+  rc = order_after_last_use(*w, st);
+  if (rc != WGRT_OK) return rc;
+  rc = legacy_step_device(*w, *p, false, st, true);
+  if (rc != WGRT_OK) return rc;
+  return record_last_use(*w, st);
+}
+
+extern "C" int wgrt_legacy_pack_active(const double* dev_src, double* dev_dst, int64_t src_len, int32_t* dev_out_count,
+                                       void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (src_len < 0 || !dev_out_count || (src_len > 0 && (!dev_src || !dev_dst))) return fail(WGRT_ERR_INVALID, "bad arguments");
+  CUDA_TRY(launch_legacy_pack(dev_src, dev_dst, src_len, 0, 0, false, dev_out_count, static_cast<cudaStream_t>(stream)));
+  return WGRT_OK;
+}
+
+extern "C" int wgrt_legacy_trace_host(const wgrt_legacy_problem_t* hp, int max_generations, uint64_t* stats) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = validate_legacy(hp);
+  if (rc != WGRT_OK) return rc;
+  if (max_generations < 0) return fail(WGRT_ERR_INVALID, "max_generations < 0");
+  rc = check_offsets(hp->FC_offset, hp->n_FC, hp->FC_n, "FC_offset");
+  if (rc != WGRT_OK) return rc;
+  rc = check_offsets(hp->OC_offset, hp->n_OC, hp->OC_n, "OC_offset");
+  if (rc != WGRT_OK) return rc;
+  if (hp->capacity >= (int64_t(1) << 31)) return fail(WGRT_ERR_UNSUPPORTED, "capacity must be below 2^31 rows");
+  Workspace* w = nullptr;
+  rc = get_workspace(&w);
+  if (rc != WGRT_OK) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());   // the arena may be in use by an asynchronous launch
+  const size_t cap = static_cast<size_t>(hp->capacity), fov = static_cast<size_t>(hp->X * hp->Y);
+  const size_t rows_b = cap * WGRT_LEGACY_COLS * sizeof(double);
+  const size_t eb_b = fov * static_cast<size_t>(hp->EBy * hp->EBx) * 4;
+  wgrt_legacy_problem_t dp = *hp;
+  double *qa = nullptr, *qb = nullptr, *aos = nullptr;
+  int32_t* d_cnt = nullptr;   // [0] child counter, [1] packed count
+  struct Item { const void* src; void** dst; size_t bytes; };
+  std::vector<Item> items = {
+      {nullptr, (void**)&qa, rows_b}, {nullptr, (void**)&qb, rows_b}, {hp->vectors, (void**)&aos, rows_b},
+      {nullptr, (void**)&d_cnt, 16},
+      {hp->IC, (void**)&dp.IC, (size_t)hp->IC_n * 16}, {hp->FC, (void**)&dp.FC, (size_t)hp->FC_n * 16},
+      {hp->FC_offset, (void**)&dp.FC_offset, (size_t)(hp->n_FC + 1) * 8}, {hp->OC, (void**)&dp.OC, (size_t)hp->OC_n * 16},
+      {hp->OC_offset, (void**)&dp.OC_offset, (size_t)(hp->n_OC + 1) * 8},
+      {hp->eff_reg1, (void**)&dp.eff_reg1, (size_t)hp->eff_reg1_n * 16}, {hp->eff_reg2, (void**)&dp.eff_reg2, (size_t)hp->eff_reg2_n * 16},
+      {hp->eff_reg_FOV, (void**)&dp.eff_reg_FOV, fov * 64}, {hp->eff_reg_FOV_range, (void**)&dp.eff_reg_FOV_range, fov * 32},
+      {hp->lut_ic1, (void**)&dp.lut_ic1, fov * hp->C_ic * 16}, {hp->lut_ic2, (void**)&dp.lut_ic2, fov * hp->C_ic * 16},
+      {hp->lut_fc1, (void**)&dp.lut_fc1, fov * hp->n_FC * hp->C_fc * 16}, {hp->lut_fc2, (void**)&dp.lut_fc2, fov * hp->n_FC * hp->C_fc * 16},
+      {hp->lut_oc, (void**)&dp.lut_oc, fov * hp->n_OC * hp->C_oc * 16},
+      {hp->lut_TIR, (void**)&dp.lut_TIR, fov * 32}, {hp->lut_gap, (void**)&dp.lut_gap, fov * 64},
+      {hp->matrix_EB, (void**)&dp.matrix_EB, eb_b},
+  };
+  size_t total = 0;
+  for (auto& it : items) total += padded(it.bytes);
+  CUDA_TRY(w->arena.reserve(total));
+  Arena ar{static_cast<char*>(w->arena.ptr), w->arena.bytes};
+  for (auto& it : items) {
+    *it.dst = ar.take(it.bytes);
+    if (!*it.dst) return fail(WGRT_ERR_CUDA, "arena overflow");
+  }
+  const size_t n0 = static_cast<size_t>(hp->useful_count_in);
+  for (auto& it : items) {
+    size_t b = it.bytes;
+    if (it.src == hp->vectors) b = n0 * WGRT_LEGACY_COLS * sizeof(double);   // only the initial rows carry data
+    if (it.src && b) CUDA_TRY(cudaMemcpy(*it.dst, it.src, b, cudaMemcpyHostToDevice));
+  }
+  unsigned long long* d_dropped = w->counters() + WGRT_NUM_COUNTERS;
+  CUDA_TRY(cudaMemset(d_dropped, 0, sizeof(unsigned long long)));
+  CUDA_TRY(launch_legacy_transpose(aos, qa, hp->useful_count_in, hp->capacity, true, nullptr));
+
+  uint64_t st[8] = {0, 0, 0, 0, 0, static_cast<uint64_t>(hp->useful_count_in), 0, 0};
+  int64_t count = hp->useful_count_in;
+  bool first = true;
+  while (count > 0 && st[0] < static_cast<uint64_t>(max_generations)) {
+    const int32_t start[2] = {static_cast<int32_t>(count), 0};
+    CUDA_TRY(cudaMemcpy(d_cnt, start, 8, cudaMemcpyHostToDevice));
+    wgrt_legacy_problem_t gp = dp;
+    gp.vectors = qa;
+    gp.useful_count_in = count;
+    gp.total_ray_counter = d_cnt;
+    rc = legacy_step_device(*w, gp, true, nullptr, first);
+    if (rc != WGRT_OK) return rc;
+    first = false;
+    int32_t after = 0;
+    CUDA_TRY(cudaMemcpy(&after, d_cnt, 4, cudaMemcpyDeviceToHost));
+    const int64_t live_end = std::min<int64_t>(after, hp->capacity);
+    st[2] += static_cast<uint64_t>(count);
+    st[3] += static_cast<uint64_t>(after - count);
+    CUDA_TRY(launch_legacy_pack(qa, qb, live_end, hp->capacity, hp->capacity, true, d_cnt + 1, nullptr));
+    int32_t packed = 0;
+    CUDA_TRY(cudaMemcpy(&packed, d_cnt + 1, 4, cudaMemcpyDeviceToHost));
+    std::swap(qa, qb);
+    count = packed;
+    st[0] += 1;
+    st[5] = std::max<uint64_t>(st[5], static_cast<uint64_t>(count));
+  }
+  st[1] = static_cast<uint64_t>(count);
+  unsigned long long dropped = 0;
+  CUDA_TRY(cudaMemcpy(&dropped, d_dropped, sizeof dropped, cudaMemcpyDeviceToHost));
+  st[4] = dropped;
+  if (count > 0) {
+    CUDA_TRY(launch_legacy_transpose(qa, aos, count, hp->capacity, false, nullptr));
+    CUDA_TRY(cudaMemcpy(hp->vectors, aos, static_cast<size_t>(count) * WGRT_LEGACY_COLS * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  CUDA_TRY(cudaMemcpy(hp->matrix_EB, dp.matrix_EB, eb_b, cudaMemcpyDeviceToHost));
+  if (stats) memcpy(stats, st, sizeof st);
+  return WGRT_OK;
+}

@@ -234,6 +234,13 @@ cudaError_t launch_fma_peak(int num_sms, double* fp64_tflops, double* fp32_tflop
 cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, float limit, int num_sms,
                                 cudaStream_t s);
 cudaError_t launch_bins_unpack_u8(const uint8_t* in, int64_t n, float* bins, int num_sms, cudaStream_t s);
+cudaError_t launch_eval_metrics(const float* perceive, int64_t Yf, int64_t Xf, int n_epy, int n_epx,
+                                const wgrt_eval_params_t& prm, double* metrics, float* image, cudaStream_t s);
+cudaError_t launch_legacy_step(const wgrt_legacy_problem_t& p, const RegionSet& rs, bool soa, unsigned long long* dropped,
+                               cudaStream_t s);
+cudaError_t launch_legacy_pack(const double* src, double* dst, int64_t src_len, int64_t src_cap, int64_t dst_cap, bool soa,
+                               int32_t* out_count, cudaStream_t s);
+cudaError_t launch_legacy_transpose(const double* src, double* dst, int64_t n, int64_t cap, bool to_soa, cudaStream_t s);
 cudaError_t launch_pupil_sums(const float* EB, int64_t L, int64_t Yf, int64_t Xf, int64_t EBy, int64_t EBx,
                               int mask, int step_y, int step_x, float* out, float* cell_sums, cudaStream_t s);
 

@@ -167,7 +167,146 @@ __global__ void __launch_bounds__(256) cell_sums_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The rest of evaluation() on the device (AR_system_evaluation_functions.py:110-160): per sampled eye
+// position, the white image through the display model -- sRGB image (clip, gamma, brightness stretch),
+// CIE XYZ / Lab, CIEDE2000 against D65, luminance min / max / mean over the FoV -- reduced to a handful of
+// numbers per eye position.  One CTA per eye position; all arithmetic in double like the reference's NumPy.
+// The colour constants arrive in wgrt_eval_params_t from the Python mirror (the reference's own matrices).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double srgb_gamma(double v) {   // EVAL:14-16
+  return v <= 0.0031308 ? v * 12.92 : 1.055 * pow(v, 1.0 / 2.4) - 0.055;
+}
+__device__ __forceinline__ double lab_f(double t) {
+  const double d = 6.0 / 29.0;
+  return t > d * d * d ? cbrt(t) : t / (3.0 * d * d) + 4.0 / 29.0;
+}
+__device__ __forceinline__ double deg_atan2_360(double y, double x) {
+  double h = atan2(y, x) * (180.0 / 3.14159265358979323846);
+  h = fmod(h, 360.0);
+  if (h < 0.0) h += 360.0;
+  return h;
+}
+__device__ __forceinline__ double rad(double deg) { return deg * (3.14159265358979323846 / 180.0); }
+__device__ __forceinline__ double pow7(double x) { const double x2 = x * x, x4 = x2 * x2; return x4 * x2 * x; }
+// CIEDE2000 (Sharma, Wu, Dalal 2005), kL = kC = kH = 1 -- the formula colour.delta_E(..., 'CIE 2000') evaluates
+__device__ double delta_e_2000(double L1, double a1, double b1, double L2, double a2, double b2) {
+  const double C1 = hypot(a1, b1), C2 = hypot(a2, b2);
+  const double Cm = 0.5 * (C1 + C2);
+  const double c7 = pow7(Cm);
+  const double G = 0.5 * (1.0 - sqrt(c7 / (c7 + 6103515625.0)));   // 25^7
+  const double a1p = (1.0 + G) * a1, a2p = (1.0 + G) * a2;
+  const double C1p = hypot(a1p, b1), C2p = hypot(a2p, b2);
+  const double h1p = deg_atan2_360(b1, a1p), h2p = deg_atan2_360(b2, a2p);
+  const double dLp = L2 - L1, dCp = C2p - C1p;
+  double dh = h2p - h1p;
+  const bool grey = C1p * C2p == 0.0;
+  dh = grey ? 0.0 : (dh > 180.0 ? dh - 360.0 : (dh < -180.0 ? dh + 360.0 : dh));
+  const double dHp = 2.0 * sqrt(C1p * C2p) * sin(rad(dh) * 0.5);
+  const double Lm = 0.5 * (L1 + L2), Cpm = 0.5 * (C1p + C2p);
+  const double hsum = h1p + h2p;
+  const double hm = grey ? hsum : (fabs(h1p - h2p) <= 180.0 ? hsum * 0.5 : (hsum < 360.0 ? (hsum + 360.0) * 0.5 : (hsum - 360.0) * 0.5));
+  const double T = 1.0 - 0.17 * cos(rad(hm - 30.0)) + 0.24 * cos(rad(2.0 * hm)) + 0.32 * cos(rad(3.0 * hm + 6.0)) -
+                   0.20 * cos(rad(4.0 * hm - 63.0));
+  const double q = (hm - 275.0) / 25.0;
+  const double dth = 30.0 * exp(-q * q);
+  const double p7 = pow7(Cpm);
+  const double Rc = 2.0 * sqrt(p7 / (p7 + 6103515625.0));
+  const double l50 = (Lm - 50.0) * (Lm - 50.0);
+  const double Sl = 1.0 + 0.015 * l50 / sqrt(20.0 + l50);
+  const double Sc = 1.0 + 0.045 * Cpm, Sh = 1.0 + 0.015 * Cpm * T;
+  const double Rt = -sin(rad(2.0 * dth)) * Rc;
+  const double x = dLp / Sl, y = dCp / Sc, z = dHp / Sh;
+  return sqrt(x * x + y * y + z * z + Rt * y * z);
+}
+
+template <typename T, typename Op>
+__device__ __forceinline__ T block_reduce(T v, Op op, T* scratch) {
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(FULL_MASK, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T r = scratch[0];
+  for (int w = 1; w < static_cast<int>(blockDim.x >> 5); ++w) r = op(r, scratch[w]);
+  return r;
+}
+
+// perceive: float32 [3, Yf, Xf, n_epy, n_epx] RAW pupil sums; scale = 1 / (num_rays_per_FoV * num_iter) (RUN:197).
+// metrics [n_ep][WGRT_EVAL_NUM]: sum dE2000, min Y, max Y, sum Y, pixels with Y == 0, max V of the gamma image.
+// image (optional): float32 [Yf, Xf, 3, n_epy, n_epx], the brightness-normalised sRGB view (EVAL:131-136).
+__global__ void __launch_bounds__(256) eval_metrics_kernel(const float* __restrict__ perceive, int Yf, int Xf, int n_epy,
+                                                           int n_epx, const __grid_constant__ wgrt_eval_params_t prm,
+                                                           double* __restrict__ metrics, float* __restrict__ image) {
+  __shared__ double scratch[8];
+  const int ep = blockIdx.x, n_ep = n_epy * n_epx;
+  const int npix = Yf * Xf;
+  const size_t plane = static_cast<size_t>(npix) * n_ep;   // one wavelength
+  double s_de = 0.0, y_min = INFINITY, y_max = -INFINITY, s_y = 0.0, zeros = 0.0, v_max = 0.0;
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+    double px[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)   // channel c (R, G, B) is wavelength index 2 - c (EVAL:119-121)
+      px[c] = prm.white_rgb[c] * (static_cast<double>(__ldg(perceive + (2 - c) * plane + static_cast<size_t>(pix) * n_ep + ep)) * prm.scale);
+    double xyz[3], g[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double lin = prm.M[3 * r] * px[0] + prm.M[3 * r + 1] * px[1] + prm.M[3 * r + 2] * px[2];
+      g[r] = srgb_gamma(fmin(fmax(lin, 0.0), 1.0));
+      xyz[r] = prm.M_xyz[3 * r] * px[0] + prm.M_xyz[3 * r + 1] * px[1] + prm.M_xyz[3 * r + 2] * px[2];
+    }
+    v_max = fmax(v_max, fmax(g[0], fmax(g[1], g[2])));
+    const double Y = xyz[1];
+    double L = 0.0, a = 0.0, b = 0.0;
+    if (Y != 0.0) {   // EVAL:141-147: normalise to Y = 100, then Lab; pixels with Y == 0 get Lab = 0
+      const double k = 100.0 / fmax(Y, 1e-10);
+      const double fx = lab_f(xyz[0] * k / prm.white_xyz[0]), fy = lab_f(xyz[1] * k / prm.white_xyz[1]),
+                   fz = lab_f(xyz[2] * k / prm.white_xyz[2]);
+      L = 116.0 * fy - 16.0; a = 500.0 * (fx - fy); b = 200.0 * (fy - fz);
+    } else {
+      zeros += 1.0;
+    }
+    s_de += delta_e_2000(L, a, b, prm.lab_d65[0], prm.lab_d65[1], prm.lab_d65[2]);
+    y_min = fmin(y_min, Y); y_max = fmax(y_max, Y); s_y += Y;
+  }
+  auto add = [](double x, double y) { return x + y; };
+  auto mn = [](double x, double y) { return fmin(x, y); };
+  auto mx = [](double x, double y) { return fmax(x, y); };
+  s_de = block_reduce(s_de, add, scratch);
+  y_min = block_reduce(y_min, mn, scratch);
+  y_max = block_reduce(y_max, mx, scratch);
+  s_y = block_reduce(s_y, add, scratch);
+  zeros = block_reduce(zeros, add, scratch);
+  v_max = block_reduce(v_max, mx, scratch);
+  if (threadIdx.x == 0) {
+    double* o = metrics + static_cast<size_t>(ep) * WGRT_EVAL_NUM;
+    o[WGRT_EVAL_SUM_DE] = s_de; o[WGRT_EVAL_Y_MIN] = y_min; o[WGRT_EVAL_Y_MAX] = y_max; o[WGRT_EVAL_Y_SUM] = s_y;
+    o[WGRT_EVAL_Y_ZEROS] = zeros; o[WGRT_EVAL_V_MAX] = v_max;
+  }
+  if (!image) return;
+  // EVAL:131-136 / 18-43: the HSV value stretch divides V, i.e. every channel, by the image's largest V
+  const double inv = v_max > 0.0 ? 1.0 / v_max : 1.0;
+  for (int pix = threadIdx.x; pix < npix; pix += blockDim.x) {
+    double px[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      px[c] = prm.white_rgb[c] * (static_cast<double>(__ldg(perceive + (2 - c) * plane + static_cast<size_t>(pix) * n_ep + ep)) * prm.scale);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const double lin = prm.M[3 * r] * px[0] + prm.M[3 * r + 1] * px[1] + prm.M[3 * r + 2] * px[2];
+      image[(static_cast<size_t>(pix) * 3 + r) * n_ep + ep] = static_cast<float>(srgb_gamma(fmin(fmax(lin, 0.0), 1.0)) * inv);
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_eval_metrics(const float* perceive, int64_t Yf, int64_t Xf, int n_epy, int n_epx,
+                                const wgrt_eval_params_t& prm, double* metrics, float* image, cudaStream_t s) {
+  const int n_ep = n_epy * n_epx;
+  if (n_ep <= 0 || Yf * Xf <= 0) return cudaSuccess;
+  eval_metrics_kernel<<<n_ep, 256, 0, s>>>(perceive, static_cast<int>(Yf), static_cast<int>(Xf), n_epy, n_epx, prm, metrics, image);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_bins_pack_u8(const float* bins, int64_t n, uint8_t* out, unsigned* stats, float limit, int num_sms,
                                 cudaStream_t s) {

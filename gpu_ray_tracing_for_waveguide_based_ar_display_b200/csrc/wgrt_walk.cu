@@ -35,6 +35,7 @@
 //    number is reported (WGRT_CNT_NEAR_TIE).
 //  * Everything state dependent is table driven from shared memory (per-cell event rows, sinfo).
 #include <climits>
+#include <cstring>
 
 #define WGRT_CHECK_TU 1   // this translation unit carries the bounds assertions of the checked build
 #include "wgrt_region.cuh"
@@ -60,6 +61,11 @@ constexpr double TIE_TOL_DEFAULT = 1e-10;
 double g_tie_tol = TIE_TOL_DEFAULT;   // wgrt_debug_set_tie_tolerance (tests widen it to exercise the redo path)
 // Resident single-warp CTAs per SM the kernel is compiled for.  Measured on C2: 32 (64 registers, a few
 // spills) 11.14 ms, 28 (72 registers, no spills) 10.8 ms, 24 (80 registers) 11.1 ms.
+// experiment switches (build.py passes -DWGRT_VARIANT=<bits>): 1 = no near-tie detection (measurement only: parity
+// is then "a few ulp from the threshold"), 2 = L1 prefetch of the next event's Jones rows at the end of phase A
+#ifndef WGRT_VARIANT
+#define WGRT_VARIANT 0
+#endif
 #ifndef WGRT_WARP_CTAS_PER_SM
 #define WGRT_WARP_CTAS_PER_SM 28
 #endif
@@ -397,11 +403,18 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       } else {
         km = __ldg(p.m + cursor); kn = __ldg(p.n + cursor); kl = has_l ? __ldg(p.lmd_num + cursor) : 0.0f;
         run_limit = t_end;   // cut on the fly where the key changes
+        // A NaN key never compares equal, not even to itself: such a ray forms a run of its own (exactly one
+        // ray is consumed, so the cursor always advances) and is left untouched, like every ray whose cell
+        // indices are outside the tables.  (Checked once per run, not per ray.)
+        if (!(km == km && kn == kn && kl == kl)) {
+          run_limit = cursor + 1;
+          km = kn = kl = -1.0f;   // (an out-of-range key: the run is invalid; lane 0's compare below is skipped)
+        }
       }
       const int64_t m = static_cast<int64_t>(km), n = static_cast<int64_t>(kn), lm = static_cast<int64_t>(kl);
       // (a non-finite key converts to an arbitrary integer; such rays are left untouched)
-      const bool valid = isfinite(km) && isfinite(kn) && isfinite(kl) && m >= 0 && m < p.X && n >= 0 && n < p.Y &&
-                         lm >= 0 && lm < p.L;
+      const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;   // (+-inf converts out of range)
+      const bool nan_run = !IMPLICIT && run_limit == cursor + 1 && km < 0.0f;
       __syncwarp();
       if (valid) build_cell_tables(p, lm, m, n, tab, jones, sh.cc, rows, lane);
       __syncwarp();
@@ -432,11 +445,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
               fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
             } else {
-              // the run key is compared by bit pattern: a NaN key still equals itself, so the ray at
-              // `cursor` always belongs to its own run and the cursor always advances
-              same = __float_as_uint(ld_stream(p.m + i)) == __float_as_uint(km) &&
-                     __float_as_uint(ld_stream(p.n + i)) == __float_as_uint(kn) &&
-                     (!has_l || __float_as_uint(ld_stream(p.lmd_num + i)) == __float_as_uint(kl));
+              same = nan_run || (ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl));
               fx = ld_stream(p.x + i); fy = ld_stream(p.y + i);
               fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i); fdl = ld_stream(p.delta_phase + i);
             }
@@ -473,7 +482,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double g = cc.inv_cos_in;
             const double e1 = (tab[R_Q] * t2 + tab[R_Q + 1] * m2 + (tab[R_Q + 2] * zre + tab[R_Q + 3] * zim)) * g;
             const double e2 = (tab[ROW + R_Q] * t2 + tab[ROW + R_Q + 1] * m2 + (tab[ROW + R_Q + 2] * zre + tab[ROW + R_Q + 3] * zim)) * g;
-            if ((fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
+            if (!(WGRT_VARIANT & 1) && (fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
               // near tie: left untouched for the literal re-walk
             } else if (u <= e1) { k = 0; esel = e1; }          // GRTF:871: no energy gate here
             else if (u <= e1 + e2) { k = 1; esel = e2; }       // GRTF:887
@@ -566,8 +575,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const bool ok3 = three && u <= e12 + e3v && r.ener * e3v > threshold;
             k = ok1 ? 0 : ok2 ? 1 : ok3 ? 2 : -1;
             esel = ok1 ? e1 : ok2 ? e2 : e3v;
-            bool tie = fabs(u - e1) < TIE_TOL || fabs(u - e12) < TIE_TOL || (three && fabs(u - (e12 + e3v)) < TIE_TOL);
-            if (threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
+            bool tie = !(WGRT_VARIANT & 1) &&
+                       (fabs(u - e1) < TIE_TOL || fabs(u - e12) < TIE_TOL || (three && fabs(u - (e12 + e3v)) < TIE_TOL));
+            if (!(WGRT_VARIANT & 1) && threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
               const double rt = 1e-9 * threshold;
               tie = tie || fabs(r.ener * e1 - threshold) < rt || fabs(r.ener * e2 - threshold) < rt ||
                     (three && fabs(r.ener * e3v - threshold) < rt);
@@ -675,6 +685,10 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             if (code != CELL_NONE) {
               r.row0 = ((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code;
               WGRT_CHECK(r.row0 >= 2 && r.row0 + 1 < rows);
+              if (WGRT_VARIANT & 2) {   // the order applied next step is row0, row0 + 1 (or + 2): bring their lines into L1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(jones + r.row0 * JROW));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(jones + (r.row0 + 2) * JROW - 1));
+              }
             } else if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) {
               lost = true;                       // GRTF:1244-1246
             } else {
@@ -785,9 +799,9 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   if (p.num_rays == 0) return cudaSuccess;
   int* tile_size = work_counter + 1;  // workspace layout: {tile counter, tile size}
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
-  const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
   const bool implicit = p.runner_points > 0;
+  const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double);
   auto kern = count ? (implicit ? walk_warp_kernel<true, true> : walk_warp_kernel<true, false>)
                     : (implicit ? walk_warp_kernel<false, true> : walk_warp_kernel<false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

@@ -82,16 +82,20 @@ def trace_full_color(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float
 def trace_and_evaluate(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: float, luts: Dict[str, np.ndarray],
                        num_rays_per_FoV: int, num_iter: int = 4, eb: Tuple[int, int] = (80, 120),
                        mask_size: int = 30, step_y: int = 8, step_x: int = 12, flags: int = 0,
-                       timings: Optional[list] = None, full_evaluation: bool = True) -> dict:
+                       timings: Optional[list] = None, full_evaluation: bool = True, return_image: bool = False,
+                       return_perceive: bool = False, host_evaluation: bool = False) -> dict:
     """The runner from its inputs to its evaluation (gpu_ray_tracing_pro_fullColor.py:59-198) with the
     bin tensor never leaving the device.
 
     Walks ``num_iter`` launches over the runner's ray layout, reduces the pupil-mask sums
-    (AR_system_evaluation_functions.py:68-109) and the per-cell totals (RUN:186) on the device and
-    downloads only those (a few MB instead of 864 MB at the default size), then finishes the
-    reference's ``evaluation()`` on the host.  Returns a dict with ``efficiency`` (RUN:186-192, per
-    wavelength), ``matrix_eye_perceive`` (normalised as RUN:197 does) and, with ``full_evaluation``,
-    ``delta_e``, ``U_fov``, ``U_EB``, ``output_image`` as the reference's ``evaluation()`` returns them.
+    (AR_system_evaluation_functions.py:68-109), the per-cell totals (RUN:186) and -- with ``full_evaluation``
+    -- the rest of ``evaluation()`` (reference lines 110-160: display model, Lab / CIEDE2000, luminance
+    statistics per eye position) on the device, and downloads only the per-cell totals (90 KB at the default
+    size) and 8 doubles per eye position (instead of the 864 MB bin tensor).  Returns a dict with ``efficiency``
+    (RUN:186-192, per wavelength), ``cell_sums`` and ``delta_e``, ``U_fov``, ``U_EB`` as the reference's
+    ``evaluation()`` returns them; ``output_image`` (5 MB) and ``matrix_eye_perceive`` (normalised as RUN:197
+    does, 5 MB) only when ``return_image`` / ``return_perceive`` ask for them.  ``host_evaluation=True`` finishes
+    ``evaluation()`` with the NumPy mirror on the host instead (the round-1 path; needs the pupil sums).
     """
     from . import AR_system_evaluation_functions as EV
     lib = _capi.load_library()
@@ -105,7 +109,9 @@ def trace_and_evaluate(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: flo
     py = np.ascontiguousarray(points[:, 1], dtype=np.float32)
     n_epy = (eb[0] - mask_size) // step_y + 1 if eb[0] >= mask_size else 0
     n_epx = (eb[1] - mask_size) // step_x + 1 if eb[1] >= mask_size else 0
-    perceive = np.zeros((L, Y, X, n_epy, n_epx), dtype=np.float32)
+    device_eval = full_evaluation and not host_evaluation
+    want_perceive = return_perceive or not device_eval
+    perceive = np.zeros((L, Y, X, n_epy, n_epx), dtype=np.float32) if want_perceive else None
     cells = np.zeros((L, Y, X), dtype=np.float32)
     args = (px, py, None, None, None, None, None, None, None, None, None, None, None,
             geom["IC"], geom["FC"], geom["FC_offset"], geom["OC"], geom["OC_offset"], float(n_g),
@@ -114,16 +120,30 @@ def trace_and_evaluate(points: np.ndarray, geom: Dict[str, np.ndarray], n_g: flo
             luts["lut_oc1"], luts["lut_oc2"], geom["lut_TIR"], geom["lut_gap"], None)
     prob, keep = pack_problem(args, host=True, flags=flags, runner_points=P, runner_first_cell=0, num_rays=N, eb=eb)
     tms = (C.c_float * 3)()
-    _capi.check(lib.wgrt_trace_evaluate_host(C.byref(prob), int(num_iter), mask_size, step_y, step_x,
-                                             perceive.ctypes.data, cells.ctypes.data, tms), lib)
+    if device_eval:
+        metrics = np.zeros((n_epy * n_epx, _capi.WGRT_EVAL_NUM), dtype=np.float64)
+        image = np.zeros((Y, X, 3, n_epy, n_epx), dtype=np.float32) if return_image else None
+        prm = EV.eval_params(1.0 / (float(num_rays_per_FoV) * float(num_iter)))
+        _capi.check(lib.wgrt_trace_evaluate_metrics_host(
+            C.byref(prob), int(num_iter), mask_size, step_y, step_x, C.byref(prm), metrics.ctypes.data,
+            cells.ctypes.data, perceive.ctypes.data if want_perceive else None,
+            image.ctypes.data if return_image else None, tms), lib)
+    else:
+        _capi.check(lib.wgrt_trace_evaluate_host(C.byref(prob), int(num_iter), mask_size, step_y, step_x,
+                                                 perceive.ctypes.data, cells.ctypes.data, tms), lib)
     if timings is not None:
         timings[:] = list(tms)
     del keep
     # RUN:186-192 with num_rays = all rays of one launch
-    out = {"efficiency": cells.astype(np.float64).sum(axis=(1, 2)) / N / num_iter * 3,
-           "cell_sums": cells,
-           "matrix_eye_perceive": perceive / np.float32(num_rays_per_FoV) / np.float32(num_iter)}   # RUN:197 is linear
-    if full_evaluation:
+    out = {"efficiency": cells.astype(np.float64).sum(axis=(1, 2)) / N / num_iter * 3, "cell_sums": cells}
+    if want_perceive:
+        out["matrix_eye_perceive"] = perceive / np.float32(num_rays_per_FoV) / np.float32(num_iter)   # RUN:197 is linear
+    if device_eval:
+        out["delta_e"], out["U_fov"], out["U_EB"] = EV.finish_metrics(metrics, Y * X, n_epy, n_epx)
+        out["eval_metrics"] = metrics
+        if return_image:
+            out["output_image"] = image
+    elif full_evaluation:
         shape_only = np.broadcast_to(np.float32(0), (L, Y, X, eb[0], eb[1]))
         out["delta_e"], out["U_fov"], out["U_EB"], out["output_image"] = EV.evaluation(
             shape_only, matrix_eye_perceive=out["matrix_eye_perceive"])

@@ -311,6 +311,50 @@ int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf
                               int mask_size, int step_y, int step_x, float* out, float* cell_sums);
 
 /*
+ * The remainder of evaluation() on the device (AR_system_evaluation_functions.py:110-160; SURVEY.md section 8,
+ * row f1): for every sampled eye position, the white image through the display model -- sRGB view (clip, gamma,
+ * brightness stretch), CIE XYZ -> Lab, CIEDE2000 against D65, luminance min / max / mean over the FoV --
+ * reduced on the device to WGRT_EVAL_NUM doubles per eye position, from which the caller forms
+ *   delta_e = mean_ep(sum_dE / (Yf * Xf)),  U_fov = sum over eye positions without a zero-luminance pixel of
+ *   Y_min / Y_max, divided by n_ep,  U_EB = min_ep / max_ep of (zero pixel ? 0 : Y_sum / (Yf * Xf)).
+ * The colour constants are the reference's own (EVAL:47-63) and arrive from the host mirror; CIE Lab and
+ * CIEDE2000 are restated from the published formulas (colour-science is the reference's dependency for them,
+ * unpinned there and absent here: "parity unpinned" for delta_e).  L must be 3 (R, G, B = wavelength 2, 1, 0).
+ */
+enum {
+  WGRT_EVAL_SUM_DE = 0, /* sum over the FoV of the CIEDE2000 colour difference to D65               */
+  WGRT_EVAL_Y_MIN,      /* min over the FoV of the luminance Y                                       */
+  WGRT_EVAL_Y_MAX,
+  WGRT_EVAL_Y_SUM,
+  WGRT_EVAL_Y_ZEROS,    /* number of FoV pixels with Y == 0                                          */
+  WGRT_EVAL_V_MAX,      /* largest gamma-encoded channel value of the view (its brightness stretch)  */
+  WGRT_EVAL_NUM = 8
+};
+typedef struct wgrt_eval_params {
+  double scale;        /* multiplies the raw pupil sums: 1 / (num_rays_per_FoV * num_iter) (RUN:197)            */
+  double white_rgb[3]; /* M^-1 @ linearised white (EVAL:112-116)                                               */
+  double M[9];         /* wavelength weights -> linear sRGB, row major (EVAL:47-49)                             */
+  double M_xyz[9];     /* wavelength weights -> CIE XYZ (EVAL:55-57)                                            */
+  double white_xyz[3]; /* Lab reference white                                                                  */
+  double lab_d65[3];   /* Lab of the D65 illuminant (EVAL:60-63)                                               */
+} wgrt_eval_params_t;
+/* dev_perceive: float32 [3, Yf, Xf, n_epy, n_epx] raw pupil sums (wgrt_eval_pupil_sums output); dev_metrics:
+ * double [n_epy * n_epx, WGRT_EVAL_NUM]; dev_image: float32 [Yf, Xf, 3, n_epy, n_epx] or NULL.  Asynchronous. */
+int wgrt_eval_metrics(const float* dev_perceive, int64_t Yf, int64_t Xf, int n_epy, int n_epx,
+                      const wgrt_eval_params_t* params, double* dev_metrics, float* dev_image, void* stream);
+/* The same for HOST arrays (synchronous). */
+int wgrt_eval_metrics_host(const float* perceive, int64_t Yf, int64_t Xf, int n_epy, int n_epx,
+                           const wgrt_eval_params_t* params, double* metrics, float* image);
+/*
+ * wgrt_trace_evaluate_host with the evaluation finished on the device: K launches, pupil sums, per-cell
+ * totals and wgrt_eval_metrics; only `metrics` [n_ep, WGRT_EVAL_NUM] (doubles), `cell_sums` [L, Y, X] and, if
+ * not NULL, `perceive` / `image` come back.  params->scale is used as given.
+ */
+int wgrt_trace_evaluate_metrics_host(const wgrt_problem_t* host_problem, int num_iter, int mask_size, int step_y,
+                                     int step_x, const wgrt_eval_params_t* params, double* metrics, float* cell_sums,
+                                     float* perceive, float* image, float* timings_ms);
+
+/*
  * Multi-GPU reduce of the bins (new; the reference is single GPU).  The bins are small integer counts in
  * float32; summing them over the ranks as uint8 (four to an int32 word) is exact whenever every entry of
  * every rank is an integer in [0, limit] with world_size * limit <= 255, and moves a quarter of the bytes
@@ -322,6 +366,70 @@ int wgrt_eval_pupil_sums_host(const float* EB, int64_t L, int64_t Yf, int64_t Xf
 int wgrt_bins_pack_u8(const float* dev_bins, int64_t n, uint8_t* dev_out, uint32_t* dev_stats, float limit,
                       void* stream);
 int wgrt_bins_unpack_u8(const uint8_t* dev_in, int64_t n, float* dev_bins, void* stream);
+
+/* ======================================================================================================
+ * Legacy deterministic energy-splitting tracer
+ *
+ * Replaces GRTF.process_rays_kernel (GPU_ray_tracing_functions.py:192-417) and its support kernels
+ * pack_active_to_front / zero_out_kernel / reset_counter_kernel (GRTF:167-190).  Instead of drawing one order
+ * per grating hit, a ray that hits a fold-coupler slice SPLITS: the zero order continues in the ray's own
+ * row, the diffracted order is appended as a new row at an atomically incremented index, and the launch
+ * ends for both (GRTF:247-282, 300-366); in the out-coupler zone every hit deposits the out-coupled energy
+ * |E|^2 (a float, not a count) into the eyebox bin and the ray continues with the zero order (GRTF:384-410).
+ * The reference ships no host driver and no LUT files for this kernel; the launch-level contract below is
+ * what its signature implies, with `vectors` as float64 rows and single-wavelength tables.
+ * ====================================================================================================== */
+#define WGRT_LEGACY_COLS 13 /* x, y, gap_x, gap_y, theta, phi, m, n, Ete, Etm, delta_phase, region_state, flag */
+
+typedef struct wgrt_legacy_problem {
+  double* vectors;            /* [capacity, 13] float64 ray rows, read and written                              */
+  int64_t capacity;           /* rows allocated: children beyond it are dropped and reported (the reference
+                               * would write out of bounds)                                                   */
+  int64_t useful_count_in;    /* rows [0, useful_count_in) are processed (GRTF:202-205)                        */
+  int32_t* total_ray_counter; /* [1]: row index of the next appended child (d_total_ray_counter)               */
+  int64_t max_steps;          /* MAX_STEPS                                                                    */
+  const double* IC;  int64_t IC_n;
+  const double* FC;  int64_t FC_n;  const int64_t* FC_offset;  int64_t n_FC;
+  const double* OC;  int64_t OC_n;  const int64_t* OC_offset;  int64_t n_OC;
+  const double* eff_reg1;  int64_t eff_reg1_n;
+  const double* eff_reg2;  int64_t eff_reg2_n;
+  const double* eff_reg_FOV;       /* [X, Y, 4, 2] */
+  const double* eff_reg_FOV_range; /* [X, Y, 4]    */
+  const double* lut_ic1; /* complex128 [X, Y, C_ic]       (channels 8, 11, 20, 23)                             */
+  const double* lut_ic2; /* complex128 [X, Y, C_ic]       (channels 0, 1, 3, 6, 15, 18)                        */
+  const double* lut_fc1; /* complex128 [n_FC, X, Y, C_fc] (channels 0, 1, 3, 4, 6, 7, 15, 16, 18, 19)          */
+  const double* lut_fc2; /* complex128 [n_FC, X, Y, C_fc] (channels 0, 1, 2, 3, 5, 6, 14, 15, 17, 18)          */
+  const double* lut_oc;  /* complex128 [n_OC, X, Y, C_oc] (channels 3, 6, 10, 13, 15, 18, 22, 25)              */
+  int32_t C_ic, C_fc, C_oc, reserved0; /* >= 24, >= 20, >= 26 */
+  const double* lut_TIR; /* [X, Y, 4] */
+  const double* lut_gap; /* [X, Y, 8] */
+  int64_t X, Y;
+  float* matrix_EB;      /* float32 [Y, X, EBy, EBx], accumulated in place (GRTF:154-165: index (n, m, iy, ix)) */
+  int64_t EBy, EBx;
+} wgrt_legacy_problem_t;
+
+int wgrt_legacy_problem_size(void);
+
+/* One launch of GRTF.process_rays_kernel[grid, block](vectors, useful_count_in, d_total_ray_counter, MAX_STEPS,
+ * ...) on DEVICE pointers, asynchronous on `stream`.  Children whose row index would be >= capacity are
+ * dropped; *total_ray_counter still counts them, so the caller sees the overflow as counter > capacity. */
+int wgrt_legacy_step(const wgrt_legacy_problem_t* dev_problem, void* stream);
+
+/* GRTF.pack_active_to_front[grid, block](src, dst, src_len, out_count) (GRTF:178-190): copies the rows of
+ * src[0:src_len] with flag != 0 and Ete^2 + Etm^2 > 0 to the front of dst; *dev_out_count (int32, must be 0
+ * before) receives their number.  Row slots are claimed per warp with a ballot / prefix sum and one atomic per
+ * warp (the reference: one atomic per row); the order of the packed rows is unspecified in both.  DEVICE
+ * pointers, asynchronous. */
+int wgrt_legacy_pack_active(const double* dev_src, double* dev_dst, int64_t src_len, int32_t* dev_out_count,
+                            void* stream);
+
+/* Whole job on HOST arrays (the driver loop the reference never shipped): upload, then per generation one
+ * wgrt_legacy_step over the live rows followed by wgrt_legacy_pack_active into the other buffer, until no row
+ * is live or `max_generations` is reached; matrix_EB comes back.  host_problem->vectors holds the initial rows
+ * [0, useful_count_in) and receives the rows still live at the end (stats[1] of them).
+ * stats (uint64[8], may be NULL): 0 generations run, 1 rows live at the end, 2 rows processed (sum over the
+ * generations), 3 children appended, 4 children dropped for lack of capacity, 5 largest live row count. */
+int wgrt_legacy_trace_host(const wgrt_legacy_problem_t* host_problem, int max_generations, uint64_t* stats);
 
 #ifdef __cplusplus
 }

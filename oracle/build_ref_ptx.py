@@ -61,7 +61,17 @@ def _signatures():
     pro = (f32,) * 11 + (arr(nt.uint32, 1),) + geom + (
         arr(c128, 3), arr(c128, 3), arr(c128, 3), arr(c128, 4), arr(c128, 4), arr(c128, 4), arr(c128, 4),
         arr(nt.float64, 3), arr(nt.float64, 3), arr(nt.float32, 4))
-    return {"process_rays_kernel_pro_fullColor": full, "process_rays_kernel_pro": pro}
+    # the legacy energy-splitting kernel and its compaction kernel (GRTF:178-417): float64 ray rows, int32 child
+    # counter, single-wavelength tables with 3 orders per group (the reference ships neither a driver nor LUT
+    # files for them; these are the argument types its signature implies)
+    legacy = (arr(nt.float64, 2), nt.int64, arr(nt.int32, 1), nt.int64,
+              arr(nt.float64, 2), arr(nt.float64, 2), arr(nt.int64, 1), arr(nt.float64, 2), arr(nt.int64, 1),
+              arr(nt.float64, 2), arr(nt.float64, 2), arr(nt.float64, 4), arr(nt.float64, 3),
+              arr(c128, 3), arr(c128, 3), arr(c128, 4), arr(c128, 4), arr(c128, 4),
+              arr(nt.float64, 3), arr(nt.float64, 3), arr(nt.float32, 4))
+    pack = (arr(nt.float64, 2), arr(nt.float64, 2), nt.int64, arr(nt.int32, 1))
+    return {"process_rays_kernel_pro_fullColor": full, "process_rays_kernel_pro": pro,
+            "process_rays_kernel": legacy, "pack_active_to_front": pack}
 
 
 def _param_layout(sig):

@@ -352,10 +352,73 @@ def make_eval(procs: int):
           f"({os.path.getsize(path) / 1e3:.0f} kB)")
 
 
+LEGACY_RECIPE = dict(num_FOV_x=3, num_FOV_y=2, scene_seed=5, lam=1, lut_seed=3, points=4, point_seed=7, max_steps=400,
+                     generations=5, capacity=8192, eb=(80, 120))
+
+
+def legacy_inputs(r=LEGACY_RECIPE):
+    """(geometry, tables, initial rows) of the legacy-tracer fixture."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import legacy, synthetic_inputs as si
+    scene = si.make_scene(r["num_FOV_x"], r["num_FOV_y"], 2, seed=r["scene_seed"], build_rays=False)
+    g, l = legacy.make_legacy_luts(scene, r["lam"], seed=r["lut_seed"])
+    pts = si.points_in_disc(scene.geom["IC"], r["points"], r["point_seed"])
+    return g, l, legacy.initial_rows(pts, r["num_FOV_x"], r["num_FOV_y"])
+
+
+def sort_rows(rows):
+    """Canonical order of ray rows (the append order of children depends on thread scheduling)."""
+    rows = np.asarray(rows)
+    return rows[np.lexsort(rows.T[::-1])]
+
+
+def make_legacy(procs: int):
+    """Golden for the legacy energy-splitting kernel process_rays_kernel (GRTF:192-417) and pack_active_to_front
+    (GRTF:178-190): `generations` rounds of launch + compaction of the unmodified reference kernels under the
+    simulator; after every launch all rows (sorted), the child counter, and after every compaction the packed
+    rows (sorted); finally the bins."""
+    GRTF = import_reference()
+    r = LEGACY_RECIPE
+    g, l, rows0 = legacy_inputs(r)
+    cap = r["capacity"]
+    a = np.zeros((cap, 13)); b = np.zeros((cap, 13))
+    a[:len(rows0)] = rows0
+    EB = np.zeros((r["num_FOV_y"], r["num_FOV_x"]) + tuple(r["eb"]), dtype=np.float32)
+    count = len(rows0)
+    out = dict(recipe=np.array(repr(r)))
+    h = hashlib.sha256()
+    for arr in list(g.values()) + list(l.values()) + [rows0]:
+        h.update(np.ascontiguousarray(arr).tobytes())
+    out["digest"] = np.array(h.hexdigest())
+    t0 = time.time()
+    for gen in range(r["generations"]):
+        counter = np.array([count], dtype=np.int32)
+        GRTF.process_rays_kernel[(count + 31) // 32, 32](
+            a, count, counter, r["max_steps"], g["IC"], g["FC"], g["FC_offset"], g["OC"], g["OC_offset"], g["eff_reg1"],
+            g["eff_reg2"], g["eff_reg_FOV"], g["eff_reg_FOV_range"], l["lut_ic1"], l["lut_ic2"], l["lut_fc1"], l["lut_fc2"],
+            l["lut_oc"], g["lut_TIR"], g["lut_gap"], EB)
+        total = int(counter[0])
+        assert total <= cap
+        out[f"launch{gen}_rows"] = sort_rows(a[:total])
+        out[f"launch{gen}_counter"] = np.array(total)
+        oc = np.zeros(1, dtype=np.int32)
+        b[:] = 0
+        GRTF.pack_active_to_front[(total + 31) // 32, 32](a, b, total, oc)
+        count = int(oc[0])
+        out[f"pack{gen}_rows"] = sort_rows(b[:count])
+        a, b = b, a
+    nz = np.flatnonzero(EB)
+    out.update(eb_index=nz.astype(np.int64), eb_value=EB.ravel()[nz], eb_shape=np.array(EB.shape),
+               sim_seconds=np.array(time.time() - t0))
+    path = os.path.join(GOLDEN_DIR, "legacy.npz")
+    np.savez_compressed(path, **out)
+    print(f"legacy: {len(rows0)} initial rows, {r['generations']} generations, live {count}, energy {EB.sum():.6f} in "
+          f"{len(nz)} bins, {time.time() - t0:.1f}s -> {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     procs = int(os.environ.get("WGRT_GOLDEN_PROCS", os.cpu_count() or 1))
-    which = sys.argv[1:] or ["units", "eval", "single_lambda"] + list(SCENES)
+    which = sys.argv[1:] or ["units", "eval", "single_lambda", "legacy"] + list(SCENES)
     for w in which:
         if w == "units":
             make_units(procs)
@@ -363,5 +426,7 @@ if __name__ == "__main__":
             make_eval(procs)
         elif w == "single_lambda":
             make_single_lambda(procs)
+        elif w == "legacy":
+            make_legacy(procs)
         else:
             make_walk(w, SCENES[w], procs)

@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 from gpu_ray_tracing_for_waveguide_based_ar_display_b200._capi import (
-    COUNTER_NAMES, WGRT_NUM_COUNTERS, WgrtProblem)
+    COUNTER_NAMES, LEGACY_COLS, WGRT_NUM_COUNTERS, WgrtLegacyProblem, WgrtProblem)
 from gpu_ray_tracing_for_waveguide_based_ar_display_b200.GPU_ray_tracing_functions import (
     pack_problem)
 
@@ -41,6 +41,10 @@ def lib() -> C.CDLL:
         L.wgrt_oracle_trace.argtypes = [C.POINTER(WgrtProblem), C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         L.wgrt_oracle_trace_events.restype = C.c_int64
         L.wgrt_oracle_trace_events.argtypes = [C.POINTER(WgrtProblem), C.c_int64, C.c_void_p, C.c_int64]
+        L.wgrt_oracle_legacy_step.restype = C.c_int
+        L.wgrt_oracle_legacy_step.argtypes = [C.POINTER(WgrtLegacyProblem), C.c_void_p]
+        L.wgrt_oracle_legacy_pack.restype = C.c_int64
+        L.wgrt_oracle_legacy_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.wgrt_oracle_locate.restype = C.c_int
         L.wgrt_oracle_locate.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p]
@@ -90,6 +94,53 @@ def trace_events(*args, idx: int, cap: int = 4096, single_lambda: bool = False, 
     if n < 0:
         raise RuntimeError(f"oracle error {n}")
     return ev[:min(n, cap)]
+
+
+def legacy_step(*args) -> int:
+    """One launch of the legacy ``process_rays_kernel`` (GRTF:192-417) on host arrays: the 21 positional
+    arguments of the reference kernel; ``vectors``, ``d_total_ray_counter`` and ``matrix_EB`` are mutated in
+    place.  Rows are processed in index order.  Returns the number of children dropped for lack of rows."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200.legacy import pack_legacy_problem
+    prob, keep = pack_legacy_problem(args, host=True)
+    dropped = C.c_uint64(0)
+    rc = lib().wgrt_oracle_legacy_step(C.byref(prob), C.byref(dropped))
+    del keep
+    if rc != 0:
+        raise RuntimeError(f"oracle error {rc}")
+    return int(dropped.value)
+
+
+def legacy_pack(src: np.ndarray, dst: np.ndarray, src_len: int) -> int:
+    """``pack_active_to_front`` (GRTF:178-190), rows visited in index order; returns the packed count."""
+    assert src.dtype == np.float64 and dst.dtype == np.float64 and src.shape[1] == LEGACY_COLS
+    return int(lib().wgrt_oracle_legacy_pack(src.ctypes.data, dst.ctypes.data, int(src_len)))
+
+
+def legacy_trace(vectors, geom, luts, eb=(80, 120), max_steps=100000, max_generations=64, capacity=None):
+    """The generation loop of ``legacy.trace`` with the oracle kernels: returns (matrix_EB, live rows, stats)."""
+    n0 = vectors.shape[0]
+    capacity = int(capacity) if capacity else max(4 * n0, 1024)
+    a = np.zeros((capacity, LEGACY_COLS)); b = np.zeros_like(a)
+    a[:n0] = vectors
+    X, Y, _ = geom["lut_TIR"].shape
+    EB = np.zeros((Y, X, eb[0], eb[1]), dtype=np.float32)
+    count, st = n0, dict(generations=0, live_rows=0, rows_processed=0, children=0, children_dropped=0, max_live_rows=n0)
+    while count > 0 and st["generations"] < max_generations:
+        counter = np.array([count], dtype=np.int32)
+        st["children_dropped"] += legacy_step(a, count, counter, int(max_steps), geom["IC"], geom["FC"], geom["FC_offset"],
+                                              geom["OC"], geom["OC_offset"], geom["eff_reg1"], geom["eff_reg2"],
+                                              geom["eff_reg_FOV"], geom["eff_reg_FOV_range"], luts["lut_ic1"], luts["lut_ic2"],
+                                              luts["lut_fc1"], luts["lut_fc2"], luts["lut_oc"], geom["lut_TIR"],
+                                              geom["lut_gap"], EB)
+        total = min(int(counter[0]), capacity)
+        st["rows_processed"] += count
+        st["children"] += int(counter[0]) - count
+        count = legacy_pack(a, b, total)
+        a, b = b, a
+        st["generations"] += 1
+        st["max_live_rows"] = max(st["max_live_rows"], count)
+    st["live_rows"] = count
+    return EB, a[:count].copy(), st
 
 
 def locate(verts, offsets, px, py):

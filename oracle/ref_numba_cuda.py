@@ -95,8 +95,9 @@ def _array_params(obj, want):
     return vals
 
 
-def launch(name: str, args: Sequence, stream: int = 0, threads_per_block: int = 256) -> None:
-    """``GRTF.<name>[ceil(N/256), 256, stream](*args)`` with the reference's compiled kernel."""
+def launch(name: str, args: Sequence, stream: int = 0, threads_per_block: int = 256, n: int = None) -> None:
+    """``GRTF.<name>[ceil(N/256), 256, stream](*args)`` with the reference's compiled kernel (N = length of the
+    first array unless ``n`` is given)."""
     cu = _driver()
     _, fn, info = _function(name)
     if len(args) != len(info["params"]):
@@ -105,9 +106,12 @@ def launch(name: str, args: Sequence, stream: int = 0, threads_per_block: int = 
     for a, want in zip(args, info["params"]):
         if want["kind"] == "array":
             vals += _array_params(a, want)
+        elif want["dtype"].startswith("int"):
+            vals.append(C.c_int64(int(a)))
         else:
             vals.append(C.c_double(float(a)))
-    n = int(args[0].__cuda_array_interface__["shape"][0])
+    if n is None:
+        n = int(args[0].__cuda_array_interface__["shape"][0])
     if n == 0:
         return
     params = (C.c_void_p * len(vals))(*[C.cast(C.pointer(v), C.c_void_p) for v in vals])

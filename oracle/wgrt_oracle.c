@@ -532,6 +532,181 @@ int64_t wgrt_oracle_trace_events(const wgrt_problem_t* p, int64_t idx, double* e
   return tr.n;
 }
 
+
+/* ================================================================================================
+ * Legacy deterministic energy-splitting tracer: process_rays_kernel (GRTF:192-417) and
+ * pack_active_to_front (GRTF:178-190), restated.  Rows are processed in index order by ONE thread, so
+ * children are appended in a deterministic order (the reference's order depends on thread scheduling;
+ * tests compare the rows as a multiset).
+ * ================================================================================================ */
+static inline void legacy_efield(const double* lut, int64_t entry, int32_t C, int c0, int c1, int c2, int c3,
+                                 double Ete, double Etm, double dl, double* o_te, double* o_tm, double* o_dl) {
+  counters_t cn;
+  cplx q[4] = {lut_at(lut, entry, C, c0), lut_at(lut, entry, C, c1), lut_at(lut, entry, C, c2), lut_at(lut, entry, C, c3)};
+  efield(Ete, Etm, dl, q, o_te, o_tm, o_dl, &cn);
+}
+
+/* GRTF:154-165: float32 atomic add of `value` at (n, m, iy, ix) */
+static void legacy_deposit(const wgrt_legacy_problem_t* p, int64_t m, int64_t n, double x, double y, double value) {
+  const double* r = p->eff_reg_FOV_range + 4 * (m * p->Y + n);
+  double xmin = r[0], xmax = r[1], ymin = r[2], ymax = r[3];
+  double dx = (xmax - xmin) / (double)p->EBx;
+  double dy = (ymax - ymin) / (double)p->EBy;
+  int64_t ix = (int64_t)floor((x - xmin) / dx);
+  int64_t iy = (int64_t)floor((y - ymin) / dy);
+  int64_t flat = ((n * p->X + m) * p->EBy + iy) * p->EBx + ix;
+  int64_t total = p->Y * p->X * p->EBy * p->EBx;
+  if (flat >= 0 && flat < total) p->matrix_EB[flat] += (float)value;
+}
+
+/* writes a row the way the split branches do (GRTF:252-263 ff.) */
+static void legacy_write(double* v, double te, double tm, double dl, double x, double y, double gx, double gy,
+                         double theta, double phi, int64_t m, int64_t n, double state) {
+  v[8] = te; v[9] = tm; v[10] = dl;
+  v[0] = x; v[1] = y; v[2] = gx; v[3] = gy; v[4] = theta; v[5] = phi;
+  v[6] = (double)m; v[7] = (double)n; v[11] = state; v[12] = 1.0;
+}
+
+static void legacy_walk_row(const wgrt_legacy_problem_t* p, int64_t idx, uint64_t* dropped) {
+  counters_t cn;
+  double* v = p->vectors + WGRT_LEGACY_COLS * idx;
+  if (v[12] == 0.0) return;
+  double x = v[0], y = v[1], gap_x = v[2], gap_y = v[3], theta = v[4], phi = v[5];
+  const int64_t m = (int64_t)v[6], n = (int64_t)v[7];
+  double Ete = v[8], Etm = v[9], dl = v[10], region_state = v[11];
+  if (m < 0 || m >= p->X || n < 0 || n >= p->Y) return;   /* outside every table (the reference would read out of bounds) */
+  const int64_t cell = m * p->Y + n, cpp = p->X * p->Y;
+  const double* T = p->lut_TIR + 4 * cell;
+  const double* G = p->lut_gap + 8 * cell;
+  const int32_t Ci = p->C_ic, Cf = p->C_fc, Co = p->C_oc;
+  double te, tm, d2;
+
+  if (region_state == 0.0) {   /* GRTF:222-233 */
+    theta = lut_at(p->lut_ic2, cell, Ci, 0).re;   /* only .real is ever stored (GRTF:256-257) */
+    phi = lut_at(p->lut_ic2, cell, Ci, 1).re;
+    legacy_efield(p->lut_ic1, cell, Ci, 8, 11, 20, 23, Ete, Etm, dl, &Ete, &Etm, &dl);
+    dl += T[0];
+    gap_x = G[0]; gap_y = G[1];
+    x += gap_x; y += gap_y;
+    region_state = 1.0;
+  }
+#define LEGACY_CHILD(lut, e, c0, c1, c2, c3, tir, g0, dirlut, st)                                        \
+  do {                                                                                                   \
+    int64_t ni = (int64_t)(*p->total_ray_counter);                                                       \
+    *p->total_ray_counter = (int32_t)(ni + 1);                                                           \
+    if (ni < p->capacity) {                                                                              \
+      legacy_efield(lut, e, Cf, c0, c1, c2, c3, Ete, Etm, dl, &te, &tm, &d2);                            \
+      legacy_write(p->vectors + WGRT_LEGACY_COLS * ni, te, tm, d2 + T[tir], x + G[g0], y + G[(g0) + 1], \
+                   G[g0], G[(g0) + 1], lut_at(dirlut, e, Cf, 0).re, lut_at(dirlut, e, Cf, 1).re, m, n, st); \
+    } else {                                                                                             \
+      ++*dropped;                                                                                        \
+    }                                                                                                    \
+  } while (0)
+
+  if (region_state == 1.0) {   /* GRTF:235-286 */
+    for (int64_t it = 0; it < p->max_steps; ++it) {
+      if (!inside_or_on_edge(x, y, p->IC, 0, p->IC_n, &cn)) {
+        for (int64_t i = 0; i < p->n_FC; ++i) {
+          if (inside_or_on_edge(x, y, p->FC, p->FC_offset[i], p->FC_offset[i + 1], &cn)) {
+            const int64_t e = i * cpp + cell;
+            legacy_efield(p->lut_fc1, e, Cf, 3, 6, 15, 18, Ete, Etm, dl, &te, &tm, &d2);
+            legacy_write(v, te, tm, d2 + T[0], x + gap_x, y + gap_y, gap_x, gap_y, theta, phi, m, n, 2.0);
+            LEGACY_CHILD(p->lut_fc1, e, 4, 7, 16, 19, 1, 2, p->lut_fc2, 3.0);
+            return;
+          }
+        }
+        dl += 2 * T[0];
+        x += gap_x; y += gap_y;
+      } else {
+        legacy_efield(p->lut_ic2, cell, Ci, 3, 6, 15, 18, Ete, Etm, dl, &Ete, &Etm, &dl);
+        dl += T[0];
+        x += gap_x; y += gap_y;
+      }
+    }
+    v[12] = 0.0;   /* GRTF:284-286 */
+    return;
+  }
+
+  if (region_state == 2.0 || region_state == 3.0) {   /* GRTF:288-377 */
+    if (!inside_or_on_edge(x, y, p->eff_reg1, 0, p->eff_reg1_n, &cn)) { v[12] = 0.0; return; }
+    for (int64_t it = 0; it < p->max_steps; ++it) {
+      for (int64_t i = 0; i < p->n_FC; ++i) {
+        if (inside_or_on_edge(x, y, p->FC, p->FC_offset[i], p->FC_offset[i + 1], &cn)) {
+          const int64_t e = i * cpp + cell;
+          if (region_state == 2.0) {
+            legacy_efield(p->lut_fc1, e, Cf, 3, 6, 15, 18, Ete, Etm, dl, &te, &tm, &d2);
+            legacy_write(v, te, tm, d2 + T[0], x + gap_x, y + gap_y, gap_x, gap_y, theta, phi, m, n, region_state);
+            LEGACY_CHILD(p->lut_fc1, e, 4, 7, 16, 19, 1, 2, p->lut_fc2, 3.0);
+          } else {
+            legacy_efield(p->lut_fc2, e, Cf, 3, 6, 15, 18, Ete, Etm, dl, &te, &tm, &d2);
+            legacy_write(v, te, tm, d2 + T[1], x + gap_x, y + gap_y, gap_x, gap_y, theta, phi, m, n, region_state);
+            LEGACY_CHILD(p->lut_fc2, e, 2, 5, 14, 17, 0, 0, p->lut_fc1, 2.0);
+          }
+          return;
+        }
+      }
+      if (!inside_or_on_edge(x, y, p->eff_reg2, 0, p->eff_reg2_n, &cn)) {
+        if (region_state == 3.0) { region_state = 4.0; break; }
+        v[12] = 0.0;
+        return;
+      }
+      dl += 2 * T[0];   /* GRTF:375: T[.., 0] also for state 3 */
+      x += gap_x; y += gap_y;
+    }
+  }
+#undef LEGACY_CHILD
+
+  if (region_state == 4.0) {   /* GRTF:378-417; nothing but the flag is ever written back from here */
+    for (int64_t it = 0; it < p->max_steps; ++it) {
+      if (!inside_or_on_edge(x, y, p->eff_reg1, 0, p->eff_reg1_n, &cn)) { v[12] = 0.0; return; }
+      int hit = 0;
+      for (int64_t i = 0; i < p->n_OC; ++i) {
+        if (inside_or_on_edge(x, y, p->OC, p->OC_offset[i], p->OC_offset[i + 1], &cn)) {
+          const int64_t e = i * cpp + cell;
+          hit = 1;
+          if (inside_or_on_edge(x, y, p->eff_reg_FOV + 8 * cell, 0, 4, &cn)) {
+            legacy_efield(p->lut_oc, e, Co, 10, 13, 22, 25, Ete, Etm, dl, &te, &tm, &d2);
+            const double efficiency = te * te + tm * tm;
+            if (efficiency > 0) legacy_deposit(p, m, n, x, y, efficiency);
+          }
+          legacy_efield(p->lut_oc, e, Co, 3, 6, 15, 18, Ete, Etm, dl, &Ete, &Etm, &dl);
+          dl += T[1];
+          x += gap_x; y += gap_y;
+          if (Ete * Ete + Etm * Etm < 0) { v[12] = 0.0; return; }
+          break;
+        }
+      }
+      if (!hit) {
+        dl += 2 * T[1];
+        x += gap_x; y += gap_y;
+      }
+    }
+  }
+}
+
+int wgrt_oracle_legacy_step(const wgrt_legacy_problem_t* p, uint64_t* dropped) {
+  if (!p || !p->vectors || !p->total_ray_counter || !p->matrix_EB || p->useful_count_in < 0 ||
+      p->useful_count_in > p->capacity || p->C_ic < 24 || p->C_fc < 20 || p->C_oc < 26)
+    return WGRT_ERR_INVALID;
+  uint64_t d = 0;
+  for (int64_t i = 0; i < p->useful_count_in; ++i) legacy_walk_row(p, i, &d);
+  if (dropped) *dropped = d;
+  return WGRT_OK;
+}
+
+/* GRTF:178-190, rows visited in index order */
+int64_t wgrt_oracle_legacy_pack(const double* src, double* dst, int64_t src_len) {
+  int64_t pos = 0;
+  for (int64_t i = 0; i < src_len; ++i) {
+    const double* r = src + WGRT_LEGACY_COLS * i;
+    if (r[12] != 0.0 && r[8] * r[8] + r[9] * r[9] > 0.0) {
+      memcpy(dst + WGRT_LEGACY_COLS * pos, r, sizeof(double) * WGRT_LEGACY_COLS);
+      ++pos;
+    }
+  }
+  return pos;
+}
+
 /* ---- unit-level entry points (same contracts as the wgrt_debug_* functions) --------------- */
 int wgrt_oracle_locate(const double* verts, int64_t n_verts, const int64_t* offsets, int64_t n_polys,
                        const double* px, const double* py, int64_t n_points, int32_t* out) {

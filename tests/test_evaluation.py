@@ -151,3 +151,48 @@ def test_bins_pack_unpack_u8():
             EV._capi.check(lib.wgrt_bins_pack_u8(C.c_void_p(t.data_ptr()), a.size, C.c_void_p(q.data_ptr()),
                                                  C.c_void_p(st.data_ptr()), C.c_float(31.0), None), lib)
             assert int(st[1].item()) == int(a.max() > 31)      # entries above the limit are flagged
+
+
+@pytest.mark.gpu
+def test_device_evaluation_matches_reference():
+    """evaluation() lines 110-160 on the device (wgrt_eval_metrics): U_fov, U_EB and the sRGB view against the
+    reference's own outputs (rel 1e-5), delta_e against the restated colour maths the fixture was made with."""
+    g, EB, EB2 = load()
+    raw, _ = EV.pupil_sums(EB)                                   # raw integer pupil sums, exact
+    scale = 1.0 / (int(g["rays_per_fov"]) * int(g["num_iter"]))
+    delta_e, U_fov, U_EB, img = EV.evaluation_device(raw, scale)
+    assert U_fov == pytest.approx(float(g["U_fov"]), rel=1e-5)
+    assert U_EB == pytest.approx(float(g["U_EB"]), rel=1e-5)
+    assert delta_e == pytest.approx(float(g["delta_e_stubbed"]), rel=1e-6)
+    np.testing.assert_allclose(img, g["output_image"], rtol=1e-4, atol=1e-5)
+    # and against the host mirror on the same raw sums (same formulas, double precision both sides)
+    d2, uf2, ue2, img2 = EV.evaluation(EB2, matrix_eye_perceive=raw * np.float32(scale))
+    assert (delta_e, U_fov, U_EB) == pytest.approx((d2, uf2, ue2), rel=1e-6)
+    # eye positions that see a dark pixel count as zero uniformity on both sides
+    raw0 = raw.copy(); raw0[:, 2, 3, 1, 4] = 0
+    d3, uf3, ue3, _ = EV.evaluation_device(raw0, scale, return_image=False)
+    d4, uf4, ue4, _ = EV.evaluation(EB2, matrix_eye_perceive=raw0 * np.float32(scale))
+    assert (d3, uf3, ue3) == pytest.approx((d4, uf4, ue4), rel=1e-6) and ue3 == 0
+
+
+@pytest.mark.gpu
+def test_trace_and_evaluate_finishes_on_the_device():
+    """runner.trace_and_evaluate: K launches + pupil sums + evaluation() on the device, < 100 KB downloaded;
+    equal to the host-finished path on the same job."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import runner, synthetic_inputs as si
+    eff = dict(incouple=0.9, incouple_m1=0.05, ic_zero=0.95, ic_cross=0.02, fc_zero=0.8, fc_turn=0.18,
+               oc_zero=0.85, oc_cross=0.02, outcouple=0.12)
+    rpc = 4000
+    scene = si.make_scene(6, 5, rpc, seed=41, eff=eff, build_rays=False)
+    pts = si.points_in_disc(scene.geom["IC"], rpc // 2, 42)
+    dev = runner.trace_and_evaluate(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, return_image=True,
+                                    return_perceive=True)
+    host = runner.trace_and_evaluate(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2, host_evaluation=True)
+    assert np.array_equal(dev["cell_sums"], host["cell_sums"]) and dev["cell_sums"].sum() > 0
+    assert np.array_equal(dev["matrix_eye_perceive"], host["matrix_eye_perceive"])
+    for k in ("delta_e", "U_fov", "U_EB"):
+        assert dev[k] == pytest.approx(host[k], rel=1e-6), k
+    np.testing.assert_allclose(dev["output_image"], host["output_image"], rtol=1e-4, atol=1e-5)
+    lean = runner.trace_and_evaluate(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=2)
+    assert "output_image" not in lean and "matrix_eye_perceive" not in lean
+    assert (lean["delta_e"], lean["U_fov"], lean["U_EB"]) == (dev["delta_e"], dev["U_fov"], dev["U_EB"])
