@@ -102,14 +102,14 @@ def test_trace_and_evaluate_keeps_bins_on_the_device():
     EB = runner.trace_full_color(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=it)
     assert EB.sum() > 1000
     want_p, want_c = EV.pupil_sums(EB)
-    got = runner.trace_and_evaluate(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=it)
+    got = runner.trace_and_evaluate(pts, scene.geom, scene.n_g, scene.luts, rpc, num_iter=it, return_perceive=True, return_image=True)
     assert np.array_equal(got["cell_sums"], want_c)
     assert np.array_equal(got["matrix_eye_perceive"] * np.float32(rpc) * np.float32(it), want_p) or \
         np.allclose(got["matrix_eye_perceive"], want_p / rpc / it, rtol=1e-6, atol=0)
     d_e, U_fov, U_EB, img = EV.evaluation(EB / np.float32(rpc) / np.float32(it))
     assert got["U_fov"] == pytest.approx(U_fov, rel=1e-5) and got["U_EB"] == pytest.approx(U_EB, rel=1e-5)
     assert got["delta_e"] == pytest.approx(d_e, rel=1e-5)
-    np.testing.assert_allclose(got["output_image"], img, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(got["output_image"], img, rtol=1e-4, atol=1e-5)   # device: double -> float32; host: cv2 float32 HSV
     eff = EV.efficiency_per_colour(EB, scene.eb_shape[0] * 6 * 5 * rpc, it)
     np.testing.assert_allclose(got["efficiency"], eff, rtol=1e-12)
 

@@ -240,3 +240,25 @@ def test_strided_device_views_are_rejected():
                            ((2, 3, 4), (96, 16, 4))):          # padded rows
         with pytest.raises(ValueError):
             _describe(Fake(shape, strides), "bad")
+
+
+def test_integration_stub_matches_the_library():
+    """INTEGRATION.md section 3 shows the ctypes stub a maintainer would add; its struct must have the size
+    the built library reports (the stub had gone stale)."""
+    import ctypes as C
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = text[text.index("class wgrt_problem_t(C.Structure)"):]
+    block = block[:block.index("lib = C.CDLL")]
+    ns = {"C": C}
+    exec(block, ns)
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import _capi
+    lib = _capi.load_library()
+    assert C.sizeof(ns["wgrt_problem_t"]) == lib.wgrt_problem_size() == C.sizeof(_capi.WgrtProblem)
+    assert [f[0] for f in ns["wgrt_problem_t"]._fields_] == [f[0] for f in _capi.WgrtProblem._fields_]
+    assert lib.wgrt_legacy_problem_size() == C.sizeof(_capi.WgrtLegacyProblem)
+    # every entry point named in the table of section 1 exists in the library
+    table = text[text.index("## 1."):text.index("## 2.")]
+    for name in set(re.findall(r"`(wgrt_[a-z0-9_]+)(?![a-z0-9_.])", table)) - {"wgrt_problem_t"}:
+        assert any(e == name or e.startswith(name + "_") for e in _capi.EXPORTED_SYMBOLS), name
