@@ -60,6 +60,8 @@ struct Workspace {
   int num_sms = 0;
   DeviceBuf cells[NUM_REGIONS], detail[NUM_REGIONS], rowmask[NUM_REGIONS], coarse[NUM_REGIONS], rowmask_c[NUM_REGIONS];
   DeviceBuf atlas;   // uint32 [ATLAS_N * ATLAS_N] level 1, then [ATLAS_N2 * ATLAS_N2] level 2
+  DeviceBuf zone2;   // uint16 [ATLAS_N2 * ATLAS_N2] level-2 zone ids
+  DeviceBuf zone_small;   // level1 | words | trans | hash_keys | hash_zone | words1 | ZoneDyn (see setup_regions)
   DeviceBuf small;   // RegionDyn[NUM_REGIONS] | AtlasDyn @ 256 | tile counters @ 512 | hash state @ 768 | counters @ 1024 | Region[NUM_REGIONS] @ 1280
   bool index_stale = true;  // the index buffers were (re)allocated or used by a debug call
   DeviceBuf jones[3];   // per-warp Jones-matrix scratch of the warp walk, one per launch slot
@@ -92,6 +94,8 @@ struct Workspace {
     }
     small.release();
     atlas.release();
+    zone2.release();
+    zone_small.release();
     for (auto& j : jones) j.release();
     for (auto& j : redo) j.release();
     arena.release();
@@ -181,6 +185,25 @@ int setup_regions(Workspace& w, RegionSet& rs, const double* const verts[NUM_REG
     const void* before = w.atlas.ptr;
     CUDA_TRY(w.atlas.reserve(sizeof(uint32_t) * (static_cast<size_t>(ATLAS_N) * ATLAS_N + static_cast<size_t>(ATLAS_N2) * ATLAS_N2)));
     if (before != w.atlas.ptr) w.index_stale = true;
+  }
+  {
+    const void* b2 = w.zone2.ptr;
+    const void* bs = w.zone_small.ptr;
+    CUDA_TRY(w.zone2.reserve(sizeof(uint16_t) * static_cast<size_t>(ATLAS_N2) * ATLAS_N2));
+    const size_t o_words = sizeof(uint16_t) * ZONE_N1 * ZONE_N1, o_trans = o_words + sizeof(uint32_t) * ZONE_CAP,
+                 o_keys = o_trans + sizeof(uint32_t) * ZONE_STATES * ZONE_CAP, o_hz = o_keys + sizeof(uint32_t) * 2 * ZONE_CAP,
+                 o_w1 = o_hz + sizeof(uint16_t) * 2 * ZONE_CAP, o_dyn = o_w1 + sizeof(uint32_t) * ZONE_N1 * ZONE_N1;
+    CUDA_TRY(w.zone_small.reserve(o_dyn + sizeof(ZoneDyn)));
+    if (b2 != w.zone2.ptr || bs != w.zone_small.ptr) w.index_stale = true;
+    char* base = static_cast<char*>(w.zone_small.ptr);
+    rs.zones.level1 = reinterpret_cast<uint16_t*>(base);
+    rs.zones.level2 = static_cast<uint16_t*>(w.zone2.ptr);
+    rs.zones.words = reinterpret_cast<uint32_t*>(base + o_words);
+    rs.zones.trans = reinterpret_cast<uint32_t*>(base + o_trans);
+    rs.zones.hash_keys = reinterpret_cast<uint32_t*>(base + o_keys);
+    rs.zones.hash_zone = reinterpret_cast<uint16_t*>(base + o_hz);
+    rs.zones.words1 = reinterpret_cast<uint32_t*>(base + o_w1);
+    rs.zones.dyn = reinterpret_cast<ZoneDyn*>(base + o_dyn);
   }
   rs.atlas = static_cast<uint32_t*>(w.atlas.ptr);
   rs.atlas_dyn = w.atlas_dyn();
@@ -818,7 +841,7 @@ int wgrt_debug_locate(const double* verts, int64_t n_verts, const int64_t* offse
     if (rc != WGRT_OK) return rc;
     CUDA_TRY(launch_region_build(rs, true, nullptr));
     w->index_stale = true;  // the walk's index was overwritten
-    CUDA_TRY(launch_debug_locate_grid(rs, REG_FC, d_x, d_y, n_points, d_out, w->counters(), mode == 2 ? 1 : 0, nullptr));
+    CUDA_TRY(launch_debug_locate_grid(rs, REG_FC, d_x, d_y, n_points, d_out, w->counters(), mode == 2 ? 1 : (mode == 3 ? 2 : 0), nullptr));
   }
   CUDA_TRY(cudaDeviceSynchronize());
   if (n_points) CUDA_TRY(cudaMemcpy(out, d_out, (size_t)n_points * 4, cudaMemcpyDeviceToHost));

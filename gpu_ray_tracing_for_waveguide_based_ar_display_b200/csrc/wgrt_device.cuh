@@ -201,8 +201,39 @@ constexpr int ATLAS_SUB_SHIFT = 6;                      // level 2: every level-
 constexpr int ATLAS_N2 = ATLAS_N << ATLAS_SUB_SHIFT;    // 4096 x 4096 words = 64 MB; only
                                                         // cells under MIXED level-1 cells are populated
 
+// The ZONE form of the atlas (what the production walk reads).  Every distinct atlas word -- a combination
+// of (in-coupler, effective region 1 / 2, fold slice, out-coupler slice) answers, certain or MIXED -- is a
+// "zone" with a 16-bit id; the two grid levels store zone ids instead of words (half the bytes, and twice the
+// first-level resolution in the same L1 footprint), and a per-geometry TRANSITION TABLE trans[state][zone]
+// holds what the walk's loop head does with a ray of that region state in that zone: next state, lost,
+// event row or free-bounce vector / phase.  The table is produced by running the walk's own decode function
+// on every (state, zone word) pair, so the two cannot disagree; entries whose state needs a MIXED field are
+// flagged and take the word path (zone word -> atlas_resolve -> decode).
+constexpr int ZONE_N1 = 128;                       // level 1: 128 x 128 uint16 = 32 KB
+constexpr int ZONE_SUB_SHIFT = 5;                  // level 2: 32 x 32 per level-1 cell = the 4096 x 4096 level-2 grid of the atlas
+constexpr int ZONE_CAP = 4096;                     // distinct zones supported (hash slots 2 x that)
+constexpr uint16_t ZONE_MIXED = 0xFFFFu;           // level-1 marker: ask level 2
+constexpr int ZONE_STATES = 8;                     // region states 0..5 and the two pending states
+struct ZoneDyn {                                   // computed on the device
+  double x0, y0, inv_dx, inv_dy;                   // level-1 cell coordinates (same box as the atlas)
+  int num_zones;                                   // <= ZONE_CAP, else the zone form is invalid (word path everywhere)
+  int outside_zone;                                // zone of points outside the atlas box
+  int valid, pad_;
+};
+struct ZoneSet {
+  uint16_t* level1;                 // [ZONE_N1 * ZONE_N1]
+  uint16_t* level2;                 // [ATLAS_N2 * ATLAS_N2], populated under MIXED level-1 cells
+  uint32_t* words;                  // [ZONE_CAP] zone -> atlas word
+  uint32_t* trans;                  // [ZONE_STATES * ZONE_CAP] transition table (wgrt_walk.cu: decode_transition)
+  uint32_t* hash_keys;              // [2 * ZONE_CAP] open addressing, word -> slot
+  uint16_t* hash_zone;              // [2 * ZONE_CAP] slot -> zone id
+  uint32_t* words1;                 // [ZONE_N1 * ZONE_N1] scratch: level-1 words at the zone resolution
+  ZoneDyn* dyn;
+};
+
 struct RegionSet {
   RegionStatic st[NUM_REGIONS];
+  ZoneSet zones;
   uint32_t* atlas;                  // device [ATLAS_N * ATLAS_N] then [ATLAS_N2 * ATLAS_N2]
   AtlasDyn* atlas_dyn;              // device
   void* regions;                    // device Region[NUM_REGIONS] (wgrt_region.cuh), refreshed at every index build
@@ -213,6 +244,8 @@ struct RegionSet {
 
 cudaError_t launch_walk_strict(const wgrt_problem_t& p, unsigned long long* counters, cudaStream_t s);
 cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s);
+// transition-table entry for (state, zone word): defined next to the walk that applies it (wgrt_walk.cu)
+cudaError_t launch_zone_transitions(const RegionSet& rs, int n_FC, int n_OC, cudaStream_t s);
 void set_tie_tolerance(double tol);
 cudaError_t walk_check_failures(unsigned long long* out, bool reset);   // cudaErrorNotSupported unless WGRT_CHECKED
 cudaError_t launch_debug_deposit_inside(const double* rect, const double* px, const double* py, int64_t n, int32_t* out,

@@ -303,6 +303,162 @@ __global__ void __launch_bounds__(256) region_atlas2_kernel(const __grid_constan
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Zone form of the atlas (wgrt_device.cuh: ZoneSet): distinct atlas words -> 16-bit zone ids.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t ZONE_EMPTY = 0xFFFFFFFFu;   // never a valid atlas word (bits 24-30 are always 0)
+constexpr uint32_t ZONE_SLOTS = 2u * ZONE_CAP;
+
+__device__ __forceinline__ uint32_t zone_hash(uint32_t w) {
+  w ^= w >> 16; w *= 0x7feb352dU; w ^= w >> 15; w *= 0x846ca68bU; w ^= w >> 16;
+  return w & (ZONE_SLOTS - 1u);
+}
+__device__ __forceinline__ void zone_insert(uint32_t* __restrict__ keys, uint32_t w) {
+  uint32_t h = zone_hash(w);
+  for (uint32_t probe = 0; probe < ZONE_SLOTS; ++probe) {
+    const uint32_t cur = keys[h];
+    if (cur == w) return;
+    if (cur == ZONE_EMPTY) {
+      const uint32_t old = atomicCAS(keys + h, ZONE_EMPTY, w);
+      if (old == ZONE_EMPTY || old == w) return;
+    }
+    h = (h + 1u) & (ZONE_SLOTS - 1u);
+  }
+}
+__device__ __forceinline__ int zone_find(const uint32_t* __restrict__ keys, uint32_t w) {
+  uint32_t h = zone_hash(w);
+  for (uint32_t probe = 0; probe < ZONE_SLOTS; ++probe) {
+    const uint32_t cur = keys[h];
+    if (cur == w) return static_cast<int>(h);
+    if (cur == ZONE_EMPTY) return -1;
+    h = (h + 1u) & (ZONE_SLOTS - 1u);
+  }
+  return -1;
+}
+
+__global__ void zone_reset_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ZONE_SLOTS) rs.zones.hash_keys[t] = ZONE_EMPTY;
+}
+
+// level 1 at the zone resolution: every cell classified against all five sets (as region_atlas_kernel does
+// at the atlas resolution); the words go to a scratch grid and into the hash
+__global__ void zone_level1_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  double xmin, ymin, w, h;
+  atlas_bbox(rs, xmin, ymin, w, h);
+  const double w1 = w * (static_cast<double>(ATLAS_N) / ZONE_N1), h1 = h * (static_cast<double>(ATLAS_N) / ZONE_N1);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) zone_insert(rs.zones.hash_keys, ATLAS_OUTSIDE);
+  if (t >= ZONE_N1 * ZONE_N1) return;
+  const int iy = t / ZONE_N1, ix = t - iy * ZONE_N1;
+  const double mx = margin_of(w1), my = margin_of(h1);
+  uint32_t word = 0;
+  for (int r = 0; r < NUM_REGIONS; ++r) {
+    uint32_t detail;
+    const uint8_t code = classify_cell(rs.st[r], nullptr, xmin + ix * w1 - mx, xmin + (ix + 1) * w1 + mx, ymin + iy * h1 - my,
+                                       ymin + (iy + 1) * h1 + my, xmin + (ix + 0.5) * w1, ymin + (iy + 0.5) * h1, detail);
+    word |= atlas_field(r, code);
+    if (code == CELL_AMBIG) word |= ATLAS_ANY_MIXED;
+  }
+  rs.zones.words1[t] = word;
+  zone_insert(rs.zones.hash_keys, word);
+}
+
+// level 2: the words the atlas already holds under its MIXED level-1 cells
+__global__ void __launch_bounds__(256) zone_collect2_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  if (!(rs.atlas[blockIdx.x] & ATLAS_ANY_MIXED)) return;
+  constexpr int S = 1 << ATLAS_SUB_SHIFT;
+  const int cy = blockIdx.x / ATLAS_N, cx = blockIdx.x - cy * ATLAS_N;
+  const uint32_t* in = rs.atlas + ATLAS_N * ATLAS_N;
+  uint32_t last = ZONE_EMPTY;
+  for (int t = threadIdx.x; t < S * S; t += blockDim.x) {
+    const int iy = (cy << ATLAS_SUB_SHIFT) + t / S, ix = (cx << ATLAS_SUB_SHIFT) + (t & (S - 1));
+    const uint32_t wd = in[static_cast<size_t>(iy) * ATLAS_N2 + ix];
+    if (wd != last) zone_insert(rs.zones.hash_keys, wd);
+    last = wd;
+  }
+}
+
+// dense zone ids in slot order (one block)
+__global__ void __launch_bounds__(1024) zone_number_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty) return;
+  __shared__ int s_cnt[1024];
+  constexpr int PER = ZONE_SLOTS / 1024;
+  const uint32_t* keys = rs.zones.hash_keys;
+  int c = 0;
+  for (int k = 0; k < PER; ++k) c += keys[threadIdx.x * PER + k] != ZONE_EMPTY;
+  s_cnt[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {   // inclusive scan
+    const int v = threadIdx.x >= o ? s_cnt[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_cnt[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int id = s_cnt[threadIdx.x] - c;
+  const int total = s_cnt[1023];
+  for (int k = 0; k < PER; ++k) {
+    const int slot = threadIdx.x * PER + k;
+    if (keys[slot] != ZONE_EMPTY) {
+      if (id < ZONE_CAP) {
+        rs.zones.hash_zone[slot] = static_cast<uint16_t>(id);
+        rs.zones.words[id] = keys[slot];
+      }
+      ++id;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double xmin, ymin, w, h;
+    atlas_bbox(rs, xmin, ymin, w, h);
+    ZoneDyn d;
+    d.x0 = xmin; d.y0 = ymin;
+    d.inv_dx = 2.0 * (1.0 / w); d.inv_dy = 2.0 * (1.0 / h);   // exactly twice the atlas' level-1 scale: the same level-2 cell
+    static_assert(ZONE_N1 == 2 * ATLAS_N && ZONE_SUB_SHIFT + 1 == ATLAS_SUB_SHIFT, "zone grid = atlas grid refined once");
+    d.num_zones = total;
+    d.valid = total <= ZONE_CAP ? 1 : 0;
+    const int so = zone_find(keys, ATLAS_OUTSIDE);
+    d.outside_zone = (d.valid && so >= 0) ? rs.zones.hash_zone[so] : 0;
+    d.pad_ = 0;
+    *rs.zones.dyn = d;
+  }
+}
+
+__global__ void zone_write1_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty || !rs.zones.dyn->valid) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ZONE_N1 * ZONE_N1) return;
+  const int iy = t / ZONE_N1, ix = t - iy * ZONE_N1;
+  const uint32_t wd = rs.zones.words1[t];
+  // defer to level 2 only where the atlas populated it (under ITS MIXED level-1 cell); otherwise the (possibly
+  // MIXED) word itself is the zone and the walk resolves it through the per-set grids
+  const bool parent_mixed = (rs.atlas[(iy >> 1) * ATLAS_N + (ix >> 1)] & ATLAS_ANY_MIXED) != 0;
+  uint16_t z = ZONE_MIXED;
+  if (!((wd & ATLAS_ANY_MIXED) && parent_mixed)) z = rs.zones.hash_zone[zone_find(rs.zones.hash_keys, wd)];
+  rs.zones.level1[t] = z;
+}
+
+__global__ void __launch_bounds__(256) zone_write2_kernel(const __grid_constant__ RegionSet rs) {
+  if (!*rs.dirty || !rs.zones.dyn->valid) return;
+  if (!(rs.atlas[blockIdx.x] & ATLAS_ANY_MIXED)) return;
+  constexpr int S = 1 << ATLAS_SUB_SHIFT;
+  const int cy = blockIdx.x / ATLAS_N, cx = blockIdx.x - cy * ATLAS_N;
+  const uint32_t* in = rs.atlas + ATLAS_N * ATLAS_N;
+  uint32_t last = ZONE_EMPTY;
+  uint16_t lz = 0;
+  for (int t = threadIdx.x; t < S * S; t += blockDim.x) {
+    const int iy = (cy << ATLAS_SUB_SHIFT) + t / S, ix = (cx << ATLAS_SUB_SHIFT) + (t & (S - 1));
+    const size_t at = static_cast<size_t>(iy) * ATLAS_N2 + ix;
+    const uint32_t wd = in[at];
+    if (wd != last) { lz = rs.zones.hash_zone[zone_find(rs.zones.hash_keys, wd)]; last = wd; }
+    rs.zones.level2[at] = lz;
+  }
+}
+
 // gpu_ray_tracing_pro_fullColor.py:158: rng_states[i] = 0x9E3779B9 * (i + 1) mod 2^32
 __global__ void seed_rng_kernel(uint32_t* __restrict__ states, int64_t n, int64_t first_index) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -315,11 +471,16 @@ __global__ void locate_grid_kernel(const __grid_constant__ RegionSet rs, int reg
                                    int via_atlas) {
   __shared__ Region reg;
   __shared__ Atlas atlas;
+  __shared__ ZoneAtlas zones;
   if (threadIdx.x == 0) {
     region_load(reg, rs.st[region], rs.dyn[region]);
     const AtlasDyn ad = *rs.atlas_dyn;
     atlas.x0 = ad.x0; atlas.y0 = ad.y0; atlas.inv_dx = ad.inv_dx; atlas.inv_dy = ad.inv_dy; atlas.words = rs.atlas;
     atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
+    const ZoneDyn zd = *rs.zones.dyn;
+    zones.x0 = zd.x0; zones.y0 = zd.y0; zones.inv_dx = zd.inv_dx; zones.inv_dy = zd.inv_dy;
+    zones.level1 = rs.zones.level1; zones.level2 = rs.zones.level2; zones.trans = rs.zones.trans;
+    zones.words = rs.zones.words; zones.outside_zone = zd.outside_zone; zones.valid = zd.valid;
   }
   __syncthreads();
   Counts cn;
@@ -327,7 +488,9 @@ __global__ void locate_grid_kernel(const __grid_constant__ RegionSet rs, int reg
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) {
     if (via_atlas) {
-      const uint32_t word = atlas_lookup(atlas, px[i], py[i]);
+      // via_atlas 1: the word atlas; 2: the zone grids (zone id -> word), as the production walk reads them
+      const uint32_t word = (via_atlas == 2 && zones.valid) ? __ldg(zones.words + zone_lookup(zones, px[i], py[i]))
+                                                            : atlas_lookup(atlas, px[i], py[i]);
       out[i] = (region == REG_FC || region == REG_OC)
                    ? atlas_hit<COUNT>(word, region == REG_FC ? ATLAS_SHIFT_FC : ATLAS_SHIFT_OC, reg, px[i], py[i], &cn)
                    : (atlas_inside<COUNT>(word, region == REG_IC ? ATLAS_SHIFT_IC : region == REG_R1 ? ATLAS_SHIFT_R1 : ATLAS_SHIFT_R2,
@@ -354,7 +517,16 @@ cudaError_t launch_region_build(const RegionSet& rs, bool force, cudaStream_t s)
   region_fine_kernel<<<dim3(max_coarse, NUM_REGIONS), 256, 0, s>>>(rs);
   region_atlas_kernel<<<(ATLAS_N * ATLAS_N + 127) / 128, 128, 0, s>>>(rs);
   region_atlas2_kernel<<<ATLAS_N * ATLAS_N, 256, 0, s>>>(rs);
-  return cudaGetLastError();
+  // the zone form of the atlas and the walk's transition table
+  zone_reset_kernel<<<(ZONE_SLOTS + 255) / 256, 256, 0, s>>>(rs);
+  zone_level1_kernel<<<(ZONE_N1 * ZONE_N1 + 127) / 128, 128, 0, s>>>(rs);
+  zone_collect2_kernel<<<ATLAS_N * ATLAS_N, 256, 0, s>>>(rs);
+  zone_number_kernel<<<1, 1024, 0, s>>>(rs);
+  zone_write1_kernel<<<(ZONE_N1 * ZONE_N1 + 127) / 128, 128, 0, s>>>(rs);
+  zone_write2_kernel<<<ATLAS_N * ATLAS_N, 256, 0, s>>>(rs);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return err;
+  return launch_zone_transitions(rs, rs.st[REG_FC].npoly, rs.st[REG_OC].npoly, s);
 }
 
 cudaError_t launch_seed_rng(uint32_t* states, int64_t n, int64_t first_index, cudaStream_t s) {

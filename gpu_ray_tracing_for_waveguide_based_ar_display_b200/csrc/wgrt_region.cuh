@@ -197,6 +197,28 @@ __device__ __forceinline__ uint32_t atlas_lookup(const Atlas& a, double x, doubl
   return word;
 }
 
+// zone atlas as the walk reads it (shared memory copy)
+struct alignas(16) ZoneAtlas {
+  double x0, y0, inv_dx, inv_dy;     // level-1 zone cells
+  const uint16_t* level1;
+  const uint16_t* level2;
+  const uint32_t* trans;
+  const uint32_t* words;
+  int outside_zone, valid;
+};
+__device__ __forceinline__ int zone_lookup(const ZoneAtlas& a, double x, double y) {
+  const double fx = (x - a.x0) * a.inv_dx, fy = (y - a.y0) * a.inv_dy;
+  const double lim = static_cast<double>(ZONE_N1);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return a.outside_zone;   // also NaN
+  int z = __ldg(a.level1 + static_cast<int>(fy) * ZONE_N1 + static_cast<int>(fx));
+  if (z == ZONE_MIXED) {
+    const double sub = static_cast<double>(1 << ZONE_SUB_SHIFT);
+    const int ix = min(static_cast<int>(fx * sub), ATLAS_N2 - 1), iy = min(static_cast<int>(fy * sub), ATLAS_N2 - 1);
+    z = __ldg(a.level2 + static_cast<size_t>(iy) * ATLAS_N2 + ix);
+  }
+  return z;
+}
+
 // single-ring sets (in-coupler, effective regions): inside?
 template <bool COUNT>
 __device__ __forceinline__ bool atlas_inside(uint32_t word, int shift, const Region& r, double x, double y, Counts* cn) {

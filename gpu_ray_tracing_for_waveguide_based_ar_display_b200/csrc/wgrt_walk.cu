@@ -143,6 +143,72 @@ constexpr unsigned long long kNeedPacked =
     need_bits(6, (1u << REG_IC) | (1u << REG_R1) | (1u << REG_FC)) |                    // becomes 0 or 2
     need_bits(7, (1u << REG_IC) | (1u << REG_R1));                                      // becomes 1 or ends
 
+// sinfo[state] for a design with nFC fold-coupler and nOC out-coupler slices: states 0 and 2 travel along the +1
+// in-coupled direction (gap pair 0), state 1 along the -1 direction (2), states 3 and 4 along the folded direction
+// (1), state 5 along the conjugate out-coupler direction (3)
+__host__ __device__ constexpr int sinfo_of(int state, int nFC, int nOC) {
+  return state == 0 ? make_sinfo(SI_REGION_NONE, 2, 0, 0, 0, 0)
+       : state == 1 ? make_sinfo(SI_REGION_NONE, 4, 0, 0, 0, 2)
+       : state == 2 ? make_sinfo(REG_FC, 6, 2, 0, 0, 0)                          // miss: bounce, 2 T[0]
+       : state == 3 ? make_sinfo(REG_FC, 6 + 2 * nFC, 2, 1, 1, 1)                // miss: eff_reg2 test, 2 T[1]
+       : state == 4 ? make_sinfo(REG_OC, 6 + 4 * nFC, 3, 0, 1, 1)                // miss: bounce, 2 T[1]
+       : state == 5 ? make_sinfo(REG_OC, 6 + 4 * nFC + 3 * nOC, 3, 2, 0, 3)      // miss: lost
+       : 0;
+}
+
+// What the loop head (GRTF:905-907 and the region tests of the state that follows) does with a ray of region
+// state `state` standing in a zone whose atlas word is `word` -- the walk's "go to the next grating" phase as a
+// pure function, tabulated per geometry as trans[state][zone] (wgrt_device.cuh: ZoneSet):
+//   bits 0-2  region state afterwards        bit 3   the ray is lost (left the effective region / the in-coupler on
+//   bit 4     it stands on a grating: bits 12-27 = first event-table row      the -1 order / state-5 miss)
+//   bits 5-6  else: free bounce along gap pair, bit 7 its doubled TIR phase
+//   bits 8-9  loop iterations consumed (2 when state 3 falls through to state 4, GRTF:1102-1104)
+//   bit 31    a field this state needs is MIXED in the word: resolve it first (word path)
+constexpr uint32_t ACT_LOST = 1u << 3, ACT_EVENT = 1u << 4, ACT_RESOLVE = 1u << 31;
+__host__ __device__ inline uint32_t mixed_fields(uint32_t word) {
+  return (((word >> ATLAS_SHIFT_IC) & 3u) == 2u ? 1u << REG_IC : 0u) | (((word >> ATLAS_SHIFT_R1) & 3u) == 2u ? 1u << REG_R1 : 0u) |
+         (((word >> ATLAS_SHIFT_R2) & 3u) == 2u ? 1u << REG_R2 : 0u) |
+         (((word >> ATLAS_SHIFT_FC) & 0xffu) == CELL_AMBIG ? 1u << REG_FC : 0u) |
+         (((word >> ATLAS_SHIFT_OC) & 0xffu) == CELL_AMBIG ? 1u << REG_OC : 0u);
+}
+__host__ __device__ inline uint32_t decode_transition(uint32_t word, int state, int nFC, int nOC) {
+  if (static_cast<uint32_t>(kNeedPacked >> (5 * state)) & 31u & mixed_fields(word)) return ACT_RESOLVE;
+  const bool in_ic = ((word >> ATLAS_SHIFT_IC) & 3u) == 1u;
+  const bool in_r1 = ((word >> ATLAS_SHIFT_R1) & 3u) == 1u;
+  const bool in_r2 = ((word >> ATLAS_SHIFT_R2) & 3u) == 1u;
+  const int fc = (word >> ATLAS_SHIFT_FC) & 0xff, oc = (word >> ATLAS_SHIFT_OC) & 0xff;
+  int st = state, inc = 0;
+  bool lost = false;
+  if (st == ST_PEND_FWD) st = in_ic ? 0 : 2;                  // GRTF:883-886
+  else if (st == ST_PEND_BACK) { st = 1; lost = !in_ic; }     // GRTF:899-902
+  if (!lost) { inc = 1; lost = !in_r1; }                      // GRTF:905-907
+  int sinfo = sinfo_of(st, nFC, nOC);
+  const int region = sinfo & SI_REGION_MASK;
+  int code = region == REG_FC ? fc : region == REG_OC ? oc : 0;
+  if (code == CELL_NONE && ((sinfo >> SI_MISS_SHIFT) & 3) == 1 && !in_r2 && !lost) {   // GRTF:1102-1104
+    st = 4; inc = 2;
+    sinfo = sinfo_of(4, nFC, nOC);
+    code = oc;
+  }
+  uint32_t act = static_cast<uint32_t>(st) | (static_cast<uint32_t>(inc) << 8);
+  if (lost) return act | ACT_LOST;
+  if (code != CELL_NONE)
+    return act | ACT_EVENT | (static_cast<uint32_t>(((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code) << 12);
+  if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) return act | ACT_LOST;                      // GRTF:1244-1246
+  return act | (static_cast<uint32_t>((sinfo >> SI_GAP_SHIFT) & 3) << 5) | (static_cast<uint32_t>((sinfo >> SI_PHASE_SHIFT) & 1) << 7);
+}
+
+// the word path of the loop head: used where the table says "resolve first" and when there is no table
+template <bool COUNT>
+__device__ __noinline__ uint32_t resolve_transition(const Atlas& atlas, const ZoneAtlas& zones, int z, int state,
+                                                    const Region* __restrict__ regions, double x, double y, int nFC, int nOC,
+                                                    Counts* cn) {
+  uint32_t word = z >= 0 ? __ldg(zones.words + z) : atlas_lookup(atlas, x, y);
+  if (word & ATLAS_ANY_MIXED)
+    word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * state)) & 31u, regions, x, y, cn);
+  return decode_transition(word, state, nFC, nOC);
+}
+
 struct alignas(16) CellConst {
   cplx ph1[4];      // e^{i T[k]}
   cplx ph2[4];      // e^{i 2 T[k]}
@@ -168,7 +234,8 @@ struct Queue {
 };
 
 struct alignas(16) WarpShared {
-  Atlas atlas;
+  Atlas atlas;      // word form (fallback when the design has more than ZONE_CAP zones)
+  ZoneAtlas zones;
   CellConst cc;
   Queue q;
 };
@@ -274,15 +341,7 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
   } else if (t == 24) {
     cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
   } else if (t == 25) {
-    // states 0 and 2 travel along the +1 in-coupled direction (gap pair 0), state 1 along the -1
-    // direction (2), states 3 and 4 along the folded direction (1), state 5 along the conjugate
-    // out-coupler direction (3)
-    cc.sinfo[0] = make_sinfo(SI_REGION_NONE, 2, 0, 0, 0, 0);
-    cc.sinfo[1] = make_sinfo(SI_REGION_NONE, 4, 0, 0, 0, 2);
-    cc.sinfo[2] = make_sinfo(REG_FC, 6, 2, 0, 0, 0);                         // miss: bounce, 2 T[0]
-    cc.sinfo[3] = make_sinfo(REG_FC, 6 + 2 * nFC, 2, 1, 1, 1);               // miss: eff_reg2 test, 2 T[1]
-    cc.sinfo[4] = make_sinfo(REG_OC, 6 + 4 * nFC, 3, 0, 1, 1);               // miss: bounce, 2 T[1]
-    cc.sinfo[5] = make_sinfo(REG_OC, 6 + 4 * nFC + 3 * nOC, 3, 2, 0, 3);     // miss: lost
+    for (int st = 0; st < 6; ++st) cc.sinfo[st] = sinfo_of(st, nFC, nOC);
     cc.sinfo[6] = 0;
     cc.sinfo[7] = 0;
   } else if (t == 26) {
@@ -372,9 +431,14 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
     sh.atlas.x0 = ad.x0; sh.atlas.y0 = ad.y0; sh.atlas.inv_dx = ad.inv_dx; sh.atlas.inv_dy = ad.inv_dy;
     sh.atlas.words = rs.atlas;
     sh.atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
+    const ZoneDyn zd = *rs.zones.dyn;
+    sh.zones.x0 = zd.x0; sh.zones.y0 = zd.y0; sh.zones.inv_dx = zd.inv_dx; sh.zones.inv_dy = zd.inv_dy;
+    sh.zones.level1 = rs.zones.level1; sh.zones.level2 = rs.zones.level2; sh.zones.trans = rs.zones.trans;
+    sh.zones.words = rs.zones.words; sh.zones.outside_zone = zd.outside_zone; sh.zones.valid = zd.valid;
   }
   __syncwarp();
   const CellConst& cc = sh.cc;
+  const int nFC_i = static_cast<int>(p.n_FC), nOC_i = static_cast<int>(p.n_OC);
   const int64_t tile_size = *tile_size_ptr;
   const int64_t num_tiles = (p.num_rays + tile_size - 1) / tile_size;
   const double threshold = p.threshold;
@@ -654,52 +718,39 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         }
         __syncwarp();
 
-        // ---- phase A: go to the next grating.  Every lane whose ray moved asks the atlas once. ----
+        // ---- phase A: go to the next grating.  Every lane whose ray moved looks up its zone and the
+        //      transition table entry of (region state, zone): one L1-resident 16-bit id (a second, finer
+        //      level under MIXED cells) and one 32-bit word say what the loop head does with the ray. ----
         if (r.state != ST_DEAD && r.row0 < 0) {
-          uint32_t word = atlas_lookup(sh.atlas, r.x, r.y);
-          if (word & ATLAS_ANY_MIXED) word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * r.state)) & 31u, static_cast<const Region*>(rs.regions), r.x, r.y, &cn);
-          const bool in_ic = ((word >> ATLAS_SHIFT_IC) & 3u) == 1u;
-          const bool in_r1 = ((word >> ATLAS_SHIFT_R1) & 3u) == 1u;
-          const bool in_r2 = ((word >> ATLAS_SHIFT_R2) & 3u) == 1u;
-          const int fc = (word >> ATLAS_SHIFT_FC) & 0xff, oc = (word >> ATLAS_SHIFT_OC) & 0xff;
-          int st = r.state;
-          if (st == ST_PEND_FWD) st = in_ic ? 0 : 2;
-          else if (st == ST_PEND_BACK) { st = 1; lost = !in_ic; }
-          if (!lost) {
-            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
-            lost = ++r.iter > 100000 || !in_r1;
+          uint32_t act = ACT_RESOLVE;
+          int z = -1;
+          if (sh.zones.valid) {
+            z = zone_lookup(sh.zones, r.x, r.y);
+            WGRT_CHECK(z >= 0 && z < ZONE_CAP && r.state >= 0 && r.state < ZONE_STATES);
+            act = __ldg(sh.zones.trans + r.state * ZONE_CAP + z);
           }
-          WGRT_CHECK(st >= 0 && st < 6);
-          int sinfo = cc.sinfo[st];
-          int region = sinfo & SI_REGION_MASK;
-          int code = region == REG_FC ? fc : region == REG_OC ? oc : 0;
-          if (code == CELL_NONE && ((sinfo >> SI_MISS_SHIFT) & 3) == 1 && !in_r2 && !lost) {
-            st = 4;
-            if (COUNT) cn.c[WGRT_CNT_ITERS]++;
-            lost = ++r.iter > 100000;
-            sinfo = cc.sinfo[4];
-            code = oc;
-          }
-          r.state = st;
+          // rare: a field this state needs is MIXED in the zone (per-set grids / literal edges decide), or the
+          // design has too many zones for the table (word atlas + decode on the fly)
+          if (act & ACT_RESOLVE)
+            act = resolve_transition<COUNT>(sh.atlas, sh.zones, z, r.state, static_cast<const Region*>(rs.regions), r.x, r.y, nFC_i, nOC_i, &cn);
+          const int inc = (act >> 8) & 3;
+          if (COUNT) cn.c[WGRT_CNT_ITERS] += (inc == 2 && r.iter + 1 > 100000) ? 1 : inc;
+          r.iter += inc;
+          lost = (act & ACT_LOST) != 0 || r.iter > 100000;   // GRTF:905: at most 100000 iterations
+          r.state = static_cast<int>(act & 7u);
           if (!lost) {
-            if (code != CELL_NONE) {
-              r.row0 = ((sinfo >> SI_ROWBASE_SHIFT) & SI_ROWBASE_MASK) + ((sinfo >> SI_STRIDE_SHIFT) & 3) * code;
+            if (act & ACT_EVENT) {
+              r.row0 = static_cast<int>((act >> 12) & 0xffffu);
               WGRT_CHECK(r.row0 >= 2 && r.row0 + 1 < rows);
-              if (WGRT_VARIANT & 2) {   // the order applied next step is row0, row0 + 1 (or + 2): bring their lines into L1
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(jones + r.row0 * JROW));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(jones + (r.row0 + 2) * JROW - 1));
-              }
-            } else if (((sinfo >> SI_MISS_SHIFT) & 3) == 2) {
-              lost = true;                       // GRTF:1244-1246
             } else {
-              const int g = (sinfo >> SI_GAP_SHIFT) & 3;
+              const int g = (act >> 5) & 3;
               r.x += cc.gap[2 * g];
               r.y += cc.gap[2 * g + 1];
-              r.tm = cmul(r.tm, cc.ph2[(sinfo >> SI_PHASE_SHIFT) & 1]);
+              r.tm = cmul(r.tm, cc.ph2[(act >> 7) & 1]);
               if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
             }
-          }
-          if (lost) {
+          } else {
+            WGRT_CHECK(r.idx >= 0 && t_begin + r.idx < t_end);
             st_stream(p.rng_states + t_begin + r.idx, r.rng);
             r.state = ST_DEAD;
           }
@@ -769,6 +820,23 @@ cudaError_t launch_debug_deposit_inside(const double* rect, const double* px, co
                                         int literal, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   deposit_inside_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, s>>>(rect, px, py, n, out, literal);
+  return cudaGetLastError();
+}
+
+namespace {
+__global__ void zone_trans_kernel(const __grid_constant__ RegionSet rs, int nFC, int nOC) {
+  if (!*rs.dirty) return;
+  const ZoneDyn zd = *rs.zones.dyn;
+  if (!zd.valid) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ZONE_STATES * zd.num_zones) return;
+  const int st = t / zd.num_zones, z = t - st * zd.num_zones;
+  rs.zones.trans[st * ZONE_CAP + z] = decode_transition(rs.zones.words[z], st, nFC, nOC);
+}
+}  // namespace
+
+cudaError_t launch_zone_transitions(const RegionSet& rs, int n_FC, int n_OC, cudaStream_t s) {
+  zone_trans_kernel<<<(ZONE_STATES * ZONE_CAP + 255) / 256, 256, 0, s>>>(rs, n_FC, n_OC);
   return cudaGetLastError();
 }
 

@@ -249,7 +249,8 @@ int wgrt_counters_reset(void);
 
 /* is_inside_or_on_edge over a set of rings (GPU_ray_tracing_functions.py:36-71): out[i] = index
  * of the first ring containing point i, or -1.  mode 0 = literal scan, mode 1 = cell-grid index
- * + exact row-masked fallback (the fast path's classifier). */
+ * + exact row-masked fallback, mode 2 = through the word atlas, mode 3 = through the zone grids (what the
+ * production walk reads). */
 int wgrt_debug_locate(const double* verts, int64_t n_verts, const int64_t* offsets, int64_t n_polys,
                       const double* px, const double* py, int64_t n_points, int32_t* out, int mode);
 

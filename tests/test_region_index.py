@@ -56,6 +56,9 @@ def test_grid_index_equals_literal_scan(design, oracle):
         atlas = locate(verts, off, pts[:, 0], pts[:, 1], 2)     # the warp walk's path: atlas word, then the grids
         bad = np.flatnonzero(atlas != want)
         assert bad.size == 0, f"{name}: atlas differs at {pts[bad[:5]]} got {atlas[bad[:5]]} want {want[bad[:5]]}"
+        zone = locate(verts, off, pts[:, 0], pts[:, 1], 3)      # the production walk's path: zone id -> word, then the grids
+        bad = np.flatnonzero(zone != want)
+        assert bad.size == 0, f"{name}: zone grids differ at {pts[bad[:5]]} got {zone[bad[:5]]} want {want[bad[:5]]}"
         assert (want >= 0).sum() > 1000 and (want < 0).sum() > 1000
 
 
@@ -72,4 +75,22 @@ def test_grid_index_odd_ring_sets(oracle):
     want = oracle.locate(verts, off, pts[:, 0], pts[:, 1])
     assert np.array_equal(locate(verts, off, pts[:, 0], pts[:, 1], 1), want)
     assert np.array_equal(locate(verts, off, pts[:, 0], pts[:, 1], 2), want)
+    assert np.array_equal(locate(verts, off, pts[:, 0], pts[:, 1], 3), want)
     assert set(np.unique(want)) >= {-1, 0, 2, 3}
+
+
+def test_many_slices_overflow_the_zone_table(oracle):
+    """A ring set with 250 slices in a checkerboard has more distinct atlas words than the zone table holds
+    entries for the finer cells; whatever form the index takes, lookups must equal the literal scan."""
+    n = 250
+    xs = np.arange(n) % 25
+    ys = np.arange(n) // 25
+    sq = np.array([[0.0, 0.0], [0.9, 0.0], [0.9, 0.9], [0.0, 0.9]])
+    verts = np.concatenate([sq + np.array([x, y], dtype=np.float64) for x, y in zip(xs, ys)])
+    off = np.arange(0, 4 * n + 1, 4)
+    rs = np.random.default_rng(11)
+    pts = adversarial_points(verts, rs, 50000)
+    want = oracle.locate(verts, off, pts[:, 0], pts[:, 1])
+    for mode in (1, 2, 3):
+        assert np.array_equal(locate(verts, off, pts[:, 0], pts[:, 1], mode), want), mode
+    assert len(np.unique(want)) == n + 1
