@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-partitioned", action="store_true", help="skip the partitioned config-3 sub-record")
+    ap.add_argument("--no-legacy", action="store_true", help="skip the legacy energy-splitting tracer sub-record")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the bounded baseline sample")
     return ap.parse_args()
 
@@ -784,12 +785,46 @@ def main():
         line["cpu_baseline"] = {"value": c1["bounces"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": desc, "seconds": dt, "rays_per_s": c1["rays"] / dt}
 
+    if rank == 0 and world == 1 and not args.no_legacy:
+        line["legacy_split_tracer"] = legacy_record(args)
     if rank == 0 and world == 1:
         line["reference_cudasim"] = reference_cudasim_record()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def legacy_record(args):
+    """the legacy deterministic energy-splitting tracer (GRTF:192-417 + the compaction
+    kernel GRTF:178-190) as a whole job -- generation after generation on the device, SoA queues, ballot / prefix-sum
+    compaction -- against the CPU oracle restatement of the same kernels (one host thread, the same job)."""
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import legacy, synthetic_inputs as si
+    from oracle import oracle
+    oracle.build()
+    nx, ny, npts, gens, cap = 24, 18, 64, 6, 1 << 21
+    scene = si.make_scene(nx, ny, 2, seed=9, build_rays=False)
+    geom, luts = legacy.make_legacy_luts(scene, 1, seed=4)
+    pts = si.points_in_disc(scene.geom["IC"], npts, 10)
+    rows0 = legacy.initial_rows(pts, nx, ny)
+    kw = dict(max_steps=300, max_generations=gens, capacity=cap)
+    legacy.trace(rows0, geom, luts, **kw)                       # warm-up (index build, arena)
+    t0 = time.perf_counter()
+    EB, live, st = legacy.trace(rows0, geom, luts, **kw)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    EB_o, live_o, st_o = oracle.legacy_trace(rows0, geom, luts, **kw)
+    dt_o = time.perf_counter() - t0
+    return {"job": f"{nx}x{ny} FoV cells x {npts} start points x TE/TM = {len(rows0)} initial rows, {gens} generations, "
+                   "single wavelength, synthetic 3-order tables",
+            "rows_processed": st["rows_processed"], "children": st["children"], "children_dropped": st["children_dropped"],
+            "max_live_rows": st["max_live_rows"], "generations": st["generations"],
+            "wall_ms": dt * 1e3, "rows_per_s": st["rows_processed"] / dt,
+            "cpu_oracle": {"wall_ms": dt_o * 1e3, "rows_per_s": st_o["rows_processed"] / dt_o, "threads": 1},
+            "counts_equal_to_oracle": st == st_o,
+            "deposited_energy": float(EB.sum(dtype=np.float64)),
+            "bins_max_rel_diff_to_oracle": float(np.max(np.abs(EB - EB_o) / np.maximum(np.abs(EB_o), 1e-30))) if EB_o.any() else 0.0,
+            "api": "legacy.trace -> wgrt_legacy_trace_host (host arrays in and out, all generations on the device)"}
 
 
 def reference_cudasim_record():

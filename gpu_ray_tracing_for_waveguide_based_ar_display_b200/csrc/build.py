@@ -21,11 +21,10 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = {
     "wgrt_strict.cu": ["-fmad=false"],
     "wgrt_legacy.cu": ["-fmad=false"],
-    "wgrt_index.cu": [],
+    "wgrt_index.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_ZONE_REFINE",) if k in os.environ],
     "wgrt_eval.cu": [],
-    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WARP_CTAS_PER_SM", "WGRT_STREAM_CTAS_PER_SM", "WGRT_STAGE_BLOCK",
-                                                        "WGRT_STAGE_BLOCKS", "WGRT_VARIANT") if k in os.environ],
-    "wgrt_api.cu": [],
+    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_WARP_CTAS_PER_SM", "WGRT_QUEUE_CAP", "WGRT_ZONE_REFINE") if k in os.environ],
+    "wgrt_api.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_ZONE_REFINE",) if k in os.environ],
 }
 HEADERS = ["wgrt_device.cuh", "wgrt_region.cuh", os.path.join("..", "..", "include", "wgrt.h")]
 

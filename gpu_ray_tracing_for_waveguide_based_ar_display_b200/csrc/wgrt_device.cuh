@@ -209,8 +209,12 @@ constexpr int ATLAS_N2 = ATLAS_N << ATLAS_SUB_SHIFT;    // 4096 x 4096 words = 6
 // event row or free-bounce vector / phase.  The table is produced by running the walk's own decode function
 // on every (state, zone word) pair, so the two cannot disagree; entries whose state needs a MIXED field are
 // flagged and take the word path (zone word -> atlas_resolve -> decode).
-constexpr int ZONE_N1 = 128;                       // level 1: 128 x 128 uint16 = 32 KB
-constexpr int ZONE_SUB_SHIFT = 5;                  // level 2: 32 x 32 per level-1 cell = the 4096 x 4096 level-2 grid of the atlas
+#ifndef WGRT_ZONE_REFINE
+#define WGRT_ZONE_REFINE 1                         // level-1 zone cells per atlas level-1 cell and axis: 2^refine
+#endif
+constexpr int ZONE_REFINE = WGRT_ZONE_REFINE;
+constexpr int ZONE_N1 = ATLAS_N << ZONE_REFINE;    // level 1: 128 x 128 uint16 = 32 KB (refine 1), 64 x 64 = 8 KB (refine 0)
+constexpr int ZONE_SUB_SHIFT = ATLAS_SUB_SHIFT - ZONE_REFINE;   // level 2 = the 4096 x 4096 level-2 grid of the atlas
 constexpr int ZONE_CAP = 4096;                     // distinct zones supported (hash slots 2 x that)
 constexpr uint16_t ZONE_MIXED = 0xFFFFu;           // level-1 marker: ask level 2
 constexpr int ZONE_STATES = 8;                     // region states 0..5 and the two pending states

@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(1024) zone_number_kernel(const __grid_constant
     atlas_bbox(rs, xmin, ymin, w, h);
     ZoneDyn d;
     d.x0 = xmin; d.y0 = ymin;
-    d.inv_dx = 2.0 * (1.0 / w); d.inv_dy = 2.0 * (1.0 / h);   // exactly twice the atlas' level-1 scale: the same level-2 cell
-    static_assert(ZONE_N1 == 2 * ATLAS_N && ZONE_SUB_SHIFT + 1 == ATLAS_SUB_SHIFT, "zone grid = atlas grid refined once");
+    // a power of two times the atlas' level-1 scale (exact): a point maps to the same level-2 cell in both forms
+    d.inv_dx = static_cast<double>(1 << ZONE_REFINE) * (1.0 / w); d.inv_dy = static_cast<double>(1 << ZONE_REFINE) * (1.0 / h);
     d.num_zones = total;
     d.valid = total <= ZONE_CAP ? 1 : 0;
     const int so = zone_find(keys, ATLAS_OUTSIDE);
@@ -436,7 +436,7 @@ __global__ void zone_write1_kernel(const __grid_constant__ RegionSet rs) {
   const uint32_t wd = rs.zones.words1[t];
   // defer to level 2 only where the atlas populated it (under ITS MIXED level-1 cell); otherwise the (possibly
   // MIXED) word itself is the zone and the walk resolves it through the per-set grids
-  const bool parent_mixed = (rs.atlas[(iy >> 1) * ATLAS_N + (ix >> 1)] & ATLAS_ANY_MIXED) != 0;
+  const bool parent_mixed = (rs.atlas[(iy >> ZONE_REFINE) * ATLAS_N + (ix >> ZONE_REFINE)] & ATLAS_ANY_MIXED) != 0;
   uint16_t z = ZONE_MIXED;
   if (!((wd & ATLAS_ANY_MIXED) && parent_mixed)) z = rs.zones.hash_zone[zone_find(rs.zones.hash_keys, wd)];
   rs.zones.level1[t] = z;

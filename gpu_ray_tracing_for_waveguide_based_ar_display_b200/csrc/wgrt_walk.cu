@@ -44,16 +44,16 @@ namespace wgrt {
 
 namespace {
 
-// Per-cell event table.  Shared memory holds, per (event, order) row, what EVERY event evaluation
-// reads: the quadratic form of the order's efficiency, 1 / cos of the new direction and the meta
-// word (7 doubles, an odd stride: rows of different lanes spread over the banks).  The order's Jones
-// matrix (8 doubles) is read once per event, for the chosen order only, and lives in a per-warp
-// global scratch (L1 / L2 resident): keeping it out of shared memory halves the footprint of a warp
-// and lets 32 single-warp CTAs run per SM -- the walk is latency bound, warps are what hides it.
-constexpr int ROW = 7;
+// Per-cell event table.  Shared memory holds, per (event, order) row, what EVERY event evaluation reads: the
+// quadratic form of the order's efficiency and 1 / cos of the new direction (5 doubles, an odd stride: rows of
+// different lanes spread over the banks); the 11-bit meta word of a row lives in a 16-bit array behind the table.
+// The order's Jones matrix (8 doubles) is read once per event, for the chosen order only, and lives in a per-warp
+// global scratch (L1 / L2 resident).  Shared memory and L1 share the SM's 256 KB, and this walk lives on L1 hits
+// (atlas levels, Jones rows, polygon data): every byte kept out of shared memory is L1 (see launch_walk_warp for
+// the measured carve-out).
+constexpr int ROW = 5;
 constexpr int R_Q = 0;             // [0..3] quadratic form of the order's efficiency (cos factor folded in)
 constexpr int R_INVCOS = 4;        // 1 / cos(theta_new)
-constexpr int R_META = 5;          // bit field, see below
 constexpr int JROW = 8;            // doubles per Jones row in the scratch
 constexpr int ST_DEAD = -1, ST_PEND_FWD = 6, ST_PEND_BACK = 7;
 // |u - cumulative efficiency| below this: the ray is re-walked literally (see the file header)
@@ -61,11 +61,6 @@ constexpr double TIE_TOL_DEFAULT = 1e-10;
 double g_tie_tol = TIE_TOL_DEFAULT;   // wgrt_debug_set_tie_tolerance (tests widen it to exercise the redo path)
 // Resident single-warp CTAs per SM the kernel is compiled for.  Measured on C2: 32 (64 registers, a few
 // spills) 11.14 ms, 28 (72 registers, no spills) 10.8 ms, 24 (80 registers) 11.1 ms.
-// experiment switches (build.py passes -DWGRT_VARIANT=<bits>): 1 = no near-tie detection (measurement only: parity
-// is then "a few ulp from the threshold"), 2 = L1 prefetch of the next event's Jones rows at the end of phase A
-#ifndef WGRT_VARIANT
-#define WGRT_VARIANT 0
-#endif
 #ifndef WGRT_WARP_CTAS_PER_SM
 #define WGRT_WARP_CTAS_PER_SM 28
 #endif
@@ -225,7 +220,10 @@ struct alignas(16) CellConst {
 // Rays whose in-coupling draw picked an order wait here (a per-warp stack) for a free lane: the raw
 // ray as loaded, its index, its RNG state after the draw, the order (bit 31 of idx) and the order's
 // efficiency; the lane that pops an entry applies the order in phase B.
-constexpr int QUEUE_CAP = 48;
+#ifndef WGRT_QUEUE_CAP
+#define WGRT_QUEUE_CAP 36
+#endif
+constexpr int QUEUE_CAP = WGRT_QUEUE_CAP;
 struct Queue {
   double esel[QUEUE_CAP];
   uint32_t idx[QUEUE_CAP];
@@ -268,7 +266,7 @@ __device__ __forceinline__ void eyebox_box(const double* __restrict__ r, CellCon
 
 // Event table and per-cell constants of cell (lm, m, n); the 32 lanes of the warp share the rows.
 __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m, int64_t n, double* tab,
-                                  double* __restrict__ jones, CellConst& cc, int rows, int lane) {
+                                  unsigned short* meta_tab, double* __restrict__ jones, CellConst& cc, int rows, int lane) {
   const int64_t cell = (lm * p.X + m) * p.Y + n;
   const int64_t cpp = p.L * p.X * p.Y;
   const int nFC = static_cast<int>(p.n_FC), nOC = static_cast<int>(p.n_OC);
@@ -321,8 +319,7 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     int meta = (sp.tir & 3) | ((sp.gap & 3) << 2) | ((nstate & 7) << 4) | ((sp.post & 3) << 7);
     if (ev >= EV_S4) meta |= META_THREE;
     if (ev >= EV_S2) meta |= META_GATED;
-    row[R_META] = __longlong_as_double(static_cast<long long>(meta));
-    row[6] = 0.0;
+    meta_tab[t] = static_cast<unsigned short>(meta);
   }
   const int t = lane;
   if (t < 4) {
@@ -420,6 +417,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
   WarpShared& sh = *reinterpret_cast<WarpShared*>(smem_raw);
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   double* tab = reinterpret_cast<double*>(smem_raw + table_offset());
+  unsigned short* meta_tab = reinterpret_cast<unsigned short*>(tab + rows * ROW);
   const int lane = threadIdx.x;
   const unsigned lt_mask = (1u << lane) - 1u;
   Counts cn;
@@ -457,6 +455,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       // ---- the run of rays that share the cell of ray `cursor` ---------------------------------
       float km, kn, kl;
       int64_t run_limit;
+      const int64_t run_first = cursor;
       if (IMPLICIT) {
         const int64_t rpc = 2 * p.runner_points;
         const int64_t cell = p.runner_first_cell + cursor / rpc;  // runner order: x outer, y, lambda inner
@@ -467,20 +466,13 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       } else {
         km = __ldg(p.m + cursor); kn = __ldg(p.n + cursor); kl = has_l ? __ldg(p.lmd_num + cursor) : 0.0f;
         run_limit = t_end;   // cut on the fly where the key changes
-        // A NaN key never compares equal, not even to itself: such a ray forms a run of its own (exactly one
-        // ray is consumed, so the cursor always advances) and is left untouched, like every ray whose cell
-        // indices are outside the tables.  (Checked once per run, not per ray.)
-        if (!(km == km && kn == kn && kl == kl)) {
-          run_limit = cursor + 1;
-          km = kn = kl = -1.0f;   // (an out-of-range key: the run is invalid; lane 0's compare below is skipped)
-        }
       }
       const int64_t m = static_cast<int64_t>(km), n = static_cast<int64_t>(kn), lm = static_cast<int64_t>(kl);
       // (a non-finite key converts to an arbitrary integer; such rays are left untouched)
-      const bool valid = m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;   // (+-inf converts out of range)
-      const bool nan_run = !IMPLICIT && run_limit == cursor + 1 && km < 0.0f;
+      // (+-inf converts out of range; NaN converts to 0, hence the explicit test)
+      const bool valid = km == km && kn == kn && kl == kl && m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
       __syncwarp();
-      if (valid) build_cell_tables(p, lm, m, n, tab, jones, sh.cc, rows, lane);
+      if (valid) build_cell_tables(p, lm, m, n, tab, meta_tab, jones, sh.cc, rows, lane);
       __syncwarp();
 
       Ray r;
@@ -509,7 +501,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
               fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
             } else {
-              same = nan_run || (ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl));
+              same = ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl);
               fx = ld_stream(p.x + i); fy = ld_stream(p.y + i);
               fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i); fdl = ld_stream(p.delta_phase + i);
             }
@@ -546,7 +538,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double g = cc.inv_cos_in;
             const double e1 = (tab[R_Q] * t2 + tab[R_Q + 1] * m2 + (tab[R_Q + 2] * zre + tab[R_Q + 3] * zim)) * g;
             const double e2 = (tab[ROW + R_Q] * t2 + tab[ROW + R_Q + 1] * m2 + (tab[ROW + R_Q + 2] * zre + tab[ROW + R_Q + 3] * zim)) * g;
-            if (!(WGRT_VARIANT & 1) && (fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
+            if ((fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
               // near tie: left untouched for the literal re-walk
             } else if (u <= e1) { k = 0; esel = e1; }          // GRTF:871: no energy gate here
             else if (u <= e1 + e2) { k = 1; esel = e2; }       // GRTF:887
@@ -562,7 +554,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             sh.q.x[slot] = fx; sh.q.y[slot] = fy; sh.q.te[slot] = fte; sh.q.tm[slot] = ftm; sh.q.dl[slot] = fdl;
           }
           qn += __popc(surv);
-          cursor += cnt;
+          // (A NaN cell key never compares equal, not even to itself: the run of such a ray would be empty and the
+          // cursor would never advance.  The ray is outside every table: skip it, untouched.)
+          cursor += (cnt == 0 && cursor == run_first) ? 1 : cnt;
           __syncwarp();
         }
 
@@ -612,7 +606,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           if (r.iter >= 0) {
             WGRT_CHECK(r.row0 >= 0 && r.row0 + 1 < rows && t_begin + r.idx < t_end);
             const double* e = tab + r.row0 * ROW;
-            const int meta0 = static_cast<int>(__double_as_longlong(e[R_META]));
+            const int meta0 = meta_tab[r.row0];
             const bool three = (meta0 & META_THREE) != 0;
             const bool gated = (meta0 & META_GATED) != 0;
             const double u = xorshift_draw(r.rng, p.ray_index_base + t_begin + r.idx);
@@ -639,9 +633,8 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const bool ok3 = three && u <= e12 + e3v && r.ener * e3v > threshold;
             k = ok1 ? 0 : ok2 ? 1 : ok3 ? 2 : -1;
             esel = ok1 ? e1 : ok2 ? e2 : e3v;
-            bool tie = !(WGRT_VARIANT & 1) &&
-                       (fabs(u - e1) < TIE_TOL || fabs(u - e12) < TIE_TOL || (three && fabs(u - (e12 + e3v)) < TIE_TOL));
-            if (!(WGRT_VARIANT & 1) && threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
+            bool tie = fabs(u - e1) < TIE_TOL || fabs(u - e12) < TIE_TOL || (three && fabs(u - (e12 + e3v)) < TIE_TOL);
+            if (threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
               const double rt = 1e-9 * threshold;
               tie = tie || fabs(r.ener * e1 - threshold) < rt || fabs(r.ener * e2 - threshold) < rt ||
                     (three && fabs(r.ener * e3v - threshold) < rt);
@@ -665,7 +658,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           } else {
             WGRT_CHECK(r.row0 >= 0 && r.row0 + k < rows && k <= 2);
             const double* row = tab + (r.row0 + k) * ROW;
-            const int meta = static_cast<int>(__double_as_longlong(row[R_META]));
+            const int meta = meta_tab[r.row0 + k];
             const int post = (meta >> 7) & 3;
             if (post == POST_DEPOSIT) {
               // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
@@ -869,15 +862,21 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
   const bool implicit = p.runner_points > 0;
-  const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double);
+  const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double) +
+                      ((static_cast<size_t>(rows) * sizeof(unsigned short) + 15) & ~size_t(15));
   auto kern = count ? (implicit ? walk_warp_kernel<true, true> : walk_warp_kernel<true, false>)
                     : (implicit ? walk_warp_kernel<false, true> : walk_warp_kernel<false, false>);
   cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  if (const char* e = getenv("WGRT_SMEM_CARVEOUT")) {   // experiment: percent of the 228 KB given to shared memory
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));
-    if (err != cudaSuccess) return err;
-  }
+  // Shared memory against L1 (they share the SM's 256 KB): measured on C2 with 4.75 KB per single-warp CTA, the walk
+  // is fastest with ~60 % of the carve-out range given to shared memory -- 23 resident warps and ~119 KB of L1 beat 28
+  // warps with ~92 KB (72 %: +4 %) or ~60 KB (86 %: +11 %); 50 % (19 warps) loses 15 %.  WGRT_SMEM_CARVEOUT=<percent>
+  // overrides.
+  int carve = 60;
+  if (const char* e = getenv("WGRT_SMEM_CARVEOUT"))
+    if (*e) carve = atoi(e);
+  err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  if (err != cudaSuccess) return err;
   int per_sm = 0;
   err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
   if (err != cudaSuccess) return err;
