@@ -1,12 +1,13 @@
 """Regenerate the round's judged profile summaries under profiles/ from the scratch files in gpurun_out/.
 
-    python tools/make_profiles.py <bench.json> <launches.csv> <walk.ncu-rep>
+    python tools/make_profiles.py <bench.json> <launches.csv> <walk.ncu-rep> [round tag, default r2]
 """
 import collections, csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 bench, launches, rep = sys.argv[1:4]
+TAG = sys.argv[4] if len(sys.argv) > 4 else "r2"
 line = json.loads(open(bench).read().strip().splitlines()[-1])
-with open(os.path.join(ROOT, "profiles", "r1_bench_final.json"), "w") as f:
+with open(os.path.join(ROOT, "profiles", f"{TAG}_bench_final.json"), "w") as f:
     f.write(json.dumps(line) + "\n")
 rows = [r for r in csv.reader(open(launches)) if len(r) > 10 and r[0].isdigit()]
 agg = collections.OrderedDict()
@@ -16,23 +17,25 @@ for r in rows:
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[-1])
     each[name].append(float(r[-1]))
 tot = sum(a[1] for a in agg.values())
-out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-reference-gpu",
+out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-reference-gpu --no-partitioned --no-legacy",
        "(per-launch times under ncu are serialised and cold-cache; what must agree with bench.py is the SHARE of the step.",
-       " One step of bench.py = 9 launches: region_hash, bbox, rowmask, coarse, fine, atlas, atlas2 (all no-ops after the first),",
-       " pick_tile_warp, walk_warp<0,0>.  walk_strict<1> / walk_warp<1,0> / fma_peak are the counter replay and the roofline probes, outside the timed region.)",
+       " One step of bench.py = 17 launches: region_hash, bbox, rowmask, coarse, fine, atlas, atlas2, zone_reset, zone_level1, zone_collect2,",
+       " zone_number, zone_write1, zone_write2, zone_trans (all no-ops after the first launch of a geometry), pick_tile_warp, walk_warp<0,0>,",
+       " walk_redo (the near-tie rays; usually none).  walk_strict<1> / walk_warp<1,0> / fma_peak are the counter replay and the roofline",
+       " probes, outside the timed region.)",
        f"{'kernel':45s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'avg ms':>9s}"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k[:45]:45s} {n:8d} {t / 1e6:10.3f} {t / tot * 100:6.2f}% {t / n / 1e6:9.4f}")
 import statistics
-step = sum(statistics.median(each[k]) for k in each if k.startswith(("region_", "pick_tile")))
+step = sum(statistics.median(each[k]) for k in each if k.startswith(("region_", "zone_", "pick_tile", "walk_redo")))
 walk = statistics.median(each["walk_warp_kernel<0, 0>"])
-first = sum(each[k][0] for k in each if k.startswith("region_"))
+first = sum(each[k][0] for k in each if k.startswith(("region_", "zone_")))
 out.append(f"per step (median launch of each kernel): walk_warp {walk / 1e6:.3f} ms of {(walk + step) / 1e6:.3f} ms = "
            f"{walk / (walk + step) * 100:.2f} % (bench.py: {line['ms_per_step']:.2f} ms per step); "
            f"the region index + atlas build of the FIRST launch of a geometry: {first / 1e6:.2f} ms")
-open(os.path.join(ROOT, "profiles", "r1_launch_shares_final.txt"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "profiles", f"{TAG}_launch_shares_final.txt"), "w").write("\n".join(out) + "\n")
 import shutil
-shutil.copy(launches, os.path.join(ROOT, "profiles", "r1_launches_final_bench_steps2.csv"))
+shutil.copy(launches, os.path.join(ROOT, "profiles", f"{TAG}_launches_final_bench_steps2.csv"))
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(io.StringIO(raw))); d = dict(zip(rr[0], rr[2]))
 g = lambda k: float(d[k].replace(",", ""))
@@ -56,5 +59,5 @@ hdr = ("ncu --set full --clock-control none --import-source on -k regex:walk_war
 der = (f"\nDerived: DRAM {(rd + wr) / 1e9:.2f} GB / {ms:.2f} ms = {(rd + wr) / ms / 1e6:.0f} GB/s = {(rd + wr) / ms / 1e6 / 6549.1 * 100:.1f} % of the measured 6549 GB/s copy peak;\n"
        f"FP64 pipe {traffic['fp64_pipe_pct']:.0f} % of peak, issue slots {traffic['issue_active_pct']:.0f} % busy, {traffic['threads_per_warp_inst']:.1f} of 32 lanes per warp "
        f"instruction, {traffic['warps_active_pct'] * 0.64:.0f} of 64 warp slots.\n\n")
-open(os.path.join(ROOT, "profiles", "r1_walk_warp_ncu_summary.txt"), "w").write(hdr + s1 + der + s2)
+open(os.path.join(ROOT, "profiles", f"{TAG}_walk_warp_ncu_summary.txt"), "w").write(hdr + s1 + der + s2)
 print(out[-1]); print(der)
