@@ -16,11 +16,11 @@
 //    instead of a Jones application per order in a divergent if-chain) and pick the order exactly as
 //    the reference's if/elif chain does; after a __syncwarp() ONE copy of the order application runs
 //    for all of them and for the lanes that just popped a survivor -- one Jones matrix, the chosen
-//    one.  Phase A ("go to the next grating"): every lane whose ray moved asks the ATLAS
-//    (wgrt_region.cuh) -- one L1-resident word answers in-coupler / effective region 1 / 2 / fold
-//    slice / out-coupler slice at once -- resolves what an in-coupler order left pending, and either
-//    stands on a grating, is lost, or free-bounces (GRTF:1049-1052, 1102-1108, 1175-1178) and asks
-//    again in the next step.
+//    one.  Phase A ("go to the next grating"): every lane whose ray moved looks up its ZONE (wgrt_device.cuh:
+//    one L1-resident 16-bit id per cell names the combination of in-coupler / effective region 1 / 2 / fold
+//    slice / out-coupler slice answers there) and the TRANSITION-TABLE entry of (region state, zone): next
+//    state, lost, the event's first table row, or the free bounce (GRTF:1049-1052, 1102-1108, 1175-1178) after
+//    which it asks again in the next step.
 //  * The polarisation state is the un-normalised complex Jones vector (te, tm) plus s = 1/|v|^2.
 //    E_field_cal's cos / sin / hypot / atan2 / wrap (GRTF:136-150) and the per-event normalisation
 //    (GRTF:876-877 ff.) disappear: efficiencies are v^H M v * s with M = J^H J precomputed per cell
@@ -359,6 +359,11 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
 __device__ __forceinline__ void st_stream(uint32_t* ptr, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
+__device__ __forceinline__ double2 ld_keep(const double2* ptr) {   // L1 evict-last: rows the warp will read again
+  double2 v;
+  asm volatile("ld.global.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
+  return v;
+}
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
@@ -670,7 +675,11 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             } else {
               // apply the chosen order's Jones matrix (GRTF:139-144)
               const double2* jr = reinterpret_cast<const double2*>(jones + (r.row0 + k) * JROW);
+#ifdef WGRT_JONES_EVICT_LAST
+              const double2 j0 = ld_keep(jr), j1 = ld_keep(jr + 1), j2 = ld_keep(jr + 2), j3 = ld_keep(jr + 3);
+#else
               const double2 j0 = jr[0], j1 = jr[1], j2 = jr[2], j3 = jr[3];
+#endif
               const cplx L0{j0.x, j0.y}, L1{j1.x, j1.y}, L2{j2.x, j2.y}, L3{j3.x, j3.y};
               cplx nte{L0.re * r.te.re - L0.im * r.te.im + (L2.re * r.tm.re - L2.im * r.tm.im),
                        L0.re * r.te.im + L0.im * r.te.re + (L2.re * r.tm.im + L2.im * r.tm.re)};
