@@ -785,6 +785,8 @@ def main():
         line["cpu_baseline"] = {"value": c1["bounces"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": desc, "seconds": dt, "rays_per_s": c1["rays"] / dt}
 
+    if rank == 0 and world == 1:
+        line["small_launch"] = small_launch_record(stream)
     if rank == 0 and world == 1 and not args.no_legacy:
         line["legacy_split_tracer"] = legacy_record(args)
     if rank == 0 and world == 1:
@@ -793,6 +795,41 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_launch_record(stream):
+    """Per-launch overhead: BASELINE configs[0] (532 nm, 5 x 5 FoV cells, 64 rays per cell = 1600
+    rays) device resident through the reference-shaped kernel object, 200 launches back to back -- host time per call
+    (argument packing in Python + the C ABI + 17 kernel launches, 14 of them no-ops of the cached region index) and device
+    time per launch."""
+    import torch
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import GPU_ray_tracing_functions as GRTF
+    from gpu_ray_tracing_for_waveguide_based_ar_display_b200 import synthetic_inputs as si
+    scene = si.make_scene(5, 5, 64, seed=11, lmd_subset=[1])
+
+    def to_dev(a):
+        if not isinstance(a, np.ndarray):
+            return a
+        v = a.view(np.float64) if a.dtype == np.complex128 else a
+        return GRTF._TorchAlias(torch.from_numpy(np.ascontiguousarray(v.view(np.int32) if v.dtype == np.uint32 else v)).cuda(),
+                                a.shape, a.dtype)
+    dev = [to_dev(a) for a in scene.kernel_args(scene.new_matrix_EB())]
+    launch = GRTF.process_rays_kernel_pro_fullColor[(scene.rays.num_rays + 255) // 256, 256, stream]
+    for _ in range(20):
+        launch(*dev)
+    torch.cuda.synchronize()
+    n = 200
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        launch(*dev)
+    host = time.perf_counter() - t0
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return {"rays": scene.rays.num_rays, "launches": n, "host_us_per_call": host / n * 1e6,
+            "device_us_per_launch": e0.elapsed_time(e1) / n * 1e3,
+            "note": "device time is bounded below by the host rate when the host is the slower side"}
 
 
 def legacy_record(args):

@@ -359,11 +359,6 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
 __device__ __forceinline__ void st_stream(uint32_t* ptr, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
-__device__ __forceinline__ double2 ld_keep(const double2* ptr) {   // L1 evict-last: rows the warp will read again
-  double2 v;
-  asm volatile("ld.global.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(ptr));
-  return v;
-}
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
@@ -675,11 +670,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             } else {
               // apply the chosen order's Jones matrix (GRTF:139-144)
               const double2* jr = reinterpret_cast<const double2*>(jones + (r.row0 + k) * JROW);
-#ifdef WGRT_JONES_EVICT_LAST
-              const double2 j0 = ld_keep(jr), j1 = ld_keep(jr + 1), j2 = ld_keep(jr + 2), j3 = ld_keep(jr + 3);
-#else
               const double2 j0 = jr[0], j1 = jr[1], j2 = jr[2], j3 = jr[3];
-#endif
               const cplx L0{j0.x, j0.y}, L1{j1.x, j1.y}, L2{j2.x, j2.y}, L3{j3.x, j3.y};
               cplx nte{L0.re * r.te.re - L0.im * r.te.im + (L2.re * r.tm.re - L2.im * r.tm.im),
                        L0.re * r.te.im + L0.im * r.te.re + (L2.re * r.tm.im + L2.im * r.tm.re)};
@@ -875,21 +866,35 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
                       ((static_cast<size_t>(rows) * sizeof(unsigned short) + 15) & ~size_t(15));
   auto kern = count ? (implicit ? walk_warp_kernel<true, true> : walk_warp_kernel<true, false>)
                     : (implicit ? walk_warp_kernel<false, true> : walk_warp_kernel<false, false>);
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  if (err != cudaSuccess) return err;
-  // Shared memory against L1 (they share the SM's 256 KB): measured on C2 with 4.75 KB per single-warp CTA, the walk
-  // is fastest with ~60 % of the carve-out range given to shared memory -- 23 resident warps and ~119 KB of L1 beat 28
-  // warps with ~92 KB (72 %: +4 %) or ~60 KB (86 %: +11 %); 50 % (19 warps) loses 15 %.  WGRT_SMEM_CARVEOUT=<percent>
-  // overrides.
-  int carve = 60;
-  if (const char* e = getenv("WGRT_SMEM_CARVEOUT"))
-    if (*e) carve = atoi(e);
-  err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+  // Function attributes and the occupancy query cost tens of microseconds per call: done once per (device, kernel
+  // variant, table size) -- a launch of a small problem (a pipeline chunk, BASELINE config 1) is otherwise dominated by them.
+  struct Setup { const void* kern; size_t smem; int device, per_sm; };
+  static Setup cache[16];
+  static int cached = 0;
+  int device = 0;
+  cudaError_t err = cudaGetDevice(&device);
   if (err != cudaSuccess) return err;
   int per_sm = 0;
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
-  if (err != cudaSuccess) return err;
-  if (per_sm < 1) per_sm = 1;
+  for (int i = 0; i < cached; ++i)
+    if (cache[i].kern == reinterpret_cast<const void*>(kern) && cache[i].smem == smem && cache[i].device == device) per_sm = cache[i].per_sm;
+  if (per_sm == 0) {
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    // Shared memory against L1 (they share the SM's 256 KB): measured on C2 with 4.75 KB per single-warp CTA, the walk
+    // is fastest with ~60 % of the carve-out range given to shared memory -- 24 resident warps and ~119 KB of L1 beat 28
+    // warps with ~92 KB (72 %: +4 %) or ~60 KB (86 %: +11 %); 50 % (19 warps) loses 15 %.  WGRT_SMEM_CARVEOUT=<percent>
+    // overrides (read once).
+    int carve = 60;
+    if (const char* e = getenv("WGRT_SMEM_CARVEOUT"))
+      if (*e) carve = atoi(e);
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    if (err != cudaSuccess) return err;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    cache[cached % 16] = Setup{reinterpret_cast<const void*>(kern), smem, device, per_sm};
+    if (cached < 16) ++cached;
+  }
   static int cap = -1;
   if (cap < 0) {
     const char* e = getenv("WGRT_WARPS_PER_SM");
