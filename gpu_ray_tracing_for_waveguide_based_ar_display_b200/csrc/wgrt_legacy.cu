@@ -3,7 +3,8 @@
 // process_rays_kernel (GRTF:192-417): one thread advances one ray row to its next fold-coupler split (the
 // zero order stays in the row, the diffracted order is appended as a new row) or to its end; in the
 // out-coupler zone every hit deposits the out-coupled energy |E|^2 into the eyebox bin.  Restated here with
-//  * the exact-equivalent region index of wgrt_region.cuh instead of the reference's edge scans,
+//  * the exact-equivalent region index of wgrt_region.cuh (one atlas word per position) instead of the reference's
+//    edge scans,
 //  * child rows claimed with warp-aggregated atomics (one atomic per warp and split site),
 //  * ray queues in SoA form ([13][capacity]: every column read and written coalesced) for the generation
 //    loop of wgrt_legacy_trace_host, and in the reference's AoS form ([N][13]) for the drop-in launch,
@@ -61,8 +62,17 @@ __device__ __forceinline__ int64_t claim_row(int32_t* counter) {
 
 template <bool SOA>
 __global__ void __launch_bounds__(128) legacy_step_kernel(const __grid_constant__ wgrt_legacy_problem_t p,
-                                                          const Region* __restrict__ regions,
+                                                          const __grid_constant__ RegionSet rs,
                                                           unsigned long long* __restrict__ dropped) {
+  const Region* __restrict__ regions = static_cast<const Region*>(rs.regions);
+  __shared__ Atlas atlas;
+  if (threadIdx.x == 0) {
+    const AtlasDyn ad = *rs.atlas_dyn;
+    atlas.x0 = ad.x0; atlas.y0 = ad.y0; atlas.inv_dx = ad.inv_dx; atlas.inv_dy = ad.inv_dy;
+    atlas.words = rs.atlas;
+    atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
+  }
+  __syncthreads();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= p.useful_count_in) return;
   const Row<SOA> v{p.vectors, p.capacity, idx};
@@ -77,7 +87,16 @@ __global__ void __launch_bounds__(128) legacy_step_kernel(const __grid_constant_
   const int32_t Ci = p.C_ic, Cf = p.C_fc, Co = p.C_oc;
   double te, tm, d2;
 
-  auto inside = [&](int reg) { return region_locate<false>(regions[reg], x, y, nullptr) >= 0; };
+  // all five region answers for the ray's position from one atlas word (two levels; fields still MIXED there go
+  // to the per-set grids / the literal edge expressions): the same exact-equivalent index the Monte-Carlo walk uses
+  auto look = [&](unsigned need) {
+    uint32_t w = atlas_lookup(atlas, x, y);
+    if (w & ATLAS_ANY_MIXED) w = atlas_resolve<false>(w, need, regions, x, y, nullptr);
+    return w;
+  };
+  auto in_set = [](uint32_t w, int shift) { return ((w >> shift) & 3u) == 1u; };
+  auto slice_of = [](uint32_t w, int shift) { const int c = (w >> shift) & 0xff; return c == CELL_NONE ? -1 : c; };
+  constexpr unsigned N_IC = 1u << REG_IC, N_R1 = 1u << REG_R1, N_R2 = 1u << REG_R2, N_FC = 1u << REG_FC, N_OC = 1u << REG_OC;
   // the diffracted order of a fold-coupler split goes to a new row (GRTF:264-281, 317-333, 351-366)
   auto child = [&](const double* lut, int64_t e, int c0, int c1, int c2, int c3, int tir, int g0, const double* dirlut,
                    double st) {
@@ -103,8 +122,9 @@ __global__ void __launch_bounds__(128) legacy_step_kernel(const __grid_constant_
 
   if (state == 1.0) {   // GRTF:235-286
     for (int64_t it = 0; it < p.max_steps; ++it) {
-      if (!inside(REG_IC)) {
-        const int i = region_locate<false>(regions[REG_FC], x, y, nullptr);
+      const uint32_t w = look(N_IC | N_FC);
+      if (!in_set(w, ATLAS_SHIFT_IC)) {
+        const int i = slice_of(w, ATLAS_SHIFT_FC);
         if (i >= 0) {
           const int64_t e = static_cast<int64_t>(i) * cpp + cell;
           jones(p.lut_fc1, e, Cf, 3, 6, 15, 18, Ete, Etm, dl, te, tm, d2);
@@ -125,9 +145,10 @@ __global__ void __launch_bounds__(128) legacy_step_kernel(const __grid_constant_
   }
 
   if (state == 2.0 || state == 3.0) {   // GRTF:288-377
-    if (!inside(REG_R1)) { v.set(12, 0.0); return; }
+    if (!in_set(look(N_R1), ATLAS_SHIFT_R1)) { v.set(12, 0.0); return; }
     for (int64_t it = 0; it < p.max_steps; ++it) {
-      const int i = region_locate<false>(regions[REG_FC], x, y, nullptr);
+      const uint32_t w = look(N_FC | N_R2);
+      const int i = slice_of(w, ATLAS_SHIFT_FC);
       if (i >= 0) {
         const int64_t e = static_cast<int64_t>(i) * cpp + cell;
         if (state == 2.0) {
@@ -141,7 +162,7 @@ __global__ void __launch_bounds__(128) legacy_step_kernel(const __grid_constant_
         }
         return;
       }
-      if (!inside(REG_R2)) {
+      if (!in_set(w, ATLAS_SHIFT_R2)) {
         if (state == 3.0) { state = 4.0; break; }
         v.set(12, 0.0);
         return;
@@ -155,8 +176,9 @@ __global__ void __launch_bounds__(128) legacy_step_kernel(const __grid_constant_
     const double* rect = p.eff_reg_FOV + 8 * cell;
     const double* rg = p.eff_reg_FOV_range + 4 * cell;
     for (int64_t it = 0; it < p.max_steps; ++it) {
-      if (!inside(REG_R1)) { v.set(12, 0.0); return; }
-      const int i = region_locate<false>(regions[REG_OC], x, y, nullptr);
+      const uint32_t w = look(N_R1 | N_OC);
+      if (!in_set(w, ATLAS_SHIFT_R1)) { v.set(12, 0.0); return; }
+      const int i = slice_of(w, ATLAS_SHIFT_OC);
       if (i >= 0) {
         const int64_t e = static_cast<int64_t>(i) * cpp + cell;
         if (inside_or_on_edge_literal<false>(x, y, rect, 0, 4, nullptr)) {
@@ -223,9 +245,8 @@ cudaError_t launch_legacy_step(const wgrt_legacy_problem_t& p, const RegionSet& 
                                cudaStream_t s) {
   if (p.useful_count_in <= 0) return cudaSuccess;
   const unsigned blocks = static_cast<unsigned>((p.useful_count_in + 127) / 128);
-  const Region* regions = static_cast<const Region*>(rs.regions);
-  if (soa) legacy_step_kernel<true><<<blocks, 128, 0, s>>>(p, regions, dropped);
-  else legacy_step_kernel<false><<<blocks, 128, 0, s>>>(p, regions, dropped);
+  if (soa) legacy_step_kernel<true><<<blocks, 128, 0, s>>>(p, rs, dropped);
+  else legacy_step_kernel<false><<<blocks, 128, 0, s>>>(p, rs, dropped);
   return cudaGetLastError();
 }
 

@@ -880,11 +880,18 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   if (per_sm == 0) {
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    // Shared memory against L1 (they share the SM's 256 KB): measured on C2 with 4.75 KB per single-warp CTA, the walk
-    // is fastest with ~60 % of the carve-out range given to shared memory -- 24 resident warps and ~119 KB of L1 beat 28
-    // warps with ~92 KB (72 %: +4 %) or ~60 KB (86 %: +11 %); 50 % (19 warps) loses 15 %.  WGRT_SMEM_CARVEOUT=<percent>
-    // overrides (read once).
-    int carve = 60;
+    // Shared memory against L1 (they share the SM's 256 KB, and the split comes in steps: 100 / 132 / 164 / 196 /
+    // 228 KB of shared memory).  This walk lives on L1 hits, so it takes the SMALLEST step that still holds 22 single-warp
+    // CTAs (each costs its bytes + 1 KB of system reserve).  Measured on C2 (4.75 KB per CTA): 132 KB = 23 CTAs, 124 KB
+    // of L1: 8.8 ms; 164 KB = 28 CTAs, 92 KB: 9.15 ms; >= 196 KB = 28 CTAs, <= 60 KB: 9.7 ms; 100 KB = 17 CTAs: 10.1 ms.
+    // WGRT_SMEM_CARVEOUT=<percent> overrides (read once per kernel variant and table size).
+    int carve = 100;
+    {
+      const size_t per_cta = smem + 1024;
+      const int steps_kb[5] = {100, 132, 164, 196, 228};
+      for (int k = 0; k < 5; ++k)
+        if (static_cast<size_t>(steps_kb[k]) * 1024 / per_cta >= 22) { carve = (steps_kb[k] * 100 + 227) / 228; break; }
+    }
     if (const char* e = getenv("WGRT_SMEM_CARVEOUT"))
       if (*e) carve = atoi(e);
     err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
