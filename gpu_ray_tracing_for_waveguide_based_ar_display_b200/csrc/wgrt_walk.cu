@@ -35,6 +35,7 @@
 //    number is reported (WGRT_CNT_NEAR_TIE).
 //  * Everything state dependent is table driven from shared memory (per-cell event rows, sinfo).
 #include <climits>
+#include <cstdio>
 #include <cstring>
 
 #define WGRT_CHECK_TU 1   // this translation unit carries the bounds assertions of the checked build
@@ -44,17 +45,18 @@ namespace wgrt {
 
 namespace {
 
-// Per-cell event table.  Shared memory holds, per (event, order) row, what EVERY event evaluation reads: the
-// quadratic form of the order's efficiency and 1 / cos of the new direction (5 doubles, an odd stride: rows of
-// different lanes spread over the banks); the 11-bit meta word of a row lives in a 16-bit array behind the table.
-// The order's Jones matrix (8 doubles) is read once per event, for the chosen order only, and lives in a per-warp
-// global scratch (L1 / L2 resident).  Shared memory and L1 share the SM's 256 KB, and this walk lives on L1 hits
-// (atlas levels, Jones rows, polygon data): every byte kept out of shared memory is L1 (see launch_walk_warp for
-// the measured carve-out).
-constexpr int ROW = 5;
+// Per-cell event table, one row per (event, order), in the warp's slice of shared memory.  A row is what an event
+// evaluation reads, laid out for 128-bit shared loads: [Q0 Q1 | Q2 Q3 | 1/cos, meta] -- the quadratic form of the
+// order's efficiency, 1 / cos of the new direction and the row's meta word (in the low half of the sixth double).
+// The row stride of 12 words puts 8 consecutive rows on disjoint 4-bank groups.  The order's Jones matrix (8 doubles,
+// read for the chosen order only; deposit orders have none) lives behind the table in the JSM layout -- 64-byte rows
+// whose four 16-byte chunks are XOR-swizzled by the row pair, so that 8 consecutive rows are conflict free as well --
+// and in a per-warp global scratch (L1 / L2 resident) otherwise.
+constexpr int ROW = 6;
 constexpr int R_Q = 0;             // [0..3] quadratic form of the order's efficiency (cos factor folded in)
 constexpr int R_INVCOS = 4;        // 1 / cos(theta_new)
-constexpr int JROW = 8;            // doubles per Jones row in the scratch
+constexpr int R_META = 5;          // meta word (integer in the low 32 bits)
+constexpr int JROW = 8;            // doubles per Jones row
 constexpr int ST_DEAD = -1, ST_PEND_FWD = 6, ST_PEND_BACK = 7;
 // |u - cumulative efficiency| below this: the ray is re-walked literally (see the file header)
 constexpr double TIE_TOL_DEFAULT = 1e-10;
@@ -109,6 +111,7 @@ __constant__ OrderSpec kOrders[NUM_EV][3] = {
 // FIRST row of an event additionally: bit 9 the event has three orders, bit 10 its branches carry
 // `and ener_k > threshold` (GRTF:1020 ff.; absent at GRTF:871-999)
 constexpr int META_THREE = 1 << 9, META_GATED = 1 << 10;
+constexpr int META_JROW_SHIFT = 12;   // bits 12-27: the row's Jones row in the JSM layout
 
 // sinfo[state]: which coupler decides the event, first row, rows per slice, what a miss means,
 // which doubled TIR phase / bounce vector a free bounce uses
@@ -193,15 +196,70 @@ __host__ __device__ inline uint32_t decode_transition(uint32_t word, int state, 
   return act | (static_cast<uint32_t>((sinfo >> SI_GAP_SHIFT) & 3) << 5) | (static_cast<uint32_t>((sinfo >> SI_PHASE_SHIFT) & 1) << 7);
 }
 
+// Per-launch descriptors of the region index, copied device-to-device from where the index builders left them
+// (RegionSet::atlas_dyn, ZoneSet::dyn) into constant memory right before the launch: every lane reads them at
+// every step, and constant-bank reads cost neither shared-memory wavefronts nor registers.
+struct WalkConst {
+  AtlasDyn atlas;
+  ZoneDyn zone;
+};
+__constant__ WalkConst c_walk;
+
+// Zone tables of the geometry in the CTA's shared memory (all warps of the SM read them at every step): the level-1
+// grid as 8-bit zone ids (designs with at most 254 zones; BASELINE's have ~40) and the transition table (at most
+// TRANS_SM zones).  Larger designs read the 16-bit grid / the table from global memory.
+constexpr int TRANS_SM = 128;
+constexpr int ZONE_SM_MAX = 254;
+constexpr uint8_t ZONE_MIXED8 = 0xFFu;
+struct alignas(16) CtaShared {
+  uint8_t level1[ZONE_N1 * ZONE_N1];
+  uint32_t trans[ZONE_STATES * TRANS_SM];
+};
+
 // the word path of the loop head: used where the table says "resolve first" and when there is no table
 template <bool COUNT>
-__device__ __noinline__ uint32_t resolve_transition(const Atlas& atlas, const ZoneAtlas& zones, int z, int state,
-                                                    const Region* __restrict__ regions, double x, double y, int nFC, int nOC,
-                                                    Counts* cn) {
-  uint32_t word = z >= 0 ? __ldg(zones.words + z) : atlas_lookup(atlas, x, y);
+__device__ __noinline__ uint32_t resolve_transition(const RegionSet& rs, int z, int state, double x, double y, int nFC,
+                                                    int nOC, Counts* cn) {
+  uint32_t word;
+  if (z >= 0) {
+    word = __ldg(rs.zones.words + z);
+  } else {
+    Atlas atlas;
+    atlas.x0 = c_walk.atlas.x0; atlas.y0 = c_walk.atlas.y0; atlas.inv_dx = c_walk.atlas.inv_dx; atlas.inv_dy = c_walk.atlas.inv_dy;
+    atlas.words = rs.atlas;
+    atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
+    word = atlas_lookup(atlas, x, y);
+  }
   if (word & ATLAS_ANY_MIXED)
-    word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * state)) & 31u, regions, x, y, cn);
+    word = atlas_resolve<COUNT>(word, static_cast<uint32_t>(kNeedPacked >> (5 * state)) & 31u,
+                                static_cast<const Region*>(rs.regions), x, y, cn);
   return decode_transition(word, state, nFC, nOC);
+}
+
+// zone of a point: level 1 from shared memory (SM) or global memory, level 2 (under MIXED level-1 cells) from
+// global memory
+template <bool SM>
+__device__ __forceinline__ int zone_lookup_walk(const uint8_t* __restrict__ level1_sm, const uint16_t* __restrict__ level1,
+                                                const uint16_t* __restrict__ level2, double x, double y) {
+  const double fx = (x - c_walk.zone.x0) * c_walk.zone.inv_dx, fy = (y - c_walk.zone.y0) * c_walk.zone.inv_dy;
+  const double lim = static_cast<double>(ZONE_N1);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return c_walk.zone.outside_zone;   // also NaN
+  const int cell = static_cast<int>(fy) * ZONE_N1 + static_cast<int>(fx);
+  int z;
+  bool mixed;
+  if (SM) {
+    z = level1_sm[cell];
+    mixed = z == ZONE_MIXED8;
+  } else {
+    z = __ldg(level1 + cell);
+    mixed = z == ZONE_MIXED;
+  }
+  if (mixed) {
+    const double sub = static_cast<double>(1 << ZONE_SUB_SHIFT);
+    const int ix = min(static_cast<int>(fx * sub), ATLAS_N2 - 1), iy = min(static_cast<int>(fy * sub), ATLAS_N2 - 1);
+    z = __ldg(level2 + static_cast<size_t>(iy) * ATLAS_N2 + ix);
+  }
+  return z;
 }
 
 struct alignas(16) CellConst {
@@ -212,9 +270,8 @@ struct alignas(16) CellConst {
   double range[4];  // eff_reg_FOV_range[m, n, :]
   double box[4];    // xmin, xmax, ymin, ymax of the eyebox rectangle when it is axis aligned
   double inv_cos_in;
-  int sinfo[8];
   int box_ok;       // rect is exactly the axis-aligned rectangle `box` in the runner's vertex order
-  int pad_[3];
+  int pad_;
 };
 
 // Rays whose in-coupling draw picked an order wait here (a per-warp stack) for a free lane: the raw
@@ -224,21 +281,28 @@ struct alignas(16) CellConst {
 #define WGRT_QUEUE_CAP 36
 #endif
 constexpr int QUEUE_CAP = WGRT_QUEUE_CAP;
-struct Queue {
-  double esel[QUEUE_CAP];
-  uint32_t idx[QUEUE_CAP];
-  uint32_t rng[QUEUE_CAP];
-  float x[QUEUE_CAP], y[QUEUE_CAP], te[QUEUE_CAP], tm[QUEUE_CAP], dl[QUEUE_CAP];
+struct alignas(16) QEntry {   // 32 bytes: two 128-bit shared accesses per push / pop
+  uint32_t idx, rng;
+  float x, y;
+  float te, tm, dl, pad_;
 };
 
-struct alignas(16) WarpShared {
-  Atlas atlas;      // word form (fallback when the design has more than ZONE_CAP zones)
-  ZoneAtlas zones;
+struct alignas(16) WarpShared {   // one per warp
   CellConst cc;
-  Queue q;
+  QEntry q[QUEUE_CAP];
 };
 
 __host__ __device__ constexpr size_t table_offset() { return (sizeof(WarpShared) + 15) & ~size_t(15); }
+// rows = 6 + 4 nFC + 6 nOC table rows, of which 2 nOC (the deposit orders) have no Jones matrix
+__host__ __device__ constexpr size_t warp_bytes(int rows, int jrows, bool jsm) {
+  return table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double) + (jsm ? static_cast<size_t>(jrows) * JROW * sizeof(double) : 0);
+}
+
+// Efficiency of an in-coupling order from its quadratic form.  Evaluated twice per surviving ray -- when the order
+// is drawn and when a lane pops the ray -- with explicit operations, so that both give the same bits.
+__device__ __forceinline__ double incouple_eff(double2 qa, double2 qb, double t2, double m2, double zre, double zim, double g) {
+  return __dmul_rn(__dadd_rn(__fma_rn(qa.x, t2, __dmul_rn(qa.y, m2)), __fma_rn(qb.x, zre, __dmul_rn(qb.y, zim))), g);
+}
 
 __device__ __forceinline__ const double* lut_slice(const wgrt_problem_t& p, int which, int i, int64_t cell,
                                                    int64_t cells_per_poly, int32_t& C) {
@@ -265,8 +329,10 @@ __device__ __forceinline__ void eyebox_box(const double* __restrict__ r, CellCon
 }
 
 // Event table and per-cell constants of cell (lm, m, n); the 32 lanes of the warp share the rows.
+template <bool JSM>
 __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m, int64_t n, double* tab,
-                                  unsigned short* meta_tab, double* __restrict__ jones, CellConst& cc, int rows, int lane) {
+                                  double* __restrict__ jones, CellConst& cc, int rows, int lane) {
+  double* jones_sm = tab + rows * ROW;
   const int64_t cell = (lm * p.X + m) * p.Y + n;
   const int64_t cpp = p.L * p.X * p.Y;
   const int nFC = static_cast<int>(p.n_FC), nOC = static_cast<int>(p.n_OC);
@@ -286,6 +352,9 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
       i = v / 3; k = v - 3 * i;
     }
     const OrderSpec sp = kOrders[ev][k];
+    // Jones row: table rows in order, the deposit orders (k = 2 of the out-coupler events) left out
+    const int oc_first = 6 + 4 * nFC;
+    const int jrow = t < oc_first ? t : (k == 2 ? -1 : oc_first + 2 * ((t - oc_first) / 3) + k);
     const int src = ev == EV_INIT ? DIR_IC1 : ev == EV_S0 ? DIR_IC2 : ev == EV_S1 ? DIR_IC3
                   : ev == EV_S2 ? DIR_FC1 : ev == EV_S3 ? DIR_FC2 : ev == EV_S4 ? DIR_OC1 : DIR_OC2;
     int32_t C;
@@ -296,7 +365,8 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     for (int q = 0; q < 4; ++q) {
       const double2 v = __ldg(reinterpret_cast<const double2*>(L) + sp.ch[q]);
       J[q] = cplx{v.x, v.y};
-      reinterpret_cast<double2*>(jones + t * JROW)[q] = v;
+      if (!JSM) reinterpret_cast<double2*>(jones + t * JROW)[q] = v;
+      else if (jrow >= 0) reinterpret_cast<double2*>(jones_sm + jrow * JROW)[q ^ ((jrow >> 1) & 3)] = v;
     }
     int32_t Cd;
     const double* D = lut_slice(p, sp.dir, i, cell, cpp, Cd);
@@ -319,7 +389,8 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     int meta = (sp.tir & 3) | ((sp.gap & 3) << 2) | ((nstate & 7) << 4) | ((sp.post & 3) << 7);
     if (ev >= EV_S4) meta |= META_THREE;
     if (ev >= EV_S2) meta |= META_GATED;
-    meta_tab[t] = static_cast<unsigned short>(meta);
+    if (jrow >= 0) meta |= jrow << META_JROW_SHIFT;
+    row[R_META] = __hiloint2double(0, meta);
   }
   const int t = lane;
   if (t < 4) {
@@ -337,10 +408,6 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     cc.range[t - 20] = __ldg(p.eff_reg_FOV_range + 4 * (m * p.Y + n) + (t - 20));
   } else if (t == 24) {
     cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
-  } else if (t == 25) {
-    for (int st = 0; st < 6; ++st) cc.sinfo[st] = sinfo_of(st, nFC, nOC);
-    cc.sinfo[6] = 0;
-    cc.sinfo[7] = 0;
   } else if (t == 26) {
     eyebox_box(p.eff_reg_FOV + 8 * (m * p.Y + n), cc);
   }
@@ -361,6 +428,9 @@ __device__ __forceinline__ void st_stream(uint32_t* ptr, uint32_t v) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
+__device__ __forceinline__ void prefetch_l1(const void* ptr) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 }
 
 // is_inside_or_on_edge_4d (GRTF:73-108) on the eyebox rectangle.  For an exactly axis-aligned
@@ -404,37 +474,65 @@ struct Ray {
   int state;        // region state 0..5, ST_PEND_* after an in-coupler order, ST_DEAD
   int iter;
   int idx;          // ray index relative to the start of the tile
-  int row0;         // >= 0: the ray stands on a grating, first table row of the event; < 0: ask the atlas
+  int row0;         // >= 0: the ray stands on a grating, first table row of the event; < 0: ask the zone tables
 };
 
-template <bool COUNT, bool IMPLICIT>
-__global__ void __launch_bounds__(32, WGRT_WARP_CTAS_PER_SM)
+// One persistent CTA per SM, WALK_WARPS(JSM) independent warps in it.  The warps share only the geometry's zone
+// tables (CtaShared); each walks its own tiles with its own cell table, survivor stack and Jones rows.
+#ifndef WGRT_JSM_WARPS
+#define WGRT_JSM_WARPS 24
+#endif
+__host__ __device__ constexpr int walk_max_warps(bool jsm) { return jsm ? WGRT_JSM_WARPS : 24; }
+
+template <bool COUNT, bool IMPLICIT, bool JSM>
+__global__ void __launch_bounds__(32 * walk_max_warps(JSM), 1)
 walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
                  int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
                  unsigned long long* counters, double* __restrict__ jones_scratch, RedoList* __restrict__ redo,
                  const double TIE_TOL) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpShared& sh = *reinterpret_cast<WarpShared*>(smem_raw);
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
-  double* tab = reinterpret_cast<double*>(smem_raw + table_offset());
-  unsigned short* meta_tab = reinterpret_cast<unsigned short*>(tab + rows * ROW);
-  const int lane = threadIdx.x;
+  const int jrows = rows - 2 * static_cast<int>(p.n_OC);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
+
+  // ---- the geometry's zone tables: once per CTA ---------------------------------------------------------------
+  const bool zone_ok = c_walk.zone.valid != 0;
+  const bool level1_sm = zone_ok && c_walk.zone.num_zones <= ZONE_SM_MAX;
+  const bool trans_sm = zone_ok && c_walk.zone.num_zones <= TRANS_SM;
+  CtaShared& cta = *reinterpret_cast<CtaShared*>(smem_raw);
+  if (level1_sm) {
+    const uint4* src = reinterpret_cast<const uint4*>(rs.zones.level1);
+    for (int i = threadIdx.x; i < ZONE_N1 * ZONE_N1 / 8; i += blockDim.x) {   // 8 ids per 128-bit load
+      const uint4 v = __ldg(src + i);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t out[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t a = w[2 * h], b = w[2 * h + 1];   // ids a.lo, a.hi, b.lo, b.hi; MIXED (0xFFFF) -> 0xFF
+        out[h] = (a & 0xffu) | (((a >> 16) & 0xffu) << 8) | ((b & 0xffu) << 16) | (((b >> 16) & 0xffu) << 24);
+      }
+      reinterpret_cast<uint2*>(cta.level1)[i] = make_uint2(out[0], out[1]);
+    }
+  }
+  if (trans_sm) {
+    const int nz = c_walk.zone.num_zones;
+    for (int i = threadIdx.x; i < ZONE_STATES * nz; i += blockDim.x) {
+      const int st = i / nz, z = i - st * nz;
+      cta.trans[st * TRANS_SM + z] = __ldg(rs.zones.trans + st * ZONE_CAP + z);
+    }
+  }
+  __syncthreads();   // the only block barrier: from here on the warps never meet again
+
+  unsigned char* wbase = smem_raw + sizeof(CtaShared) + static_cast<size_t>(warp) * warp_bytes(rows, jrows, JSM);
+  WarpShared& sh = *reinterpret_cast<WarpShared*>(wbase);
+  double* tab = reinterpret_cast<double*>(wbase + table_offset());
+  const double* jones_sm = tab + rows * ROW;
   Counts cn;
   if (COUNT) cn.clear();
 
-  double* jones = jones_scratch + static_cast<size_t>(blockIdx.x) * rows * JROW;
-  if (lane == 0) {
-    const AtlasDyn ad = *rs.atlas_dyn;
-    sh.atlas.x0 = ad.x0; sh.atlas.y0 = ad.y0; sh.atlas.inv_dx = ad.inv_dx; sh.atlas.inv_dy = ad.inv_dy;
-    sh.atlas.words = rs.atlas;
-    sh.atlas.words2 = rs.atlas + ATLAS_N * ATLAS_N;
-    const ZoneDyn zd = *rs.zones.dyn;
-    sh.zones.x0 = zd.x0; sh.zones.y0 = zd.y0; sh.zones.inv_dx = zd.inv_dx; sh.zones.inv_dy = zd.inv_dy;
-    sh.zones.level1 = rs.zones.level1; sh.zones.level2 = rs.zones.level2; sh.zones.trans = rs.zones.trans;
-    sh.zones.words = rs.zones.words; sh.zones.outside_zone = zd.outside_zone; sh.zones.valid = zd.valid;
-  }
-  __syncwarp();
+  const int warps = blockDim.x >> 5;
+  double* jones = JSM ? nullptr : jones_scratch + (static_cast<size_t>(blockIdx.x) * warps + warp) * rows * JROW;
   const CellConst& cc = sh.cc;
   const int nFC_i = static_cast<int>(p.n_FC), nOC_i = static_cast<int>(p.n_OC);
   const int64_t tile_size = *tile_size_ptr;
@@ -472,7 +570,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       // (+-inf converts out of range; NaN converts to 0, hence the explicit test)
       const bool valid = km == km && kn == kn && kl == kl && m >= 0 && m < p.X && n >= 0 && n < p.Y && lm >= 0 && lm < p.L;
       __syncwarp();
-      if (valid) build_cell_tables(p, lm, m, n, tab, meta_tab, jones, sh.cc, rows, lane);
+      if (valid) build_cell_tables<JSM>(p, lm, m, n, tab, jones, sh.cc, rows, lane);
       __syncwarp();
 
       Ray r;
@@ -500,12 +598,19 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               const int64_t pt = te_half ? kk : kk - p.runner_points;
               fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
               fte = te_half ? 1.0f : 0.0f; ftm = te_half ? 0.0f : 1.0f;
+              frng = ld_stream(p.rng_states + i);
             } else {
-              same = ld_stream(p.m + i) == km && ld_stream(p.n + i) == kn && (!has_l || ld_stream(p.lmd_num + i) == kl);
+              // (all loads first: a short-circuit chain of volatile loads would pay the memory latency three times)
+              const float vm = ld_stream(p.m + i), vn = ld_stream(p.n + i), vl = has_l ? ld_stream(p.lmd_num + i) : kl;
               fx = ld_stream(p.x + i); fy = ld_stream(p.y + i);
               fte = ld_stream(p.te + i); ftm = ld_stream(p.tm + i); fdl = ld_stream(p.delta_phase + i);
+              frng = ld_stream(p.rng_states + i);
+              same = vm == km && vn == kn && vl == kl;
             }
-            frng = ld_stream(p.rng_states + i);
+#ifndef WGRT_PF
+#define WGRT_PF 2
+#endif
+#if WGRT_PF == 0
             if (i + 64 < run_limit) {   // two batches ahead
               prefetch_l2(p.rng_states + i + 64);
               if (!IMPLICIT) {
@@ -515,12 +620,33 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
                 if (has_l) prefetch_l2(p.lmd_num + i + 64);
               }
             }
+#else
+            if (i + 32 < run_limit) {   // the next batch into L1 (translation included)
+              prefetch_l1(p.rng_states + i + 32);
+              if (!IMPLICIT) {
+                prefetch_l1(p.x + i + 32); prefetch_l1(p.y + i + 32);
+                prefetch_l1(p.te + i + 32); prefetch_l1(p.tm + i + 32); prefetch_l1(p.delta_phase + i + 32);
+                prefetch_l1(p.m + i + 32); prefetch_l1(p.n + i + 32);
+                if (has_l) prefetch_l1(p.lmd_num + i + 32);
+              }
+            }
+#if WGRT_PF == 1
+            if (i + 96 < run_limit) {
+              prefetch_l2(p.rng_states + i + 96);
+              if (!IMPLICIT) {
+                prefetch_l2(p.x + i + 96); prefetch_l2(p.y + i + 96);
+                prefetch_l2(p.te + i + 96); prefetch_l2(p.tm + i + 96); prefetch_l2(p.delta_phase + i + 96);
+                prefetch_l2(p.m + i + 96); prefetch_l2(p.n + i + 96);
+                if (has_l) prefetch_l2(p.lmd_num + i + 96);
+              }
+            }
+#endif
+#endif
           }
           const unsigned okmask = __ballot_sync(FULL_MASK, same);
           const int cnt = okmask == FULL_MASK ? 32 : __ffs(~okmask) - 1;   // leading rays of this run
           if (cnt < 32) open = false;
           int k = -1;
-          double esel = 0.0;
           if (lane < cnt && valid) {   // (rays of a run whose cell indices are out of range are left untouched)
             if (COUNT) {
               cn.c[WGRT_CNT_RAYS]++; cn.c[WGRT_CNT_DRAWS]++; cn.c[WGRT_CNT_DRAW2]++; cn.c[WGRT_CNT_EFIELD] += 2;
@@ -536,22 +662,24 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             // GRTF:860-869: the raw amplitudes enter E_field_cal as they are (s = 1)
             const double t2 = te * te, m2 = w.re * w.re + w.im * w.im, zre = te * w.re, zim = te * w.im;
             const double g = cc.inv_cos_in;
-            const double e1 = (tab[R_Q] * t2 + tab[R_Q + 1] * m2 + (tab[R_Q + 2] * zre + tab[R_Q + 3] * zim)) * g;
-            const double e2 = (tab[ROW + R_Q] * t2 + tab[ROW + R_Q + 1] * m2 + (tab[ROW + R_Q + 2] * zre + tab[ROW + R_Q + 3] * zim)) * g;
+            const double2* q = reinterpret_cast<const double2*>(tab);
+            const double2 a0 = q[0], a1 = q[1], b0 = q[ROW / 2], b1 = q[ROW / 2 + 1];
+            const double e1 = incouple_eff(a0, a1, t2, m2, zre, zim, g);
+            const double e2 = incouple_eff(b0, b1, t2, m2, zre, zim, g);
             if ((fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
               // near tie: left untouched for the literal re-walk
-            } else if (u <= e1) { k = 0; esel = e1; }          // GRTF:871: no energy gate here
-            else if (u <= e1 + e2) { k = 1; esel = e2; }       // GRTF:887
+            } else if (u <= e1) k = 0;                          // GRTF:871: no energy gate here
+            else if (u <= e1 + e2) k = 1;                       // GRTF:887
             else st_stream(p.rng_states + i, frng);            // GRTF:903-904: absorbed
           }
           const unsigned surv = __ballot_sync(FULL_MASK, k >= 0);
           if (k >= 0) {
             const int slot = qn + __popc(surv & lt_mask);
             WGRT_CHECK(slot >= 0 && slot < QUEUE_CAP && i >= t_begin && i < t_end);
-            sh.q.idx[slot] = static_cast<uint32_t>(i - t_begin) | (static_cast<uint32_t>(k) << 31);
-            sh.q.rng[slot] = frng;
-            sh.q.esel[slot] = esel;
-            sh.q.x[slot] = fx; sh.q.y[slot] = fy; sh.q.te[slot] = fte; sh.q.tm[slot] = ftm; sh.q.dl[slot] = fdl;
+            uint4* qe = reinterpret_cast<uint4*>(&sh.q[slot]);
+            const uint32_t idxk = static_cast<uint32_t>(i - t_begin) | (static_cast<uint32_t>(k) << 31);
+            qe[0] = make_uint4(idxk, frng, __float_as_uint(fx), __float_as_uint(fy));
+            qe[1] = make_uint4(__float_as_uint(fte), __float_as_uint(ftm), __float_as_uint(fdl), 0u);
           }
           qn += __popc(surv);
           // (A NaN cell key never compares equal, not even to itself: the run of such a ray would be empty and the
@@ -567,14 +695,14 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           if (r.state == ST_DEAD && rank < take) {
             const int slot = qn - 1 - rank;
             WGRT_CHECK(slot >= 0 && slot < QUEUE_CAP);
-            const uint32_t e = sh.q.idx[slot];
-            r.idx = static_cast<int>(e & 0x7fffffffu);
-            r.rng = sh.q.rng[slot];
-            r.ener = sh.q.esel[slot];        // ener = 1 * efficiency of the in-coupled order (GRTF:882)
-            r.x = static_cast<double>(sh.q.x[slot]);
-            r.y = static_cast<double>(sh.q.y[slot]);
-            const double te = static_cast<double>(sh.q.te[slot]), tm = static_cast<double>(sh.q.tm[slot]);
-            const float fdl = sh.q.dl[slot];
+            const uint4* qe = reinterpret_cast<const uint4*>(&sh.q[slot]);
+            const uint4 q0 = qe[0], q1 = qe[1];
+            const float fdl = __uint_as_float(q1.z);
+            r.idx = static_cast<int>(q0.x & 0x7fffffffu);
+            r.rng = q0.y;
+            r.x = static_cast<double>(__uint_as_float(q0.z));
+            r.y = static_cast<double>(__uint_as_float(q0.w));
+            const double te = static_cast<double>(__uint_as_float(q1.x)), tm = static_cast<double>(__uint_as_float(q1.y));
             r.te = cplx{te, 0.0};
             r.tm = cplx{tm, 0.0};
             if (fdl != 0.0f) {
@@ -582,11 +710,16 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               sincos(static_cast<double>(fdl), &sn, &cs);
               r.tm = cplx{tm * cs, tm * sn};
             }
+            r.row0 = static_cast<int>(q0.x >> 31);   // the chosen in-coupling row (0 or 1)
+            {   // ener = 1 * efficiency of the in-coupled order (GRTF:882), the very value the draw was compared with
+              const double2* q = reinterpret_cast<const double2*>(tab + r.row0 * ROW);
+              r.ener = incouple_eff(q[0], q[1], te * te, r.tm.re * r.tm.re + r.tm.im * r.tm.im, te * r.tm.re, te * r.tm.im,
+                                    cc.inv_cos_in);
+            }
             r.s = 1.0;
             r.inv_cos = cc.inv_cos_in;
             r.iter = -1;                     // marks "order already chosen"
             r.state = 0;
-            r.row0 = static_cast<int>(e >> 31);   // the chosen in-coupling row (0 or 1)
           }
           qn -= take;
           __syncwarp();
@@ -605,10 +738,15 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         if (at_event) {
           if (r.iter >= 0) {
             WGRT_CHECK(r.row0 >= 0 && r.row0 + 1 < rows && t_begin + r.idx < t_end);
-            const double* e = tab + r.row0 * ROW;
-            const int meta0 = meta_tab[r.row0];
+            const double2* e = reinterpret_cast<const double2*>(tab + r.row0 * ROW);
+            const double2 a0 = e[0], a1 = e[1], a2 = e[2];
+            const double2 b0 = e[ROW / 2], b1 = e[ROW / 2 + 1];
+            const int meta0 = __double2loint(a2.y);
             const bool three = (meta0 & META_THREE) != 0;
             const bool gated = (meta0 & META_GATED) != 0;
+            WGRT_CHECK(!three || r.row0 + 2 < rows);
+            double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
+            if (three) { c0 = e[ROW]; c1 = e[ROW + 1]; }
             const double u = xorshift_draw(r.rng, p.ray_index_base + t_begin + r.idx);
             if (COUNT) {
               cn.c[WGRT_CNT_DRAWS]++;
@@ -620,11 +758,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double zre = r.te.re * r.tm.re + r.te.im * r.tm.im;   // conj(te) * tm
             const double zim = r.te.re * r.tm.im - r.te.im * r.tm.re;
             const double g = r.s * r.inv_cos;
-            WGRT_CHECK(!three || r.row0 + 2 < rows);
-            const double* e3 = three ? e + 2 * ROW : e;                 // two-order events: never selected
-            const double e1 = (e[R_Q] * t2 + e[R_Q + 1] * m2 + (e[R_Q + 2] * zre + e[R_Q + 3] * zim)) * g;
-            const double e2 = (e[ROW + R_Q] * t2 + e[ROW + R_Q + 1] * m2 + (e[ROW + R_Q + 2] * zre + e[ROW + R_Q + 3] * zim)) * g;
-            const double e3v = (e3[R_Q] * t2 + e3[R_Q + 1] * m2 + (e3[R_Q + 2] * zre + e3[R_Q + 3] * zim)) * g;
+            const double e1 = (a0.x * t2 + a0.y * m2 + (a1.x * zre + a1.y * zim)) * g;
+            const double e2 = (b0.x * t2 + b0.y * m2 + (b1.x * zre + b1.y * zim)) * g;
+            const double e3v = (c0.x * t2 + c0.y * m2 + (c1.x * zre + c1.y * zim)) * g;   // two-order events: never selected
             // the reference's if / elif chain (GRTF:919-953, 1020-1048, 1135-1174)
             // (evaluated without branches: the three tests are cheap, a divergent chain is not)
             const double e12 = e1 + e2;
@@ -657,8 +793,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             }
           } else {
             WGRT_CHECK(r.row0 >= 0 && r.row0 + k < rows && k <= 2);
-            const double* row = tab + (r.row0 + k) * ROW;
-            const int meta = meta_tab[r.row0 + k];
+            const double2* row = reinterpret_cast<const double2*>(tab + (r.row0 + k) * ROW);
+            const double2 im = row[R_INVCOS / 2];   // {1 / cos, meta}
+            const int meta = __double2loint(im.y);
             const int post = (meta >> 7) & 3;
             if (post == POST_DEPOSIT) {
               // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
@@ -669,8 +806,10 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               lost = true;
             } else {
               // apply the chosen order's Jones matrix (GRTF:139-144)
-              const double2* jr = reinterpret_cast<const double2*>(jones + (r.row0 + k) * JROW);
-              const double2 j0 = jr[0], j1 = jr[1], j2 = jr[2], j3 = jr[3];
+              const int jrow = JSM ? (meta >> META_JROW_SHIFT) & 0xffff : r.row0 + k;
+              const int sw = JSM ? (jrow >> 1) & 3 : 0;
+              const double2* jr = reinterpret_cast<const double2*>((JSM ? jones_sm : jones) + jrow * JROW);
+              const double2 j0 = jr[sw], j1 = jr[1 ^ sw], j2 = jr[2 ^ sw], j3 = jr[3 ^ sw];
               const cplx L0{j0.x, j0.y}, L1{j1.x, j1.y}, L2{j2.x, j2.y}, L3{j3.x, j3.y};
               cplx nte{L0.re * r.te.re - L0.im * r.te.im + (L2.re * r.tm.re - L2.im * r.tm.im),
                        L0.re * r.te.im + L0.im * r.te.re + (L2.re * r.tm.im + L2.im * r.tm.re)};
@@ -695,7 +834,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               const int gp = (meta >> 2) & 3;
               r.x += cc.gap[2 * gp];
               r.y += cc.gap[2 * gp + 1];
-              r.inv_cos = row[R_INVCOS];
+              r.inv_cos = im.x;
               r.ener *= esel;
               r.state = (meta >> 4) & 7;   // region state, or "pending" after an in-coupler order
               if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
@@ -712,20 +851,21 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         __syncwarp();
 
         // ---- phase A: go to the next grating.  Every lane whose ray moved looks up its zone and the
-        //      transition table entry of (region state, zone): one L1-resident 16-bit id (a second, finer
-        //      level under MIXED cells) and one 32-bit word say what the loop head does with the ray. ----
+        //      transition table entry of (region state, zone): one 16-bit id from the CTA's shared copy of the
+        //      level-1 grid (a second, finer level in global memory under MIXED cells) and one 32-bit word say
+        //      what the loop head does with the ray. ----
         if (r.state != ST_DEAD && r.row0 < 0) {
           uint32_t act = ACT_RESOLVE;
           int z = -1;
-          if (sh.zones.valid) {
-            z = zone_lookup(sh.zones, r.x, r.y);
+          if (zone_ok) {
+            z = level1_sm ? zone_lookup_walk<true>(cta.level1, nullptr, rs.zones.level2, r.x, r.y)
+                          : zone_lookup_walk<false>(nullptr, rs.zones.level1, rs.zones.level2, r.x, r.y);
             WGRT_CHECK(z >= 0 && z < ZONE_CAP && r.state >= 0 && r.state < ZONE_STATES);
-            act = __ldg(sh.zones.trans + r.state * ZONE_CAP + z);
+            act = trans_sm ? cta.trans[r.state * TRANS_SM + z] : __ldg(rs.zones.trans + r.state * ZONE_CAP + z);
           }
           // rare: a field this state needs is MIXED in the zone (per-set grids / literal edges decide), or the
           // design has too many zones for the table (word atlas + decode on the fly)
-          if (act & ACT_RESOLVE)
-            act = resolve_transition<COUNT>(sh.atlas, sh.zones, z, r.state, static_cast<const Region*>(rs.regions), r.x, r.y, nFC_i, nOC_i, &cn);
+          if (act & ACT_RESOLVE) act = resolve_transition<COUNT>(rs, z, r.state, r.x, r.y, nFC_i, nOC_i, &cn);
           const int inc = (act >> 8) & 3;
           if (COUNT) cn.c[WGRT_CNT_ITERS] += (inc == 2 && r.iter + 1 > 100000) ? 1 : inc;
           r.iter += inc;
@@ -851,8 +991,15 @@ void set_tie_tolerance(double tol) { g_tie_tol = tol >= 0.0 ? tol : TIE_TOL_DEFA
 
 size_t walk_warp_scratch_bytes(const wgrt_problem_t& p, int num_sms) {
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
-  return static_cast<size_t>(num_sms) * 32 * rows * JROW * sizeof(double);   // at most 32 single-warp CTAs per SM
+  return static_cast<size_t>(num_sms) * 32 * rows * JROW * sizeof(double);   // at most 32 warps per SM
 }
+
+namespace {
+int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : fallback;
+}
+}  // namespace
 
 cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* work_counter,
                              unsigned long long* counters, int num_sms, double* jones_scratch, RedoList* redo,
@@ -862,58 +1009,72 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   const bool count = (p.flags & WGRT_FLAG_COUNTERS) != 0;
   const bool implicit = p.runner_points > 0;
-  const size_t smem = table_offset() + static_cast<size_t>(rows) * ROW * sizeof(double) +
-                      ((static_cast<size_t>(rows) * sizeof(unsigned short) + 15) & ~size_t(15));
-  auto kern = count ? (implicit ? walk_warp_kernel<true, true> : walk_warp_kernel<true, false>)
-                    : (implicit ? walk_warp_kernel<false, true> : walk_warp_kernel<false, false>);
-  // Function attributes and the occupancy query cost tens of microseconds per call: done once per (device, kernel
-  // variant, table size) -- a launch of a small problem (a pipeline chunk, BASELINE config 1) is otherwise dominated by them.
-  struct Setup { const void* kern; size_t smem; int device, per_sm; };
+  // One CTA per SM; its shared memory holds the geometry's zone tables once and a cell table per warp.  With the
+  // Jones rows in the table (JSM) every per-step access of the walk is a shared-memory access; that form is used
+  // when at least 16 warps of it fit beside the zone tables (up to ~75 event rows, i.e. BASELINE's designs), the
+  // form with the Jones rows in a global scratch otherwise.  WGRT_WALK_JSM / WGRT_WALK_WARPS override (experiments).
+  const size_t max_smem = 227 * 1024;
+  const size_t avail = max_smem - sizeof(CtaShared);
+  static const int env_jsm = env_int("WGRT_WALK_JSM", -1), env_warps = env_int("WGRT_WALK_WARPS", 0);
+  const int jrows = rows - 2 * static_cast<int>(p.n_OC);
+  const int fit_jsm = static_cast<int>(avail / warp_bytes(rows, jrows, true));
+  const bool jsm = env_jsm >= 0 ? env_jsm != 0 : fit_jsm >= 16;
+  int warps = static_cast<int>(avail / warp_bytes(rows, jrows, jsm));
+  if (warps > walk_max_warps(jsm)) warps = walk_max_warps(jsm);
+  if (env_warps > 0 && env_warps < warps) warps = env_warps;
+  if (warps < 1) return cudaErrorInvalidValue;   // more event rows than one warp's table can hold
+  const size_t smem = sizeof(CtaShared) + static_cast<size_t>(warps) * warp_bytes(rows, jrows, jsm);
+  typedef void (*Kern)(const wgrt_problem_t, const RegionSet, int*, const int*, unsigned long long*, double*, RedoList*,
+                       const double);
+  const Kern table[8] = {walk_warp_kernel<false, false, false>, walk_warp_kernel<false, false, true>,
+                         walk_warp_kernel<false, true, false>,  walk_warp_kernel<false, true, true>,
+                         walk_warp_kernel<true, false, false>,  walk_warp_kernel<true, false, true>,
+                         walk_warp_kernel<true, true, false>,   walk_warp_kernel<true, true, true>};
+  const Kern kern = table[(count ? 4 : 0) + (implicit ? 2 : 0) + (jsm ? 1 : 0)];
+  // Function attributes cost tens of microseconds per call: set once per (device, kernel variant, shared-memory size)
+  // -- a launch of a small problem (a pipeline chunk, BASELINE config 1) is otherwise dominated by them.
+  struct Setup { const void* kern; size_t smem; int device; };
   static Setup cache[16];
   static int cached = 0;
   int device = 0;
   cudaError_t err = cudaGetDevice(&device);
   if (err != cudaSuccess) return err;
-  int per_sm = 0;
+  bool known = false;
   for (int i = 0; i < cached; ++i)
-    if (cache[i].kern == reinterpret_cast<const void*>(kern) && cache[i].smem == smem && cache[i].device == device) per_sm = cache[i].per_sm;
-  if (per_sm == 0) {
+    if (cache[i].kern == reinterpret_cast<const void*>(kern) && cache[i].smem == smem && cache[i].device == device) known = true;
+  if (!known) {
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    // Shared memory against L1 (they share the SM's 256 KB, and the split comes in steps: 100 / 132 / 164 / 196 /
-    // 228 KB of shared memory).  This walk lives on L1 hits, so it takes the SMALLEST step that still holds 22 single-warp
-    // CTAs (each costs its bytes + 1 KB of system reserve).  Measured on C2 (4.75 KB per CTA): 132 KB = 23 CTAs, 124 KB
-    // of L1: 8.8 ms; 164 KB = 28 CTAs, 92 KB: 9.15 ms; >= 196 KB = 28 CTAs, <= 60 KB: 9.7 ms; 100 KB = 17 CTAs: 10.1 ms.
-    // WGRT_SMEM_CARVEOUT=<percent> overrides (read once per kernel variant and table size).
+    // Shared memory and L1 share the SM's 256 KB and the split comes in steps (100 / 132 / 164 / 196 / 228 KB of shared
+    // memory): the smallest step that holds the CTA leaves the most L1 (level-2 zone cells, Jones scratch, ray streams).
     int carve = 100;
-    {
-      const size_t per_cta = smem + 1024;
-      const int steps_kb[5] = {100, 132, 164, 196, 228};
-      for (int k = 0; k < 5; ++k)
-        if (static_cast<size_t>(steps_kb[k]) * 1024 / per_cta >= 22) { carve = (steps_kb[k] * 100 + 227) / 228; break; }
-    }
-    if (const char* e = getenv("WGRT_SMEM_CARVEOUT"))
-      if (*e) carve = atoi(e);
+    const int steps_kb[5] = {100, 132, 164, 196, 228};
+    for (int k = 0; k < 5; ++k)
+      if (static_cast<size_t>(steps_kb[k]) * 1024 >= smem + 1024) { carve = (steps_kb[k] * 100 + 227) / 228; break; }
+    carve = env_int("WGRT_SMEM_CARVEOUT", carve);
     err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
     if (err != cudaSuccess) return err;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
-    if (err != cudaSuccess) return err;
-    if (per_sm < 1) per_sm = 1;
-    cache[cached % 16] = Setup{reinterpret_cast<const void*>(kern), smem, device, per_sm};
+    cache[cached % 16] = Setup{reinterpret_cast<const void*>(kern), smem, device};
     if (cached < 16) ++cached;
   }
-  static int cap = -1;
-  if (cap < 0) {
-    const char* e = getenv("WGRT_WARPS_PER_SM");
-    cap = e ? atoi(e) : 0;
-  }
-  if (cap > 0 && per_sm > cap) per_sm = cap;
   const int64_t min_tiles = (p.num_rays + 31) / 32;
-  const int64_t resident = static_cast<int64_t>(num_sms) * per_sm;
-  const int grid = static_cast<int>(resident < min_tiles ? resident : (min_tiles > 1 ? min_tiles : 1));
+  const int64_t want_ctas = (min_tiles + warps - 1) / warps;
+  const int grid = static_cast<int>(want_ctas < num_sms ? (want_ctas > 1 ? want_ctas : 1) : num_sms);
+  const int64_t resident = static_cast<int64_t>(grid) * warps;
   const int64_t tcap = p.num_rays / (4 * resident);
   pick_tile_warp_kernel<<<1, 1024, 0, s>>>(p, tile_size, work_counter, static_cast<int>(tcap > (1 << 20) ? (1 << 20) : tcap), redo);
-  kern<<<grid, 32, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch, redo, g_tie_tol);
+  err = cudaMemcpyToSymbolAsync(c_walk, rs.atlas_dyn, sizeof(AtlasDyn), offsetof(WalkConst, atlas), cudaMemcpyDeviceToDevice, s);
+  if (err != cudaSuccess) return err;
+  err = cudaMemcpyToSymbolAsync(c_walk, rs.zones.dyn, sizeof(ZoneDyn), offsetof(WalkConst, zone), cudaMemcpyDeviceToDevice, s);
+  if (err != cudaSuccess) return err;
+  if (env_int("WGRT_DEBUG_ZONES", 0)) {
+    ZoneDyn zd;
+    cudaStreamSynchronize(s);
+    cudaMemcpy(&zd, rs.zones.dyn, sizeof zd, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[wgrt] zones: num=%d valid=%d outside=%d rows=%d warps=%d jsm=%d smem=%zu\n", zd.num_zones, zd.valid,
+            zd.outside_zone, rows, warps, jsm ? 1 : 0, smem);
+  }
+  kern<<<grid, 32 * warps, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch, redo, g_tie_tol);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   return launch_walk_redo(p, redo, counters, s);   // the near-tie rays, literally (usually none)
