@@ -540,13 +540,41 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
   const double threshold = p.threshold;
   const bool has_l = p.lmd_num != nullptr;
 
+  // A tile keeps a warp busy for ~1 ms, and a launch is only ~6 tiles per warp: handing out whole tiles to the end
+  // would leave the SMs half empty for half a tile (measured: 8 % of the warp slots).  The last half tile per warp is
+  // therefore handed out in TAIL_SPLIT pieces (work units past `big_tiles` address piece q % TAIL_SPLIT of tile
+  // big_tiles + q / TAIL_SPLIT).  Pieces pay the table build and the end-of-tile drain again, so more or smaller
+  // pieces lose (C2: 4 pieces of the last 0.5 / 1 / 1.5 tiles 7.79 / 7.85 / 7.87 ms, 8 of 1.5: 7.96, 16 of 2: 8.96,
+  // none: 8.34 ms).
+#ifndef WGRT_TAIL_SPLIT
+#define WGRT_TAIL_SPLIT 4
+#endif
+#ifndef WGRT_TAIL_HALVES
+#define WGRT_TAIL_HALVES 1
+#endif
+  constexpr int TAIL_SPLIT = WGRT_TAIL_SPLIT;
+  const int64_t resident = static_cast<int64_t>(gridDim.x) * warps;
+  const int64_t split_tiles = tile_size >= 2048 ? min(num_tiles, (WGRT_TAIL_HALVES * resident) / 2) : 0;
+  const int64_t big_tiles = num_tiles - split_tiles;
+  const int64_t piece = (((tile_size + TAIL_SPLIT - 1) / TAIL_SPLIT) + 31) & ~int64_t(31);
+  const int64_t work_units = big_tiles + TAIL_SPLIT * split_tiles;
+
   for (;;) {
-    int tile_i = 0;
-    if (lane == 0) tile_i = atomicAdd(work_counter, 1);
-    const int64_t tile = __shfl_sync(FULL_MASK, tile_i, 0);
-    if (tile >= num_tiles) break;
-    const int64_t t_begin = tile * tile_size;
-    const int64_t t_end = min(p.num_rays, t_begin + tile_size);
+    int unit_i = 0;
+    if (lane == 0) unit_i = atomicAdd(work_counter, 1);
+    const int64_t unit = __shfl_sync(FULL_MASK, unit_i, 0);
+    if (unit >= work_units) break;
+    int64_t t_begin, t_end;
+    if (unit < big_tiles) {
+      t_begin = unit * tile_size;
+      t_end = min(p.num_rays, t_begin + tile_size);
+    } else {
+      const int64_t q = unit - big_tiles;
+      const int64_t base = (big_tiles + q / TAIL_SPLIT) * tile_size;
+      t_begin = base + (q % TAIL_SPLIT) * piece;
+      t_end = min(min(p.num_rays, base + tile_size), t_begin + piece);
+      if (t_begin >= t_end) continue;
+    }
     int64_t cursor = t_begin;   // first ray of the tile nobody has staged yet
 
     while (cursor < t_end) {
@@ -931,8 +959,11 @@ __global__ void __launch_bounds__(1024) pick_tile_warp_kernel(const __grid_const
     // a warp walks a tile alone.  Whole runs when they fit; long runs in equal pieces; short runs
     // grouped.  `tile_cap` = rays of the launch / (4 x resident warps): small launches (pipeline
     // chunks, multi-GPU shards) cut their cells into pieces so that every resident warp gets several
-    // tiles, but never below ~1250 rays (the drain at the end of a tile is paid per tile)
-    const int64_t t_max = tile_cap < 1250 ? 1250 : (tile_cap > 8192 ? 8192 : tile_cap);
+    // tiles, but not below ~1250 rays (the drain at the end of a tile is paid per tile) -- unless the launch is so
+    // small that 1250-ray tiles would leave resident warps without any (then: one tile per warp, at least 128 rays)
+    const int64_t per_warp = 4 * static_cast<int64_t>(tile_cap);
+    const int64_t floor_t = per_warp >= 1250 ? 1250 : (per_warp < 128 ? 128 : per_warp);
+    const int64_t t_max = tile_cap < floor_t ? floor_t : (tile_cap > 8192 ? 8192 : tile_cap);
     const int64_t t_min = t_max / 2;
     int64_t t;
     if (run > t_max) {
