@@ -1,26 +1,37 @@
-// wgrt_walk.cu -- the production ray walk for sm_100a: one warp = one CTA = one cell at a time.
+// wgrt_walk.cu -- the production ray walk for sm_100a: one persistent CTA per SM, 24 independent warps in it, one
+// warp = one cell at a time, every per-step access in shared memory.
 //
 // Same Monte-Carlo walk as process_rays_kernel_pro_fullColor (GRTF:833-1246), organised so that a
 // warp instruction almost always does useful work in almost every lane:
 //
-//  * A persistent single-warp CTA claims tiles of consecutive rays (whole FoV-wavelength cells when
-//    the rays arrive cell by cell, gpu_ray_tracing_pro_fullColor.py:82-115) and walks them alone.
-//    No block barriers, no cross-warp queues; the end-of-cell drain (lanes idling while the longest
-//    paths finish) is paid once per ~5000 rays per warp instead of once per ~1250.
-//  * In-coupling decisions are taken 32 rays at a time with every lane busy (coalesced loads, cut where
-//    the cell key changes: run detection costs nothing extra); the ~72 % of rays absorbed there never
-//    reach the walk.  Survivors wait on a per-warp shared-memory stack (raw ray, RNG state, chosen
-//    order) until a lane is free.
+//  * A warp claims tiles of consecutive rays (whole FoV-wavelength cells when the rays arrive cell by cell,
+//    gpu_ray_tracing_pro_fullColor.py:82-115) and walks them alone.  The warps of a CTA meet once, at the barrier
+//    behind the cooperative load of the geometry's zone tables; after it there are no block barriers and no
+//    cross-warp queues.  The end-of-cell drain (lanes idling while the longest paths finish) is paid once per
+//    ~5000 rays per warp; the last half tile per warp is handed out in quarters so that the SMs do not run half
+//    empty while the last whole tiles finish.
+//  * Shared memory of the CTA (227 KB): the zone tables of the geometry once (level-1 grid as 8-bit ids 16 KB,
+//    transition table 4 KB) and, per warp, the cell's event table (48-byte rows: quadratic form, 1 / cos, meta),
+//    the Jones matrices of its orders (64-byte rows, XOR-swizzled), the per-cell constants and the survivor stack:
+//    8.6 KB per warp for BASELINE's designs (70 event rows), i.e. 24 warps.  The descriptors of the region index
+//    (grid origins / pitches, zone count) sit in constant memory.  What is left in global memory per step: the
+//    level-2 zone cell under MIXED level-1 cells (14 % of the lookups), the ray streams of the in-coupling batches,
+//    RNG states and bins.  Designs whose tables do not fit keep the Jones rows in a per-warp global scratch (JSM
+//    off) and / or read zone ids and transitions from global memory; same code, template / uniform branches.
+//  * In-coupling decisions are taken 32 rays at a time with every lane busy (coalesced loads issued together, the
+//    next batch prefetched into L1, cut where the cell key changes: run detection costs nothing extra); the ~72 %
+//    of rays absorbed there never reach the walk.  Survivors wait on a per-warp shared-memory stack (raw ray, RNG
+//    state, chosen order) until a lane is free.
 //  * A step = refill, phase B, phase A.  Phase B ("diffract"): lanes that stand on a grating draw,
 //    evaluate the efficiencies of ALL orders at once from per-cell quadratic forms (4 FMAs per order
 //    instead of a Jones application per order in a divergent if-chain) and pick the order exactly as
 //    the reference's if/elif chain does; after a __syncwarp() ONE copy of the order application runs
 //    for all of them and for the lanes that just popped a survivor -- one Jones matrix, the chosen
 //    one.  Phase A ("go to the next grating"): every lane whose ray moved looks up its ZONE (wgrt_device.cuh:
-//    one L1-resident 16-bit id per cell names the combination of in-coupler / effective region 1 / 2 / fold
-//    slice / out-coupler slice answers there) and the TRANSITION-TABLE entry of (region state, zone): next
-//    state, lost, the event's first table row, or the free bounce (GRTF:1049-1052, 1102-1108, 1175-1178) after
-//    which it asks again in the next step.
+//    one id per cell names the combination of in-coupler / effective region 1 / 2 / fold slice / out-coupler
+//    slice answers there) and the TRANSITION-TABLE entry of (region state, zone): next state, lost, the event's
+//    first table row, or the free bounce (GRTF:1049-1052, 1102-1108, 1175-1178) after which it asks again in the
+//    next step.
 //  * The polarisation state is the un-normalised complex Jones vector (te, tm) plus s = 1/|v|^2.
 //    E_field_cal's cos / sin / hypot / atan2 / wrap (GRTF:136-150) and the per-event normalisation
 //    (GRTF:876-877 ff.) disappear: efficiencies are v^H M v * s with M = J^H J precomputed per cell
@@ -33,7 +44,10 @@
 //    walk_redo_kernel (wgrt_strict.cu) walks it from its start with the reference's literal
 //    expressions right after this kernel.  Expected: ~0.3 such rays per 112.5 M-ray launch; their
 //    number is reported (WGRT_CNT_NEAR_TIE).
-//  * Everything state dependent is table driven from shared memory (per-cell event rows, sinfo).
+//  * What bounds it (ncu, profiles/r2_walk_warp_ncu_summary.txt): issue slots 62 % busy at 6 warps per scheduler,
+//    each warp issuing every ~9 cycles (fixed-latency dependencies 2.7, shared-memory latency 1.1, branches 1.0,
+//    the remaining global loads 1.7); 18 of 32 lanes active per instruction (lanes between gratings skip phase B,
+//    single-lane literal polygon tests near edges take 15 % of the instructions).
 #include <climits>
 #include <cstdio>
 #include <cstring>
@@ -61,11 +75,6 @@ constexpr int ST_DEAD = -1, ST_PEND_FWD = 6, ST_PEND_BACK = 7;
 // |u - cumulative efficiency| below this: the ray is re-walked literally (see the file header)
 constexpr double TIE_TOL_DEFAULT = 1e-10;
 double g_tie_tol = TIE_TOL_DEFAULT;   // wgrt_debug_set_tie_tolerance (tests widen it to exercise the redo path)
-// Resident single-warp CTAs per SM the kernel is compiled for.  Measured on C2: 32 (64 registers, a few
-// spills) 11.14 ms, 28 (72 registers, no spills) 10.8 ms, 24 (80 registers) 11.1 ms.
-#ifndef WGRT_WARP_CTAS_PER_SM
-#define WGRT_WARP_CTAS_PER_SM 28
-#endif
 enum { POST_NONE = 0, POST_IC_FWD = 1, POST_IC_BACK = 2, POST_DEPOSIT = 3 };
 enum { EV_INIT = 0, EV_S0, EV_S1, EV_S2, EV_S3, EV_S4, EV_S5, NUM_EV };
 enum { DIR_IC1 = 0, DIR_IC2, DIR_IC3, DIR_FC1, DIR_FC2, DIR_OC1, DIR_OC2 };

@@ -121,7 +121,8 @@ def test_empty_and_invalid_inputs(oracle):
 def test_tile_size_and_launch_split_invariance():
     scene = si.make_scene(5, 4, 500, seed=44)
     base = run_engine(KERNEL, scene)
-    for tile in (32, 97, 1000, 100000):
+    # (tiles of 2048 rays and more: the last tiles of a launch are handed out in quarters, wgrt_walk.cu TAIL_SPLIT)
+    for tile in (32, 97, 1000, 2048, 2500, 4099, 100000):
         assert_same(run_engine(KERNEL.configured(tile_hint=tile), scene), base, f"tile={tile}")
     # two half launches == one launch (per-ray RNG, additive bins)
     N = scene.rays.num_rays

@@ -19,16 +19,16 @@ for r in rows:
 tot = sum(a[1] for a in agg.values())
 out = ["ncu --metrics gpu__time_duration.sum --clock-control none -c 400: python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-reference-gpu --no-partitioned --no-legacy",
        "(per-launch times under ncu are serialised and cold-cache; what must agree with bench.py is the SHARE of the step.",
-       " One step of bench.py = 17 launches: region_hash, bbox, rowmask, coarse, fine, atlas, atlas2, zone_reset, zone_level1, zone_collect2,",
-       " zone_number, zone_write1, zone_write2, zone_trans (all no-ops after the first launch of a geometry), pick_tile_warp, walk_warp<0,0>,",
-       " walk_redo (the near-tie rays; usually none).  walk_strict<1> / walk_warp<1,0> / fma_peak are the counter replay and the roofline",
+       " One step of bench.py = 17 kernel launches (+ two 32-byte device-to-device copies into constant memory): region_hash, bbox, rowmask, coarse, fine, atlas, atlas2, zone_reset, zone_level1, zone_collect2,",
+       " zone_number, zone_write1, zone_write2, zone_trans (all no-ops after the first launch of a geometry), pick_tile_warp, walk_warp<0,0,1>,",
+       " walk_redo (the near-tie rays; usually none).  walk_strict<1> / walk_warp<1,0,1> / fma_peak are the counter replay and the roofline",
        " probes, outside the timed region.)",
        f"{'kernel':45s} {'launches':>8s} {'total ms':>10s} {'share':>7s} {'avg ms':>9s}"]
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k[:45]:45s} {n:8d} {t / 1e6:10.3f} {t / tot * 100:6.2f}% {t / n / 1e6:9.4f}")
 import statistics
 step = sum(statistics.median(each[k]) for k in each if k.startswith(("region_", "zone_", "pick_tile", "walk_redo")))
-walk = statistics.median(each["walk_warp_kernel<0, 0>"])
+walk = statistics.median(next(v for k, v in each.items() if k.startswith("walk_warp_kernel<0, 0")))
 first = sum(each[k][0] for k in each if k.startswith(("region_", "zone_")))
 out.append(f"per step (median launch of each kernel): walk_warp {walk / 1e6:.3f} ms of {(walk + step) / 1e6:.3f} ms = "
            f"{walk / (walk + step) * 100:.2f} % (bench.py: {line['ms_per_step']:.2f} ms per step); "
