@@ -785,7 +785,7 @@ def main():
         line["cpu_baseline"] = {"value": c1["bounces"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": desc, "seconds": dt, "rays_per_s": c1["rays"] / dt}
 
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_legacy:   # (the sub-records that are no part of the step)
         line["small_launch"] = small_launch_record(stream)
     if rank == 0 and world == 1 and not args.no_legacy:
         line["legacy_split_tracer"] = legacy_record(args)

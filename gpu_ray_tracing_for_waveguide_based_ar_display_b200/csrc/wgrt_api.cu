@@ -424,8 +424,11 @@ int host_chunk_target(int64_t num_rays, int num_iter) {
   // enough chunks to hide the transfers of the first and last one, few enough that a chunk still
   // fills the GPU: measured on C2 (B200, warp walk) for num_iter = 1: 8 chunks 19.3 ms, 16: 18.7,
   // 25: 18.2; for num_iter = 4: 4 chunks 41.2 ms, 8: 37.9, 12: 37.4, 16: 38.1, 25: 43.1
+  // The walk kernel fills every SM with one CTA, so the launches of the two walk streams do not overlap and every
+  // chunk launch ends in a tail of half-empty SMs: a long job, whose time is the walk's, wants few, large chunks
+  // (num_iter = 10: 3 chunks 91 ms, 6: 94, 12: 99; num_iter = 4: 3 to 12 chunks 41 - 42 ms; num_iter = 2: 12: 23.0).
   const int64_t by_size = num_rays / 4500000;
-  const int64_t cap = num_iter > 1 ? 12 : 25;
+  const int64_t cap = num_iter >= 8 ? 3 : num_iter >= 3 ? 6 : num_iter == 2 ? 12 : 25;
   return static_cast<int>(by_size < 1 ? 1 : (by_size > cap ? cap : by_size));
 }
 

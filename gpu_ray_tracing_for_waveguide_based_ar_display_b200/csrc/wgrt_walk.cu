@@ -563,7 +563,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
 #endif
   constexpr int TAIL_SPLIT = WGRT_TAIL_SPLIT;
   const int64_t resident = static_cast<int64_t>(gridDim.x) * warps;
-  const int64_t split_tiles = tile_size >= 2048 ? min(num_tiles, (WGRT_TAIL_HALVES * resident) / 2) : 0;
+  const int64_t split_tiles = tile_size >= 1024 ? min(num_tiles, (WGRT_TAIL_HALVES * resident) / 2) : 0;
   const int64_t big_tiles = num_tiles - split_tiles;
   const int64_t piece = (((tile_size + TAIL_SPLIT - 1) / TAIL_SPLIT) + 31) & ~int64_t(31);
   const int64_t work_units = big_tiles + TAIL_SPLIT * split_tiles;
