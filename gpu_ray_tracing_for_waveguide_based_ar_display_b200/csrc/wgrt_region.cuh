@@ -128,6 +128,36 @@ __device__ __forceinline__ int region_locate(const Region& r, double x, double y
   return code == CELL_NONE ? -1 : code;
 }
 
+// region_locate for callers that expect the fine level to decide (the walk's rare path: the atlas already said
+// "an edge is near"): the coarse byte, the fine byte and the detail word are requested together instead of one
+// after the other -- `cells` and `detail` are allocated for every fine cell, only meaningful under MIXED coarse
+// cells, and only used there.  Same answers as region_locate.
+template <bool COUNT>
+__device__ __forceinline__ int region_locate_eager(const Region& r, double x, double y, Counts* cn) {
+  if (COUNT) cn->c[WGRT_CNT_POLY_TESTS]++;
+  const double fx = (x - r.x0) * r.inv_dx;
+  const double fy = (y - r.y0) * r.inv_dy;
+  const double lim = static_cast<double>(r.n);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < lim && fy < lim)) return -1;
+  const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
+  const int cell = iy * r.n + ix;
+  const uint8_t coarse = __ldg(r.coarse + (iy >> r.shift) * r.nc + (ix >> r.shift));
+  const uint8_t fine = __ldg(r.cells + cell);
+  const uint32_t d = __ldg(r.detail + cell);
+  const uint32_t mask0 = __ldg(r.rowmask + static_cast<size_t>(iy) * r.words);   // (warms the line the scan reads)
+  if (coarse != CELL_AMBIG) return coarse == CELL_NONE ? -1 : coarse;
+  if (fine != CELL_AMBIG) return fine == CELL_NONE ? -1 : fine;
+  if (COUNT) cn->c[WGRT_CNT_EXACT_FALLBACK]++;
+  (void)mask0;
+  const int first = d & 0xff, stop = (d >> 8) & 0xff, dflt = (d >> 16) & 0xff;
+  const uint32_t* mask = r.rowmask + static_cast<size_t>(iy) * r.words;
+  for (int k = first; k < stop; ++k) {
+    const int s = ring_begin(r.offsets, r.nverts, k), e = ring_begin(r.offsets, r.nverts, k + 1);
+    if (ring_test_masked<COUNT>(x, y, r.verts, s, e, mask, cn)) return k;
+  }
+  return dflt == 255 ? -1 : dflt;
+}
+
 // Several region queries for the same point, with the memory accesses of all of them in flight
 // together: first every coarse byte, then every needed fine byte, then (rarely) the exact scans.
 // `want[k]` switches query k off (result -1).  Same answers as N calls of region_locate.
@@ -243,16 +273,24 @@ __device__ __forceinline__ int atlas_hit(uint32_t word, int shift, const Region&
 template <bool COUNT>
 __device__ __noinline__ uint32_t atlas_resolve(uint32_t word, uint32_t need, const Region* __restrict__ regions, double x,
                                                double y, Counts* cn) {
-#pragma unroll 1
-  for (int r = 0; r < NUM_REGIONS; ++r) {
-    if (!((need >> r) & 1u)) continue;
+  // fields that are needed AND still MIXED (usually exactly one)
+  uint32_t todo = need & ((((word >> ATLAS_SHIFT_IC) & 3u) == 2u ? 1u << REG_IC : 0u) |
+                          (((word >> ATLAS_SHIFT_R1) & 3u) == 2u ? 1u << REG_R1 : 0u) |
+                          (((word >> ATLAS_SHIFT_R2) & 3u) == 2u ? 1u << REG_R2 : 0u) |
+                          (((word >> ATLAS_SHIFT_FC) & 0xffu) == CELL_AMBIG ? 1u << REG_FC : 0u) |
+                          (((word >> ATLAS_SHIFT_OC) & 0xffu) == CELL_AMBIG ? 1u << REG_OC : 0u));
+  // field position of set r: REG_IC 0, REG_R1 2, REG_R2 4, REG_FC 8, REG_OC 16, one byte each in a constant
+  constexpr unsigned long long kShifts =
+      (static_cast<unsigned long long>(ATLAS_SHIFT_IC) << (8 * REG_IC)) | (static_cast<unsigned long long>(ATLAS_SHIFT_R1) << (8 * REG_R1)) |
+      (static_cast<unsigned long long>(ATLAS_SHIFT_R2) << (8 * REG_R2)) | (static_cast<unsigned long long>(ATLAS_SHIFT_FC) << (8 * REG_FC)) |
+      (static_cast<unsigned long long>(ATLAS_SHIFT_OC) << (8 * REG_OC));
+  while (todo) {
+    const int r = __ffs(todo) - 1;
+    todo &= todo - 1;
     const bool multi = r == REG_FC || r == REG_OC;
-    const int shift = r == REG_IC ? ATLAS_SHIFT_IC : r == REG_R1 ? ATLAS_SHIFT_R1 : r == REG_R2 ? ATLAS_SHIFT_R2
-                    : r == REG_FC ? ATLAS_SHIFT_FC : ATLAS_SHIFT_OC;
+    const int shift = static_cast<int>((kShifts >> (8 * r)) & 0xffu);
     const uint32_t mask = multi ? 0xffu : 3u;
-    const uint32_t f = (word >> shift) & mask;
-    if (f != (multi ? static_cast<uint32_t>(CELL_AMBIG) : 2u)) continue;
-    const int hit = region_locate<COUNT>(regions[r], x, y, cn);
+    const int hit = region_locate_eager<COUNT>(regions[r], x, y, cn);
     const uint32_t v = multi ? (hit < 0 ? static_cast<uint32_t>(CELL_NONE) : static_cast<uint32_t>(hit)) : (hit >= 0 ? 1u : 0u);
     word = (word & ~(mask << shift)) | (v << shift);
   }
