@@ -78,6 +78,21 @@ def test_deep_walks_against_oracle(oracle):
     assert want[0].sum() > 50
 
 
+def test_many_slices_take_the_fallback_layouts(oracle):
+    """The walk keeps a cell's Jones rows in shared memory when 16 warps of them fit (up to ~105 event rows) and the zone
+    tables of designs with up to 254 / 128 zones.  Designs beyond that -- 25 fold slices + 12 out-coupler slices: 178
+    rows, Jones rows in the global scratch; 60 + 20 slices: 138 zones, transition table in global memory; 160 + 40
+    slices: 886 rows, 4 warps per SM, more than 254 zones: zone ids from global memory as well -- run
+    the same code on the fallback layouts and must give the same bins and RNG states."""
+    eff = dict(incouple=0.9, ic_zero=0.9, fc_zero=0.7, fc_turn=0.2, oc_zero=0.8, outcouple=0.1)
+    for nfc, noc in ((25, 12), (60, 20), (160, 40)):
+        scene = si.make_scene(4, 3, 500, seed=90 + nfc, design=WaveguideDesign(num_FC=nfc, num_OC=noc), eff=eff)
+        assert len(scene.geom["FC_offset"]) - 1 == nfc and len(scene.geom["OC_offset"]) - 1 == noc
+        want = run_oracle(oracle, scene, 2)
+        assert_same(run_engine(KERNEL, scene, 2), want, f"fast/{nfc}+{noc} slices")
+        assert want[0].sum() > 0
+
+
 def test_fine_eyebox_grid(oracle):
     """BASELINE config 4: high-resolution bins."""
     scene = si.make_scene(3, 3, 800, eb=(320, 480), seed=12,
