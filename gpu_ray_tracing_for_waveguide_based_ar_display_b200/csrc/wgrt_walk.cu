@@ -279,9 +279,22 @@ struct alignas(16) CellConst {
   double range[4];  // eff_reg_FOV_range[m, n, :]
   double box[4];    // xmin, xmax, ymin, ymax of the eyebox rectangle when it is axis aligned
   double inv_cos_in;
+  double bin_dx, bin_dy;   // (xmax - xmin) / EBx, (ymax - ymin) / EBy of the cell's eyebox range (GRTF:154-157)
+  long long bin_base;      // flat index of bin (0, 0) of cell (lm, n, m) in matrix_EB
   int box_ok;       // rect is exactly the axis-aligned rectangle `box` in the runner's vertex order
   int pad_;
 };
+
+// deposit_bin (wgrt_device.cuh, GRTF:154-165) with the per-cell quotients and the cell's base index taken from the
+// table: the same operations on the same operands, evaluated once per cell instead of once per deposit.
+__device__ __forceinline__ void deposit_bin_cell(const wgrt_problem_t& p, const CellConst& cc, double x, double y) {
+  const int64_t ix = static_cast<int64_t>(floor((x - cc.range[0]) / cc.bin_dx));
+  const int64_t iy = static_cast<int64_t>(floor((y - cc.range[2]) / cc.bin_dy));
+  const int64_t flat = cc.bin_base + iy * p.EBx + ix;
+  const int64_t total = p.L * p.Y * p.X * p.EBy * p.EBx;
+  WGRT_CHECK(ix >= 0 && ix <= p.EBx && iy >= 0 && iy <= p.EBy);
+  if (flat >= 0 && flat < total) atomicAdd(p.matrix_EB + flat, 1.0f);
+}
 
 // Rays whose in-coupling draw picked an order wait here (a per-warp stack) for a free lane: the raw
 // ray as loaded, its index, its RNG state after the draw, the order (bit 31 of idx) and the order's
@@ -419,6 +432,11 @@ __device__ void build_cell_tables(const wgrt_problem_t& p, int64_t lm, int64_t m
     cc.inv_cos_in = 1.0 / cos(__ldg(p.lut_ic1 + 2 * cell * p.C_ic));
   } else if (t == 26) {
     eyebox_box(p.eff_reg_FOV + 8 * (m * p.Y + n), cc);
+  } else if (t == 27) {
+    const double* rg = p.eff_reg_FOV_range + 4 * (m * p.Y + n);
+    cc.bin_dx = (__ldg(rg + 1) - __ldg(rg + 0)) / static_cast<double>(p.EBx);
+    cc.bin_dy = (__ldg(rg + 3) - __ldg(rg + 2)) / static_cast<double>(p.EBy);
+    cc.bin_base = ((lm * p.Y + n) * p.X + m) * p.EBy * p.EBx;
   }
 }
 
@@ -498,7 +516,9 @@ __global__ void __launch_bounds__(32 * walk_max_warps(JSM), 1)
 walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
                  int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
                  unsigned long long* counters, double* __restrict__ jones_scratch, RedoList* __restrict__ redo,
-                 const double TIE_TOL) {
+                 const double TIE_TOL, const int warp_stride, const int jones_off) {
+  // (warp_stride = warp_bytes(rows, jrows, JSM), jones_off = rows * ROW: launch constants, so that the step loop
+  // re-derives neither from the slice counts)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int rows = 6 + 4 * static_cast<int>(p.n_FC) + 6 * static_cast<int>(p.n_OC);
   const int jrows = rows - 2 * static_cast<int>(p.n_OC);
@@ -533,10 +553,10 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
   }
   __syncthreads();   // the only block barrier: from here on the warps never meet again
 
-  unsigned char* wbase = smem_raw + sizeof(CtaShared) + static_cast<size_t>(warp) * warp_bytes(rows, jrows, JSM);
+  unsigned char* wbase = smem_raw + sizeof(CtaShared) + static_cast<size_t>(warp) * warp_stride;
   WarpShared& sh = *reinterpret_cast<WarpShared*>(wbase);
   double* tab = reinterpret_cast<double*>(wbase + table_offset());
-  const double* jones_sm = tab + rows * ROW;
+  const double* jones_sm = tab + jones_off;
   Counts cn;
   if (COUNT) cn.clear();
 
@@ -837,7 +857,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             if (post == POST_DEPOSIT) {
               // GRTF:1162-1171: count the ray if it leaves inside this FoV's eyebox rectangle
               if (deposit_inside<COUNT>(cc, r.x, r.y, &cn)) {
-                deposit_bin(p, lm, m, n, r.x, r.y, cc.range[0], cc.range[1], cc.range[2], cc.range[3]);
+                deposit_bin_cell(p, cc, r.x, r.y);
                 if (COUNT) cn.c[WGRT_CNT_DEPOSITS]++;
               }
               lost = true;
@@ -1065,7 +1085,7 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   if (warps < 1) return cudaErrorInvalidValue;   // more event rows than one warp's table can hold
   const size_t smem = sizeof(CtaShared) + static_cast<size_t>(warps) * warp_bytes(rows, jrows, jsm);
   typedef void (*Kern)(const wgrt_problem_t, const RegionSet, int*, const int*, unsigned long long*, double*, RedoList*,
-                       const double);
+                       const double, const int, const int);
   const Kern table[8] = {walk_warp_kernel<false, false, false>, walk_warp_kernel<false, false, true>,
                          walk_warp_kernel<false, true, false>,  walk_warp_kernel<false, true, true>,
                          walk_warp_kernel<true, false, false>,  walk_warp_kernel<true, false, true>,
@@ -1114,7 +1134,8 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
     fprintf(stderr, "[wgrt] zones: num=%d valid=%d outside=%d rows=%d warps=%d jsm=%d smem=%zu\n", zd.num_zones, zd.valid,
             zd.outside_zone, rows, warps, jsm ? 1 : 0, smem);
   }
-  kern<<<grid, 32 * warps, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch, redo, g_tie_tol);
+  kern<<<grid, 32 * warps, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch, redo, g_tie_tol,
+                                      static_cast<int>(warp_bytes(rows, jrows, jsm)), rows * ROW);
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   return launch_walk_redo(p, redo, counters, s);   // the near-tie rays, literally (usually none)
