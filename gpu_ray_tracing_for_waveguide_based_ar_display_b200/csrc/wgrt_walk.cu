@@ -491,12 +491,16 @@ __global__ void deposit_inside_kernel(const double* __restrict__ rect, const dou
   if (!literal && cc.box_ok) out[i] |= 2;   // bit 1: the shortcut was armed for this rectangle
 }
 
+// floor(log2(v)) of a positive normal double (a zero or subnormal gives -1023: "deep in the underflow range")
+__device__ __forceinline__ int binary_exponent(double v) { return ((__double2hiint(v) >> 20) & 0x7ff) - 1023; }
+
 struct Ray {
   double x, y;      // position
   cplx te, tm;      // Jones vector, not normalised
   double s;         // 1 / (|te|^2 + |tm|^2)
   double inv_cos;   // 1 / cos(theta_current.real)
-  double ener;
+  double ener;      // energy left (threshold > 0 launches)
+  int esum;         // THR0 launches: sum of the binary exponents of the efficiencies taken so far (ener >= 2^esum)
   uint32_t rng;
   int state;        // region state 0..5, ST_PEND_* after an in-coupler order, ST_DEAD
   int iter;
@@ -511,12 +515,17 @@ struct Ray {
 #endif
 __host__ __device__ constexpr int walk_max_warps(bool jsm) { return jsm ? WGRT_JSM_WARPS : 24; }
 
-template <bool COUNT, bool IMPLICIT, bool JSM>
+// THR0: the launch's energy threshold is 0 (process_rays_kernel_pro_fullColor, GRTF:859).  The gates `ener_k =
+// ener * efficiency_k > 0` (GRTF:1017 ff.) then only ask whether the product is positive, i.e. whether the efficiency
+// is and nothing underflowed: the walk tracks the binary exponents of the efficiencies taken instead of their product
+// (one register and four multiplies per event less, no efficiency to re-evaluate when a survivor is popped), and a ray
+// whose exponent sum nears the underflow range -- hundreds of events deep -- goes to the literal walk like a near tie.
+template <bool COUNT, bool IMPLICIT, bool JSM, bool THR0>
 __global__ void __launch_bounds__(32 * walk_max_warps(JSM), 1)
 walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant__ RegionSet rs,
                  int* __restrict__ work_counter, const int* __restrict__ tile_size_ptr,
                  unsigned long long* counters, double* __restrict__ jones_scratch, RedoList* __restrict__ redo,
-                 const double TIE_TOL, const int warp_stride, const int jones_off) {
+                 const double TIE_TOL, const int warp_stride, const int jones_off, const int esum_limit) {
   // (warp_stride = warp_bytes(rows, jrows, JSM), jones_off = rows * ROW: launch constants, so that the step loop
   // re-derives neither from the slice counts)
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -704,6 +713,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           const int cnt = okmask == FULL_MASK ? 32 : __ffs(~okmask) - 1;   // leading rays of this run
           if (cnt < 32) open = false;
           int k = -1;
+          int ex0 = 0;   // THR0: binary exponent of the chosen in-coupling efficiency
           if (lane < cnt && valid) {   // (rays of a run whose cell indices are out of range are left untouched)
             if (COUNT) {
               cn.c[WGRT_CNT_RAYS]++; cn.c[WGRT_CNT_DRAWS]++; cn.c[WGRT_CNT_DRAW2]++; cn.c[WGRT_CNT_EFIELD] += 2;
@@ -725,8 +735,8 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             const double e2 = incouple_eff(b0, b1, t2, m2, zre, zim, g);
             if ((fabs(u - e1) < TIE_TOL || fabs(u - (e1 + e2)) < TIE_TOL) && redo_push(redo, i)) {
               // near tie: left untouched for the literal re-walk
-            } else if (u <= e1) k = 0;                          // GRTF:871: no energy gate here
-            else if (u <= e1 + e2) k = 1;                       // GRTF:887
+            } else if (u <= e1) { k = 0; ex0 = binary_exponent(e1); }             // GRTF:871: no energy gate here
+            else if (u <= e1 + e2) { k = 1; ex0 = binary_exponent(e2); }          // GRTF:887
             else st_stream(p.rng_states + i, frng);            // GRTF:903-904: absorbed
           }
           const unsigned surv = __ballot_sync(FULL_MASK, k >= 0);
@@ -736,7 +746,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             uint4* qe = reinterpret_cast<uint4*>(&sh.q[slot]);
             const uint32_t idxk = static_cast<uint32_t>(i - t_begin) | (static_cast<uint32_t>(k) << 31);
             qe[0] = make_uint4(idxk, frng, __float_as_uint(fx), __float_as_uint(fy));
-            qe[1] = make_uint4(__float_as_uint(fte), __float_as_uint(ftm), __float_as_uint(fdl), 0u);
+            qe[1] = make_uint4(__float_as_uint(fte), __float_as_uint(ftm), __float_as_uint(fdl), static_cast<uint32_t>(ex0));
           }
           qn += __popc(surv);
           // (A NaN cell key never compares equal, not even to itself: the run of such a ray would be empty and the
@@ -768,7 +778,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               r.tm = cplx{tm * cs, tm * sn};
             }
             r.row0 = static_cast<int>(q0.x >> 31);   // the chosen in-coupling row (0 or 1)
-            {   // ener = 1 * efficiency of the in-coupled order (GRTF:882), the very value the draw was compared with
+            if (THR0) {
+              r.esum = static_cast<int>(q1.w);
+            } else {   // ener = 1 * efficiency of the in-coupled order (GRTF:882), the very value the draw was compared with
               const double2* q = reinterpret_cast<const double2*>(tab + r.row0 * ROW);
               r.ener = incouple_eff(q[0], q[1], te * te, r.tm.re * r.tm.re + r.tm.im * r.tm.im, te * r.tm.re, te * r.tm.im,
                                     cc.inv_cos_in);
@@ -821,13 +833,18 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
             // the reference's if / elif chain (GRTF:919-953, 1020-1048, 1135-1174)
             // (evaluated without branches: the three tests are cheap, a divergent chain is not)
             const double e12 = e1 + e2;
-            const bool ok1 = u <= e1 && (!gated || r.ener * e1 > threshold);
-            const bool ok2 = u <= e12 && (!gated || r.ener * e2 > threshold);
-            const bool ok3 = three && u <= e12 + e3v && r.ener * e3v > threshold;
+            const bool g1 = THR0 ? e1 > 0.0 : r.ener * e1 > threshold;
+            const bool g2 = THR0 ? e2 > 0.0 : r.ener * e2 > threshold;
+            const bool g3 = THR0 ? e3v > 0.0 : r.ener * e3v > threshold;
+            const bool ok1 = u <= e1 && (!gated || g1);
+            const bool ok2 = u <= e12 && (!gated || g2);
+            const bool ok3 = three && u <= e12 + e3v && g3;
             k = ok1 ? 0 : ok2 ? 1 : ok3 ? 2 : -1;
             esel = ok1 ? e1 : ok2 ? e2 : e3v;
             bool tie = fabs(u - e1) < TIE_TOL || fabs(u - e12) < TIE_TOL || (three && fabs(u - (e12 + e3v)) < TIE_TOL);
-            if (threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
+            if (THR0) {   // positive efficiency <=> positive product, unless the product may have underflowed
+              if (gated && (r.esum < esum_limit || (k >= 0 && esel < 1e-30))) tie = true;
+            } else if (threshold > 0.0 && gated) {   // the energy gates of the single-wavelength twin (GRTF:444)
               const double rt = 1e-9 * threshold;
               tie = tie || fabs(r.ener * e1 - threshold) < rt || fabs(r.ener * e2 - threshold) < rt ||
                     (three && fabs(r.ener * e3v - threshold) < rt);
@@ -892,7 +909,8 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               r.x += cc.gap[2 * gp];
               r.y += cc.gap[2 * gp + 1];
               r.inv_cos = im.x;
-              r.ener *= esel;
+              if (THR0) r.esum += binary_exponent(esel);
+              else r.ener *= esel;
               r.state = (meta >> 4) & 7;   // region state, or "pending" after an in-coupler order
               if (COUNT) cn.c[WGRT_CNT_BOUNCES]++;
             }
@@ -1085,12 +1103,14 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   if (warps < 1) return cudaErrorInvalidValue;   // more event rows than one warp's table can hold
   const size_t smem = sizeof(CtaShared) + static_cast<size_t>(warps) * warp_bytes(rows, jrows, jsm);
   typedef void (*Kern)(const wgrt_problem_t, const RegionSet, int*, const int*, unsigned long long*, double*, RedoList*,
-                       const double, const int, const int);
-  const Kern table[8] = {walk_warp_kernel<false, false, false>, walk_warp_kernel<false, false, true>,
-                         walk_warp_kernel<false, true, false>,  walk_warp_kernel<false, true, true>,
-                         walk_warp_kernel<true, false, false>,  walk_warp_kernel<true, false, true>,
-                         walk_warp_kernel<true, true, false>,   walk_warp_kernel<true, true, true>};
-  const Kern kern = table[(count ? 4 : 0) + (implicit ? 2 : 0) + (jsm ? 1 : 0)];
+                       const double, const int, const int, const int);
+#define WGRT_WALK_ROW(C, I) walk_warp_kernel<C, I, false, false>, walk_warp_kernel<C, I, false, true>, \
+                           walk_warp_kernel<C, I, true, false>, walk_warp_kernel<C, I, true, true>
+  const Kern table[16] = {WGRT_WALK_ROW(false, false), WGRT_WALK_ROW(false, true), WGRT_WALK_ROW(true, false),
+                          WGRT_WALK_ROW(true, true)};
+#undef WGRT_WALK_ROW
+  const bool thr0 = p.threshold == 0.0;
+  const Kern kern = table[(count ? 8 : 0) + (implicit ? 4 : 0) + (jsm ? 2 : 0) + (thr0 ? 1 : 0)];
   // Function attributes cost tens of microseconds per call: set once per (device, kernel variant, shared-memory size)
   // -- a launch of a small problem (a pipeline chunk, BASELINE config 1) is otherwise dominated by them.
   struct Setup { const void* kern; size_t smem; int device; };
@@ -1135,7 +1155,9 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
             zd.outside_zone, rows, warps, jsm ? 1 : 0, smem);
   }
   kern<<<grid, 32 * warps, smem, s>>>(p, rs, work_counter, tile_size, counters, jones_scratch, redo, g_tie_tol,
-                                      static_cast<int>(warp_bytes(rows, jrows, jsm)), rows * ROW);
+                                      static_cast<int>(warp_bytes(rows, jrows, jsm)), rows * ROW,
+                                      g_tie_tol > 1e-6 ? -4 : -900);   // (a widened tie tolerance -- tests -- also
+                                                                       // exercises the underflow guard of THR0)
   err = cudaGetLastError();
   if (err != cudaSuccess) return err;
   return launch_walk_redo(p, redo, counters, s);   // the near-tie rays, literally (usually none)
