@@ -44,9 +44,9 @@
 //    walk_redo_kernel (wgrt_strict.cu) walks it from its start with the reference's literal
 //    expressions right after this kernel.  Expected: ~0.3 such rays per 112.5 M-ray launch; their
 //    number is reported (WGRT_CNT_NEAR_TIE).
-//  * What bounds it (ncu, profiles/r2_walk_warp_ncu_summary.txt): issue slots 62 % busy at 6 warps per scheduler,
-//    each warp issuing every ~9 cycles (fixed-latency dependencies 2.7, shared-memory latency 1.1, branches 1.0,
-//    the remaining global loads 1.7); 18 of 32 lanes active per instruction (lanes between gratings skip phase B,
+//  * What bounds it (ncu, profiles/r2_walk_warp_ncu_summary.txt): issue slots 67 % busy at 6 warps per scheduler,
+//    each warp issuing every ~9 cycles (fixed-latency dependencies 2.6, shared-memory latency 1.0, branches 1.0,
+//    the remaining global loads 1.4); 19 of 32 lanes active per instruction (lanes between gratings skip phase B,
 //    single-lane literal polygon tests near edges take 15 % of the instructions).
 #include <climits>
 #include <cstdio>
