@@ -23,7 +23,7 @@ UNITS = {
     "wgrt_legacy.cu": ["-fmad=false"],
     "wgrt_index.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_ZONE_REFINE",) if k in os.environ],
     "wgrt_eval.cu": [],
-    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_QUEUE_CAP", "WGRT_ZONE_REFINE", "WGRT_PF", "WGRT_JSM_WARPS", "WGRT_TAIL_SPLIT", "WGRT_TAIL_HALVES") if k in os.environ],
+    "wgrt_walk.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_QUEUE_CAP", "WGRT_ZONE_REFINE", "WGRT_JSM_WARPS") if k in os.environ],
     "wgrt_api.cu": [f"-D{k}={os.environ[k]}" for k in ("WGRT_ZONE_REFINE",) if k in os.environ],
 }
 HEADERS = ["wgrt_device.cuh", "wgrt_region.cuh", os.path.join("..", "..", "include", "wgrt.h")]

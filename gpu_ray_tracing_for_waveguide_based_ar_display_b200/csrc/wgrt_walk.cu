@@ -453,9 +453,6 @@ __device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
 __device__ __forceinline__ void st_stream(uint32_t* ptr, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void* ptr) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-}
 __device__ __forceinline__ void prefetch_l1(const void* ptr) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
 }
@@ -584,15 +581,9 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
   // big_tiles + q / TAIL_SPLIT).  Pieces pay the table build and the end-of-tile drain again, so more or smaller
   // pieces lose (C2: 4 pieces of the last 0.5 / 1 / 1.5 tiles 7.79 / 7.85 / 7.87 ms, 8 of 1.5: 7.96, 16 of 2: 8.96,
   // none: 8.34 ms).
-#ifndef WGRT_TAIL_SPLIT
-#define WGRT_TAIL_SPLIT 4
-#endif
-#ifndef WGRT_TAIL_HALVES
-#define WGRT_TAIL_HALVES 1
-#endif
-  constexpr int TAIL_SPLIT = WGRT_TAIL_SPLIT;
+  constexpr int TAIL_SPLIT = 4;
   const int64_t resident = static_cast<int64_t>(gridDim.x) * warps;
-  const int64_t split_tiles = tile_size >= 1024 ? min(num_tiles, (WGRT_TAIL_HALVES * resident) / 2) : 0;
+  const int64_t split_tiles = tile_size >= 1024 ? min(num_tiles, resident / 2) : 0;
   const int64_t big_tiles = num_tiles - split_tiles;
   const int64_t piece = (((tile_size + TAIL_SPLIT - 1) / TAIL_SPLIT) + 31) & ~int64_t(31);
   const int64_t work_units = big_tiles + TAIL_SPLIT * split_tiles;
@@ -673,22 +664,8 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
               frng = ld_stream(p.rng_states + i);
               same = vm == km && vn == kn && vl == kl;
             }
-#ifndef WGRT_PF
-#define WGRT_PF 2
-#endif
-#if WGRT_PF == 0
-            if (i + 64 < run_limit) {   // two batches ahead
-              prefetch_l2(p.rng_states + i + 64);
-              if (!IMPLICIT) {
-                prefetch_l2(p.x + i + 64); prefetch_l2(p.y + i + 64);
-                prefetch_l2(p.te + i + 64); prefetch_l2(p.tm + i + 64); prefetch_l2(p.delta_phase + i + 64);
-                prefetch_l2(p.m + i + 64); prefetch_l2(p.n + i + 64);
-                if (has_l) prefetch_l2(p.lmd_num + i + 64);
-              }
-            }
-#else
-            if (i + 32 < run_limit) {   // the next batch into L1 (translation included)
-              prefetch_l1(p.rng_states + i + 32);
+            if (i + 32 < run_limit) {   // the next batch into L1 (translation included; measured against L2 prefetches
+              prefetch_l1(p.rng_states + i + 32);   // two / three batches ahead: -1 %)
               if (!IMPLICIT) {
                 prefetch_l1(p.x + i + 32); prefetch_l1(p.y + i + 32);
                 prefetch_l1(p.te + i + 32); prefetch_l1(p.tm + i + 32); prefetch_l1(p.delta_phase + i + 32);
@@ -696,18 +673,6 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
                 if (has_l) prefetch_l1(p.lmd_num + i + 32);
               }
             }
-#if WGRT_PF == 1
-            if (i + 96 < run_limit) {
-              prefetch_l2(p.rng_states + i + 96);
-              if (!IMPLICIT) {
-                prefetch_l2(p.x + i + 96); prefetch_l2(p.y + i + 96);
-                prefetch_l2(p.te + i + 96); prefetch_l2(p.tm + i + 96); prefetch_l2(p.delta_phase + i + 96);
-                prefetch_l2(p.m + i + 96); prefetch_l2(p.n + i + 96);
-                if (has_l) prefetch_l2(p.lmd_num + i + 96);
-              }
-            }
-#endif
-#endif
           }
           const unsigned okmask = __ballot_sync(FULL_MASK, same);
           const int cnt = okmask == FULL_MASK ? 32 : __ffs(~okmask) - 1;   // leading rays of this run
