@@ -610,10 +610,12 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
       // ---- the run of rays that share the cell of ray `cursor` ---------------------------------
       float km, kn, kl;
       int64_t run_limit;
+      int64_t cell_first = 0;   // runner layout: index (in the launch) of ray 0 of the run's cell
       const int64_t run_first = cursor;
       if (IMPLICIT) {
         const int64_t rpc = 2 * p.runner_points;
         const int64_t cell = p.runner_first_cell + cursor / rpc;  // runner order: x outer, y, lambda inner
+        cell_first = (cursor / rpc) * rpc;
         kl = static_cast<float>(cell % p.L);
         kn = static_cast<float>((cell / p.L) % p.Y);
         km = static_cast<float>(cell / (p.L * p.Y));
@@ -650,7 +652,7 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
           if (same) {
             if (IMPLICIT) {
               // runner layout (RUN:82-115): P TE rays then P TM rays per cell, ray k starts at point k
-              const int64_t kk = i % (2 * p.runner_points);
+              const int64_t kk = i - cell_first;   // (= i % (2 P): the run lies inside one cell)
               const bool te_half = kk < p.runner_points;
               const int64_t pt = te_half ? kk : kk - p.runner_points;
               fx = __ldg(p.x + pt); fy = __ldg(p.y + pt);
