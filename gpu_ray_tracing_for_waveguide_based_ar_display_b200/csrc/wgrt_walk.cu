@@ -1056,7 +1056,7 @@ cudaError_t launch_walk_warp(const wgrt_problem_t& p, const RegionSet& rs, int* 
   const bool implicit = p.runner_points > 0;
   // One CTA per SM; its shared memory holds the geometry's zone tables once and a cell table per warp.  With the
   // Jones rows in the table (JSM) every per-step access of the walk is a shared-memory access; that form is used
-  // when at least 16 warps of it fit beside the zone tables (up to ~75 event rows, i.e. BASELINE's designs), the
+  // when at least 16 warps of it fit beside the zone tables (up to ~110 event rows: BASELINE's designs have 70), the
   // form with the Jones rows in a global scratch otherwise.  WGRT_WALK_JSM / WGRT_WALK_WARPS override (experiments).
   const size_t max_smem = 227 * 1024;
   const size_t avail = max_smem - sizeof(CtaShared);
