@@ -384,7 +384,7 @@ def partitioned_record(args, nx, ny, rpc, eb, world, rank, local_rank, workload,
                               "per rank H2D of its table columns, walk of its cell range, D2H of its matrix_EB columns; "
                               "one launch per call, pinned host buffers, no collective",
                        "columns_bit_equal_to_device_launch": bool(io[2].item() == world)},
-               "gpu_launches": steps * 10}
+               "gpu_launches": steps * 17}
         if clocks is not None:
             rec["clocks"] = clocks.summary()
     del total
@@ -548,8 +548,9 @@ def main():
         "collective": None if world == 1 else
         ("one NCCL reduce-scatter of the bins as uint8 (exact: every count <= 255 // N), 216 MB per rank in"
          if narrow_exact else "narrow form not exact for these counts: float32 reduce-scatter needed (untimed re-run)"),
-        # per launch: geometry hash, 6 region-index / atlas kernels (no-ops when unchanged), tile pick, walk, near-tie redo
-        "gpu_launches": args.steps * 10 + (3 if world > 1 else 0),
+        # per launch (profiles/r2_launch_shares_final.txt): geometry hash, 6 region-index / atlas kernels and 7 zone-table
+        # kernels (no-ops when the geometry is unchanged), tile pick, walk, near-tie redo = 17 kernels
+        "gpu_launches": args.steps * 17 + (3 if world > 1 else 0),
         "near_tie_rays": cnt["near_tie"],
         "clocks": clocks.summary() if clocks is not None else None,
     }
