@@ -899,11 +899,15 @@ walk_warp_kernel(const __grid_constant__ wgrt_problem_t p, const __grid_constant
         if (r.state != ST_DEAD && r.row0 < 0) {
           uint32_t act = ACT_RESOLVE;
           int z = -1;
-          if (zone_ok) {
+          if (trans_sm) {   // (implies level1_sm: the design's zone tables are in shared memory -- one test on the usual path)
+            z = zone_lookup_walk<true>(cta.level1, nullptr, rs.zones.level2, r.x, r.y);
+            WGRT_CHECK(z >= 0 && z < TRANS_SM && r.state >= 0 && r.state < ZONE_STATES);
+            act = cta.trans[r.state * TRANS_SM + z];
+          } else if (zone_ok) {
             z = level1_sm ? zone_lookup_walk<true>(cta.level1, nullptr, rs.zones.level2, r.x, r.y)
                           : zone_lookup_walk<false>(nullptr, rs.zones.level1, rs.zones.level2, r.x, r.y);
             WGRT_CHECK(z >= 0 && z < ZONE_CAP && r.state >= 0 && r.state < ZONE_STATES);
-            act = trans_sm ? cta.trans[r.state * TRANS_SM + z] : __ldg(rs.zones.trans + r.state * ZONE_CAP + z);
+            act = __ldg(rs.zones.trans + r.state * ZONE_CAP + z);
           }
           // rare: a field this state needs is MIXED in the zone (per-set grids / literal edges decide), or the
           // design has too many zones for the table (word atlas + decode on the fly)
